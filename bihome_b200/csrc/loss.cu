@@ -1,0 +1,326 @@
+// K3: bidirectional perceptual (biHomE) loss, forward and backward fused in ONE pass over the features.
+//
+// Reference semantics: src/heads/PerceptualHead.py:559-561 (l1 = |f1' - f2|, l2 = |f2' - f1|, l3 = |f1 - f2|),
+// :609-665 (double-line, TRIPLET_MARGIN 'inf', channel-agnostic):
+//   W1 = m1'*m2   S1 = sum_hw W1   ln1 = sum_hw W1*(sum_c l1 - sum_c l3) / max(S1, 1)        (same for 2)
+//   ln3 = ||H12 H21 - I||_F^2      loss_b = ln1 + ln2 + mu*ln3
+// and its autograd:
+//   d/df1'   = W1 * sign(f1' - f2) / den1
+//   d/dm1'   = m2 * D1 / den1 - [S1 > 1] * num1 * m2 / den1^2
+//   d/dH12   = 2 mu E H21^T,  d/dH21 = 2 mu H12^T E,  E = H12 H21 - I
+//
+// Work decomposition: one thread-block CLUSTER per sample; the CTAs of a cluster split the h*w pixels and
+// exchange their partial mask sums (before the pass, for den) and numerator sums (after it, for d/dm)
+// through distributed shared memory.  Each feature element is read once and each gradient element written
+// once: 4*C*h*w*4 B in, 2*C*h*w*4 B out per sample -- the compulsory traffic.
+#include <cooperative_groups.h>
+
+#include "bh_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bh {
+
+struct LossArgs {
+    const float *f1, *f2, *f1w, *f2w, *m1, *m2, *m1w, *m2w, *H12, *H21;
+    float mu;
+    float *loss, *parts, *g_f1w, *g_f2w, *g_f1, *g_f2, *g_m1w, *g_m2w, *gH12, *gH21;
+    int B, C, hw;
+    long long sc, sp;  // channel / pixel strides in elements (NCHW: hw, 1; NHWC: 1, C)
+};
+
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float (&r)[V]) {
+    if (V == 4) {
+        const float4 t = ldg_stream(reinterpret_cast<const float4*>(p));
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else {
+        r[0] = __ldg(p);
+    }
+}
+template <int V>
+__device__ __forceinline__ void ldv_cached(const float* p, float (&r)[V]) {
+    if (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else {
+        r[0] = __ldg(p);
+    }
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const float (&r)[V]) {
+    if (V == 4) stg_stream(reinterpret_cast<float4*>(p), make_float4(r[0], r[1], r[2], r[3]));
+    else *p = r[0];
+}
+__device__ __forceinline__ float sgn(float x) { return static_cast<float>(x > 0.0f) - static_cast<float>(x < 0.0f); }
+
+constexpr int kLossThreads = 256;
+constexpr int kLanes = 64;  // pixel-vectors per chunk; kLossThreads / kLanes channel groups
+constexpr int kGroups = kLossThreads / kLanes;
+
+// V = pixels per thread-vector (4: NCHW with hw % 4 == 0; 1: any strides)
+template <int V, bool kInputGrads>
+__global__ void __launch_bounds__(kLossThreads) bihome_kernel(const LossArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = static_cast<int>(cluster.num_blocks());
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int b = blockIdx.x / CL;
+    const int tid = threadIdx.x, lane = tid & (kLanes - 1), grp = tid / kLanes;
+
+    __shared__ float xchg_den[2];
+    __shared__ float xchg_num[2];
+    __shared__ float red[2 * (kLossThreads / 32)];
+    __shared__ float dsm[kGroups][kLanes][2 * V];
+
+    const int nvec = a.hw / V;
+    const int v0 = static_cast<int>(static_cast<long long>(rank) * nvec / CL);
+    const int v1 = static_cast<int>(static_cast<long long>(rank + 1) * nvec / CL);
+    const long long mbase = static_cast<long long>(b) * a.hw;
+    const long long fbase = static_cast<long long>(b) * a.C * a.hw;
+
+    // ---- phase 0: mask sums of the whole sample (den1, den2) via DSMEM -------------------------------
+    float s[2] = {0.0f, 0.0f};
+    for (int pv = v0 + tid; pv < v1; pv += kLossThreads) {
+        float x1[V], x2[V], y1[V], y2[V];
+        ldv_cached<V>(a.m1w + mbase + pv * V, x1);
+        ldv_cached<V>(a.m2w + mbase + pv * V, x2);
+#pragma unroll
+        for (int i = 0; i < V; ++i) y1[i] = y2[i] = 1.0f;
+        if (a.m1) ldv_cached<V>(a.m1 + mbase + pv * V, y1);
+        if (a.m2) ldv_cached<V>(a.m2 + mbase + pv * V, y2);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            s[0] = fmaf(x1[i], y2[i], s[0]);
+            s[1] = fmaf(x2[i], y1[i], s[1]);
+        }
+    }
+    block_sum<2>(s, red);
+    if (tid == 0) { xchg_den[0] = s[0]; xchg_den[1] = s[1]; }
+    cluster.sync();
+    float S1 = 0.0f, S2 = 0.0f;
+    for (int r = 0; r < CL; ++r) {
+        const float* remote = cluster.map_shared_rank(xchg_den, r);
+        S1 += remote[0];
+        S2 += remote[1];
+    }
+    const float inv1 = 1.0f / fmaxf(S1, 1.0f), inv2 = 1.0f / fmaxf(S2, 1.0f);
+
+    // ---- phase 1: the streaming pass ---------------------------------------------------------------
+    float num[2] = {0.0f, 0.0f};
+    for (int cb = v0; cb < v1; cb += kLanes) {
+        const int pv = cb + lane;
+        const bool live = pv < v1;
+        float W1[V], W2[V], d1[V], d2[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) W1[i] = W2[i] = d1[i] = d2[i] = 0.0f;
+        if (live) {
+            float x1[V], x2[V], y1[V], y2[V];
+            ldv_cached<V>(a.m1w + mbase + pv * V, x1);
+            ldv_cached<V>(a.m2w + mbase + pv * V, x2);
+#pragma unroll
+            for (int i = 0; i < V; ++i) y1[i] = y2[i] = 1.0f;
+            if (a.m1) ldv_cached<V>(a.m1 + mbase + pv * V, y1);
+            if (a.m2) ldv_cached<V>(a.m2 + mbase + pv * V, y2);
+#pragma unroll
+            for (int i = 0; i < V; ++i) { W1[i] = x1[i] * y2[i]; W2[i] = x2[i] * y1[i]; }
+            const long long poff = fbase + static_cast<long long>(pv) * V * a.sp;
+#pragma unroll 2
+            for (int c = grp; c < a.C; c += kGroups) {
+                const long long o = poff + c * a.sc;
+                float p1w[V], p2[V], p2w[V], p1[V];
+                ldv<V>(a.f1w + o, p1w);
+                ldv<V>(a.f2 + o, p2);
+                ldv<V>(a.f2w + o, p2w);
+                ldv<V>(a.f1 + o, p1);
+                float ga[V], gb[V], gc[V], gd[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float e1 = p1w[i] - p2[i], e2 = p2w[i] - p1[i], e3 = p1[i] - p2[i];
+                    const float a3 = fabsf(e3);
+                    d1[i] += fabsf(e1) - a3;
+                    d2[i] += fabsf(e2) - a3;
+                    const float k1 = W1[i] * inv1, k2 = W2[i] * inv2;
+                    ga[i] = k1 * sgn(e1);
+                    gb[i] = k2 * sgn(e2);
+                    if (kInputGrads) {
+                        const float s3 = (k1 + k2) * sgn(e3);
+                        gc[i] = -gb[i] - s3;  // d/df1
+                        gd[i] = -ga[i] + s3;  // d/df2
+                    }
+                }
+                stv<V>(a.g_f1w + o, ga);
+                stv<V>(a.g_f2w + o, gb);
+                if (kInputGrads) {
+                    stv<V>(a.g_f1 + o, gc);
+                    stv<V>(a.g_f2 + o, gd);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) { dsm[grp][lane][i] = d1[i]; dsm[grp][lane][V + i] = d2[i]; }
+        __syncthreads();
+        if (grp == 0 && live) {
+            float D1[V], D2[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) { t1 += dsm[g][lane][i]; t2 += dsm[g][lane][V + i]; }
+                D1[i] = t1; D2[i] = t2;
+                num[0] = fmaf(W1[i], t1, num[0]);
+                num[1] = fmaf(W2[i], t2, num[1]);
+            }
+            // park D in the mask-gradient buffers; phase 3 turns it into the gradient in place
+            if (V == 4) {
+                *reinterpret_cast<float4*>(a.g_m1w + mbase + pv * V) = make_float4(D1[0], D1[1], D1[2], D1[3]);
+                *reinterpret_cast<float4*>(a.g_m2w + mbase + pv * V) = make_float4(D2[0], D2[1], D2[2], D2[3]);
+            } else {
+                a.g_m1w[mbase + pv] = D1[0];
+                a.g_m2w[mbase + pv] = D2[0];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: numerators of the whole sample via DSMEM -------------------------------------------
+    block_sum<2>(num, red);
+    if (tid == 0) { xchg_num[0] = num[0]; xchg_num[1] = num[1]; }
+    cluster.sync();
+    float N1 = 0.0f, N2 = 0.0f;
+    for (int r = 0; r < CL; ++r) {
+        const float* remote = cluster.map_shared_rank(xchg_num, r);
+        N1 += remote[0];
+        N2 += remote[1];
+    }
+    if (rank == 0 && tid == 0) {
+        float h1[9], h2[9], E[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { h1[i] = __ldg(a.H12 + b * 9 + i); h2[i] = __ldg(a.H21 + b * 9 + i); }
+        float ln3 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float e = h1[i * 3] * h2[j] + h1[i * 3 + 1] * h2[3 + j] + h1[i * 3 + 2] * h2[6 + j] - (i == j ? 1.0f : 0.0f);
+                E[i * 3 + j] = e;
+                ln3 = fmaf(e, e, ln3);
+            }
+        const float ln1 = N1 * inv1, ln2 = N2 * inv2;
+        a.loss[b] = ln1 + ln2 + a.mu * ln3;
+        a.parts[b * 5 + 0] = ln1; a.parts[b * 5 + 1] = ln2; a.parts[b * 5 + 2] = S1; a.parts[b * 5 + 3] = S2;
+        a.parts[b * 5 + 4] = ln3;
+        const float k = 2.0f * a.mu;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                // (E H21^T)[i][j] = sum_k E[i][k] H21[j][k] ; (H12^T E)[i][j] = sum_k H12[k][i] E[k][j]
+                a.gH12[b * 9 + i * 3 + j] = k * (E[i * 3] * h2[j * 3] + E[i * 3 + 1] * h2[j * 3 + 1] + E[i * 3 + 2] * h2[j * 3 + 2]);
+                a.gH21[b * 9 + i * 3 + j] = k * (h1[i] * E[j] + h1[3 + i] * E[3 + j] + h1[6 + i] * E[6 + j]);
+            }
+    }
+
+    // ---- phase 3: mask gradients, in place over the parked D ------------------------------------------
+    const float c1 = (S1 > 1.0f) ? N1 * inv1 * inv1 : 0.0f, c2 = (S2 > 1.0f) ? N2 * inv2 * inv2 : 0.0f;
+    for (int pv = v0 + tid; pv < v1; pv += kLossThreads) {
+        float y1[V], y2[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) y1[i] = y2[i] = 1.0f;
+        if (a.m1) ldv_cached<V>(a.m1 + mbase + pv * V, y1);
+        if (a.m2) ldv_cached<V>(a.m2 + mbase + pv * V, y2);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float* p1 = a.g_m1w + mbase + pv * V + i;
+            float* p2 = a.g_m2w + mbase + pv * V + i;
+            *p1 = y2[i] * (*p1 * inv1 - c1);
+            *p2 = y1[i] * (*p2 * inv2 - c2);
+        }
+    }
+    cluster.sync();  // keep this CTA's shared memory alive until every peer has read it
+}
+
+__global__ void __launch_bounds__(256)
+    bihome_rescale_kernel(const float* __restrict__ gscale, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2, float* g_m1w,
+                          float* g_m2w, float* gH12, float* gH21, int C, int hw) {
+    const int b = blockIdx.y;
+    const float s = __ldg(gscale + b);
+    if (s == 1.0f) return;  // the training loop's loss.backward(): nothing to do
+    const long long nf = static_cast<long long>(C) * hw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nf;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        g_f1w[b * nf + i] *= s;
+        g_f2w[b * nf + i] *= s;
+        if (g_f1) g_f1[b * nf + i] *= s;
+        if (g_f2) g_f2[b * nf + i] *= s;
+        if (i < hw) { g_m1w[static_cast<long long>(b) * hw + i] *= s; g_m2w[static_cast<long long>(b) * hw + i] *= s; }
+        if (i < 9) { gH12[b * 9 + i] *= s; gH21[b * 9 + i] *= s; }
+    }
+}
+
+template <int V, bool G>
+int launch_bihome(const LossArgs& a, int CL, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.B) * CL);
+    cfg.blockDim = dim3(kLossThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, bihome_kernel<V, G>, a);
+    ++g_launch_count;
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? BH_OK : static_cast<int>(e);
+}
+
+}  // namespace bh
+
+extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* f1w, const float* f2w, const float* m1,
+                                 const float* m2, const float* m1w, const float* m2w, const float* H12, const float* H21,
+                                 float mu, float* loss, float* parts, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2,
+                                 float* g_m1w, float* g_m2w, float* gH12, float* gH21, int B, int C, int h, int w,
+                                 int channels_last, bh_stream_t stream_) {
+    using namespace bh;
+    if (!f1 || !f2 || !f1w || !f2w || !m1w || !m2w || !H12 || !H21 || !loss || !parts || !g_f1w || !g_f2w || !g_m1w ||
+        !g_m2w || !gH12 || !gH21)
+        return BH_E_NULL;
+    if ((g_f1 == nullptr) != (g_f2 == nullptr)) return BH_E_NULL;
+    if (B <= 0 || C <= 0 || h <= 0 || w <= 0) return BH_E_SHAPE;
+    LossArgs a;
+    a.f1 = f1; a.f2 = f2; a.f1w = f1w; a.f2w = f2w; a.m1 = m1; a.m2 = m2; a.m1w = m1w; a.m2w = m2w; a.H12 = H12; a.H21 = H21;
+    a.mu = mu; a.loss = loss; a.parts = parts; a.g_f1w = g_f1w; a.g_f2w = g_f2w; a.g_f1 = g_f1; a.g_f2 = g_f2;
+    a.g_m1w = g_m1w; a.g_m2w = g_m2w; a.gH12 = gH12; a.gH21 = gH21; a.B = B; a.C = C; a.hw = h * w;
+    a.sc = channels_last ? 1 : a.hw;
+    a.sp = channels_last ? C : 1;
+    const bool vec = !channels_last && (a.hw % 4) == 0 && aligned16(f1) && aligned16(f2) && aligned16(f1w) && aligned16(f2w) &&
+                     aligned16(g_f1w) && aligned16(g_f2w) && aligned16(m1w) && aligned16(m2w) && aligned16(g_m1w) &&
+                     aligned16(g_m2w) && (!m1 || aligned16(m1)) && (!m2 || aligned16(m2)) && (!g_f1 || aligned16(g_f1)) &&
+                     (!g_f2 || aligned16(g_f2));
+    // cluster size: enough CTAs to cover the 148 SMs a few times over, never more than the pixel-vectors allow
+    const int nvec = vec ? a.hw / 4 : a.hw;
+    int CL = (B >= 2 * kNumSMs) ? 2 : (B >= kNumSMs ? 4 : 8);
+    while (CL > 1 && nvec / CL < kLanes) CL >>= 1;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (vec) return g_f1 ? launch_bihome<4, true>(a, CL, stream) : launch_bihome<4, false>(a, CL, stream);
+    return g_f1 ? launch_bihome<1, true>(a, CL, stream) : launch_bihome<1, false>(a, CL, stream);
+}
+
+extern "C" int bh_bihome_rescale(const float* gscale, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2, float* g_m1w,
+                                 float* g_m2w, float* gH12, float* gH21, int B, int C, int h, int w, bh_stream_t stream_) {
+    using namespace bh;
+    if (!gscale || !g_f1w || !g_f2w || !g_m1w || !g_m2w || !gH12 || !gH21) return BH_E_NULL;
+    if (B <= 0 || C <= 0 || h <= 0 || w <= 0) return BH_E_SHAPE;
+    const long long nf = static_cast<long long>(C) * h * w;
+    long long gx = (nf + 256 * 8 - 1) / (256 * 8);
+    if (gx > 64) gx = 64;
+    if (nf < 9) return BH_E_SHAPE;
+    dim3 grid(static_cast<unsigned>(gx), B);
+    bihome_rescale_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(gscale, g_f1w, g_f2w, g_f1, g_f2, g_m1w,
+                                                                                      g_m2w, gH12, gH21, C, h * w);
+    return launch_status();
+}

@@ -1,0 +1,249 @@
+"""PyTorch autograd front-end of libbihome_b200.so.
+
+Every function here takes CUDA float32 tensors, hands raw device pointers and the current CUDA stream to the
+C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to ATen: a CPU tensor raises.
+
+  dlt4(delta, corners=None, size=(W, H))                   K1   four_point_to_homography   (src/data/utils.py:20-24)
+  warp(src, H, out_h, out_w, pool=None)                    K2   warp_image(inverse=True)   (src/data/utils.py:54-59)
+  coverage_mask(H, src_hw, out_hw, pool)                   K2   warp(ones) + AvgPool2d     (PerceptualHead.py:380-382,447-459)
+  bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu)    K3   double-line biHomE loss    (PerceptualHead.py:559-561,609-665)
+  mace(delta_gt, delta_hat)                                     train.py:401-404
+"""
+import ctypes
+
+import torch
+
+from . import cabi
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda_f32(name, t):
+    if not torch.is_tensor(t):
+        raise TypeError('%s must be a tensor, got %r' % (name, type(t)))
+    if not t.is_cuda:
+        raise RuntimeError('bihome_b200: %s is on %s; the hot path runs on CUDA only (no CPU fallback)' % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError('bihome_b200: %s must be float32, got %s' % (name, t.dtype))
+
+
+def _is_nhwc(t):
+    return t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _dense(t):
+    """contiguous NCHW or channels-last as is; anything else -> contiguous copy"""
+    if t.is_contiguous() or _is_nhwc(t):
+        return t
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+class _Dlt4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, delta, corners, W, Hh):
+        _need_cuda_f32('delta', delta)
+        delta = delta.contiguous()
+        if corners is not None:
+            _need_cuda_f32('corners', corners)
+            corners = corners.contiguous()
+        B = delta.shape[0]
+        H = torch.empty(B, 3, 3, device=delta.device, dtype=torch.float32)
+        with torch.cuda.device(delta.device):
+            cabi.check(cabi.lib().bh_dlt4_fwd(_ptr(corners), _ptr(delta), _ptr(H), B, float(W), float(Hh), _stream()),
+                       'bh_dlt4_fwd')
+        ctx.save_for_backward(delta, corners, H)
+        ctx.size = (float(W), float(Hh))
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        delta, corners, H = ctx.saved_tensors
+        gH = gH.contiguous()
+        B = delta.shape[0]
+        g_delta = torch.empty_like(delta)
+        want_c = corners is not None and ctx.needs_input_grad[1]
+        g_corners = torch.empty_like(corners) if want_c else None
+        with torch.cuda.device(delta.device):
+            cabi.check(cabi.lib().bh_dlt4_bwd(_ptr(corners), _ptr(delta), _ptr(H), _ptr(gH), _ptr(g_delta), _ptr(g_corners),
+                                              B, ctx.size[0], ctx.size[1], _stream()), 'bh_dlt4_bwd')
+        return g_delta, g_corners, None, None
+
+
+def dlt4(delta, corners=None, size=None):
+    """delta [B,4,2] (+ corners [B,4,2] or the canonical rectangle of `size`=(W,H)) -> H [B,3,3], h33 = 1."""
+    if delta.dim() != 3 or delta.shape[1:] != (4, 2):
+        raise ValueError('deltas should be of size B, 4, 2, but got: {}'.format(tuple(delta.shape)))
+    if corners is None:
+        if size is None:
+            raise ValueError('dlt4 needs either corners or size=(W, H)')
+        return _Dlt4.apply(delta, None, size[0], size[1])
+    if corners.shape != delta.shape:
+        raise ValueError('corners should be of size B, 4, 2, but got: {}'.format(tuple(corners.shape)))
+    return _Dlt4.apply(delta, corners, 0.0, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, H, out_h, out_w, pool, src_hw):
+        _need_cuda_f32('homography', H)
+        Hc = H.contiguous().view(-1, 9)
+        B = Hc.shape[0]
+        lib = cabi.lib()
+        out = mask = None
+        C = 0
+        nhwc = 0
+        if src is not None:
+            _need_cuda_f32('image', src)
+            src = _dense(src)
+            if src.shape[0] != B:
+                raise ValueError('image batch %d != homography batch %d' % (src.shape[0], B))
+            nhwc = int(_is_nhwc(src))
+            C, Hs, Ws = src.shape[1], src.shape[2], src.shape[3]
+            out = torch.empty((B, C, out_h, out_w), device=src.device, dtype=torch.float32,
+                              memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+        else:
+            Hs, Ws = src_hw
+        if pool:
+            mask = torch.empty((B, out_h // pool, out_w // pool), device=Hc.device, dtype=torch.float32)
+        with torch.cuda.device(Hc.device):
+            cabi.check(lib.bh_warp_fwd(_ptr(src), _ptr(Hc), _ptr(out), _ptr(mask), B, C, Hs, Ws, out_h, out_w,
+                                       int(pool or 0), nhwc, _stream()), 'bh_warp_fwd')
+        ctx.save_for_backward(src, Hc)
+        ctx.geom = (B, C, Hs, Ws, out_h, out_w, int(pool or 0), nhwc)
+        if src is None:
+            return mask
+        if pool:
+            return out, mask
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        src, Hc = ctx.saved_tensors
+        B, C, Hs, Ws, Ho, Wo, pool, nhwc = ctx.geom
+        if src is None:
+            g_out, g_mask = None, grads[0]
+        elif pool:
+            g_out, g_mask = grads
+        else:
+            g_out, g_mask = grads[0], None
+        lib = cabi.lib()
+        if g_out is not None:
+            g_out = g_out.contiguous(memory_format=torch.channels_last) if nhwc else g_out.contiguous()
+        if g_mask is not None:
+            g_mask = g_mask.contiguous()
+        gH = torch.empty(B, 9, device=Hc.device, dtype=torch.float32)
+        if g_out is None and g_mask is None:
+            return None, gH.zero_().view(B, 3, 3), None, None, None, None
+        g_src = None
+        if src is not None and ctx.needs_input_grad[0] and g_out is not None:
+            g_src = torch.zeros_like(src)
+        nbytes = lib.bh_warp_bwd_workspace_bytes(B, C, Hs, Ws, Ho, Wo, nhwc)
+        ws = torch.empty(max(int(nbytes), 16), device=Hc.device, dtype=torch.uint8)
+        with torch.cuda.device(Hc.device):
+            cabi.check(lib.bh_warp_bwd(_ptr(src if g_out is not None else None), _ptr(Hc), _ptr(g_out), _ptr(g_mask), _ptr(gH),
+                                       _ptr(g_src), B, C, Hs, Ws, Ho, Wo, pool, nhwc, _ptr(ws), int(nbytes), _stream()),
+                       'bh_warp_bwd')
+        return g_src, gH.view(B, 3, 3), None, None, None, None
+
+
+def warp(src, H, out_h, out_w, pool=None):
+    """out[b,c,y,x] = bilinear(src[b,c], proj(H_b [x,y,1]^T)), zeros outside.
+
+    With ``pool`` also returns the analytic coverage mask warp(ones) average-pooled by ``pool``:
+    ``(out, mask [B, out_h/pool, out_w/pool])``.
+    """
+    if src.dim() != 4:
+        raise ValueError('image should be of size B, C, H, W, got {}'.format(tuple(src.shape)))
+    return _Warp.apply(src, H, int(out_h), int(out_w), pool, None)
+
+
+def coverage_mask(H, src_hw, out_hw, pool=1):
+    """warp(ones_like(image)) followed by AvgPool2d(pool), computed analytically from H: [B, out_h/pool, out_w/pool]."""
+    return _Warp.apply(None, H, int(out_hw[0]), int(out_hw[1]), int(pool), (int(src_hw[0]), int(src_hw[1])))
+
+
+# ------------------------------------------------------------------------------------------------
+# K3
+# ------------------------------------------------------------------------------------------------
+class _BihomeLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, f1w, f2w, m1, m2, m1w, m2w, H12, H21, mu):
+        for n, t in (('f1', f1), ('f2', f2), ('f1w', f1w), ('f2w', f2w), ('m1w', m1w), ('m2w', m2w), ('H12', H12), ('H21', H21)):
+            _need_cuda_f32(n, t)
+        nhwc = all(_is_nhwc(t) for t in (f1, f2, f1w, f2w))
+        if nhwc:
+            feats = [f1, f2, f1w, f2w]
+        else:
+            feats = [t.contiguous() for t in (f1, f2, f1w, f2w)]
+        f1, f2, f1w, f2w = feats
+        B, C, h, w = f1w.shape
+        m1 = None if m1 is None else m1.contiguous()
+        m2 = None if m2 is None else m2.contiguous()
+        m1w, m2w = m1w.contiguous(), m2w.contiguous()
+        H12c, H21c = H12.contiguous().view(B, 9), H21.contiguous().view(B, 9)
+        dev = f1w.device
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        parts = torch.empty(B, 5, device=dev, dtype=torch.float32)
+        g_f1w, g_f2w = torch.empty_like(f1w), torch.empty_like(f2w)
+        want_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_f1 = torch.empty_like(f1) if want_in else None
+        g_f2 = torch.empty_like(f2) if want_in else None
+        g_m1w, g_m2w = torch.empty_like(m1w), torch.empty_like(m2w)
+        gH12 = torch.empty(B, 9, device=dev, dtype=torch.float32)
+        gH21 = torch.empty(B, 9, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib().bh_bihome_fwd_bwd(
+                _ptr(f1), _ptr(f2), _ptr(f1w), _ptr(f2w), _ptr(m1), _ptr(m2), _ptr(m1w), _ptr(m2w), _ptr(H12c), _ptr(H21c),
+                float(mu), _ptr(loss), _ptr(parts), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_m1w),
+                _ptr(g_m2w), _ptr(gH12), _ptr(gH21), B, C, h, w, int(nhwc), _stream()), 'bh_bihome_fwd_bwd')
+        ctx.grads = (g_f1w, g_f2w, g_f1, g_f2, g_m1w, g_m2w, gH12, gH21)
+        ctx.dims = (B, C, h, w)
+        ctx.mark_non_differentiable(parts)
+        return loss, parts
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        if ctx.grads is None:
+            raise RuntimeError('bihome_loss: the fused loss stores its gradients once; backward twice is not supported')
+        g_f1w, g_f2w, g_f1, g_f2, g_m1w, g_m2w, gH12, gH21 = ctx.grads
+        ctx.grads = None
+        B, C, h, w = ctx.dims
+        g_loss = g_loss.contiguous().float()
+        with torch.cuda.device(g_f1w.device):
+            cabi.check(cabi.lib().bh_bihome_rescale(_ptr(g_loss), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_m1w),
+                                                    _ptr(g_m2w), _ptr(gH12), _ptr(gH21), B, C, h, w, _stream()),
+                       'bh_bihome_rescale')
+        return (g_f1, g_f2, g_f1w, g_f2w, None, None, g_m1w, g_m2w, gH12.view(B, 3, 3), gH21.view(B, 3, 3), None)
+
+
+def bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu, m1=None, m2=None):
+    """Per-sample double-line biHomE loss (margin 'inf', l1, channel-agnostic).
+
+    features [B,C,h,w]; pooled masks [B,h,w] (m1/m2 None == ones); H12,H21 [B,3,3].
+    Returns (loss_b [B], parts [B,5] = ln1, ln2, den1 (unclamped), den2, ln3); the reference's scalar is loss_b.sum().
+    """
+    return _BihomeLoss.apply(f1, f2, f1w, f2w, m1, m2, m1w, m2w, H12, H21, float(mu))
+
+
+# ------------------------------------------------------------------------------------------------
+def mace(delta_gt, delta_hat):
+    """mean corner error over B*4 corners, as a 0-dim CUDA tensor (no host sync)."""
+    _need_cuda_f32('delta_gt', delta_gt)
+    _need_cuda_f32('delta_hat', delta_hat)
+    a, b = delta_gt.detach().contiguous(), delta_hat.detach().contiguous()
+    out = torch.empty(1, device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        cabi.check(cabi.lib().bh_mace(_ptr(a), _ptr(b), _ptr(out), a.numel() // 8, _stream()), 'bh_mace')
+    return out[0]

@@ -1,0 +1,159 @@
+/*
+ * bihome_b200 -- C ABI of the B200-native biHomE hot path (libbihome_b200.so).
+ *
+ * The reference (NeurAI-Lab/biHomE) is pure Python: it has no FFI.  Its "plugin API" for this path
+ * is the set of Python call sites listed next to every entry point below; each entry point replaces
+ * the ATen/kornia op chain behind that call site with one hand-written sm_100a kernel.  The host side
+ * (bihome_b200/functional.py, loaded through ctypes) keeps the reference's Python signatures.
+ *
+ * Conventions (all entry points):
+ *   - return int: 0 = ok, <0 = bad argument (BH_E_*), >0 = cudaError_t of the launch;
+ *   - stateless, re-entrant, stream ordered: nothing is allocated, nothing synchronises; the caller
+ *     owns every buffer including workspaces; `stream` is a cudaStream_t (0 = legacy default);
+ *   - every pointer is a DEVICE pointer to contiguous float32 unless stated otherwise, 16-byte aligned
+ *     (anything from cudaMalloc / a fresh torch tensor is);
+ *   - H is a row-major 3x3 homography stored as 9 floats per sample, H[8] is carried (1 for DLT-4);
+ *   - "pixel coordinates" are pixel centres, i.e. F.grid_sample(align_corners=True) un-normalised.
+ */
+#ifndef BIHOME_B200_H_
+#define BIHOME_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* bh_stream_t; /* == cudaStream_t */
+
+#define BH_VERSION 100 /* 0.1.0 */
+
+enum {
+    BH_OK = 0,
+    BH_E_NULL = -1,      /* required pointer is NULL */
+    BH_E_SHAPE = -2,     /* non-positive or unsupported dimension */
+    BH_E_ALIGN = -3,     /* pointer not 16-byte aligned */
+    BH_E_WORKSPACE = -4, /* workspace too small */
+    BH_E_UNSUPPORTED = -5
+};
+
+int bh_version(void);
+/* human readable text for a return code of any entry point */
+const char* bh_strerror(int code);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+unsigned long long bh_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  4-point offsets -> homography (8x8 DLT, LU with partial pivoting, one 8-lane group per sample)
+ *
+ * replaces: src/data/utils.py:20-24  four_point_to_homography (torch branch)
+ *             -> kornia.get_perspective_transform (16x cat/stack + torch.solve)
+ *           src/data/utils.py:36-51  image_shape_to_corners  (corners == NULL => the canonical
+ *             [[0,0],[W,0],[W,Hh],[0,Hh]] the reference builds there)
+ *
+ * corners [B,4,2] or NULL, delta [B,4,2] -> H [B,9] mapping corner_i -> corner_i + delta_i, H[8] = 1.
+ * bwd: gH [B,9] (gH[8] ignored) -> gDelta [B,4,2] (d/d delta; also d/d dst) and, if non-NULL,
+ *      gCorners [B,4,2] (total derivative w.r.t. corners, dst = corners + delta included).
+ * ------------------------------------------------------------------------------------------- */
+int bh_dlt4_fwd(const float* corners, const float* delta, float* H, int B, float W, float Hh, bh_stream_t stream);
+int bh_dlt4_bwd(const float* corners, const float* delta, const float* H, const float* gH, float* gDelta,
+                float* gCorners, int B, float W, float Hh, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  homography warp: out[b,c,y,x] = bilinear(src[b,c], proj(H_b [x,y,1]^T)), zeros padding
+ *
+ * replaces: src/data/utils.py:54-59  warp_image(inverse=True) -> torch.inverse + kornia.warp_perspective
+ *             (normalize_homography, 2 more inversions, create_meshgrid, transform_points, F.grid_sample)
+ *           src/heads/PerceptualHead.py:339-340,380-382,401  warp(ones) masks and
+ *           src/heads/PerceptualHead.py:447-459              their AvgPool2d(pool): mask_pooled is the
+ *             analytic coverage mx(u)*my(v) averaged over pool x pool output pixels, no source read.
+ *
+ * src [B,C,Hs,Ws] (channels_last=0) or [B,Hs,Ws,C] (channels_last=1); out likewise with Ho,Wo.
+ * src/out may both be NULL (masks only).  mask_pooled [B,Ho/pool,Wo/pool] or NULL (then pool is ignored).
+ * bwd: gOut (layout of out, or NULL), gMaskPooled or NULL -> gH [B,9] (overwritten, gH[8] = d/dh33),
+ *      and if gSrc != NULL the image gradient is ACCUMULATED into gSrc (caller zero-fills).
+ *      workspace: bh_warp_bwd_workspace_bytes(...) bytes (may be 0 -> pass NULL).
+ * ------------------------------------------------------------------------------------------- */
+int bh_warp_fwd(const float* src, const float* H, float* out, float* mask_pooled, int B, int C, int Hs, int Ws,
+                int Ho, int Wo, int pool, int channels_last, bh_stream_t stream);
+size_t bh_warp_bwd_workspace_bytes(int B, int C, int Hs, int Ws, int Ho, int Wo, int channels_last);
+int bh_warp_bwd(const float* src, const float* H, const float* gOut, const float* gMaskPooled, float* gH,
+                float* gSrc, int B, int C, int Hs, int Ws, int Ho, int Wo, int pool, int channels_last,
+                void* workspace, size_t workspace_bytes, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  bidirectional perceptual (biHomE) loss, fused forward + backward, one pass over the features
+ *
+ * replaces: src/heads/PerceptualHead.py:559-561 (l1 distances), :609-665 (double-line, margin 'inf',
+ *           channel-agnostic: ln1, ln2, ln3, loss) and the ~110 autograd kernels behind them.
+ *
+ *   W1 = m1w*m2, W2 = m2w*m1 (pooled masks, NULL m1/m2 == ones)      S1 = sum W1, den1 = max(S1,1)
+ *   D1 = sum_c|f1w-f2| - sum_c|f1-f2|,  D2 = sum_c|f2w-f1| - sum_c|f1-f2|
+ *   loss_b = sum_hw W1*D1/den1 + sum_hw W2*D2/den2 + mu*||H12 H21 - I||_F^2
+ *
+ * features [B,C,h,w] (channels_last=0) or [B,h,w,C] (=1); masks [B,h,w]; H12,H21 [B,9].
+ * outputs: loss [B]; parts [B,5] = {ln1, ln2, S1, S2, ln3} (ln3 without mu);
+ *          g_f1w,g_f2w (feature layout), g_m1w,g_m2w [B,h,w], gH12,gH21 [B,9]: d loss_b / d(.) ;
+ *          g_f1,g_f2: optional (NULL when the extractor inputs need no gradient, the shipped configs).
+ * bh_bihome_rescale multiplies every gradient of sample b by gscale[b] (device vector) and is a no-op
+ * launch when gscale[b] == 1 -- the autograd backward calls it with the upstream gradient.
+ * ------------------------------------------------------------------------------------------- */
+int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* f1w, const float* f2w, const float* m1,
+                      const float* m2, const float* m1w, const float* m2w, const float* H12, const float* H21,
+                      float mu, float* loss, float* parts, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2,
+                      float* g_m1w, float* g_m2w, float* gH12, float* gH21, int B, int C, int h, int w,
+                      int channels_last, bh_stream_t stream);
+int bh_bihome_rescale(const float* gscale, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2, float* g_m1w,
+                      float* g_m2w, float* gH12, float* gH21, int B, int C, int h, int w, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  N-point normalised DLT (Zeng / DSAC branch), one warp per hypothesis
+ *
+ * replaces: src/heads/ransac_utils.py:58-72 (gather + kornia.find_homography_dlt: normalize_points,
+ *           A^T A, torch.svd, denormalise, /H33) and src/heads/PerceptualHead.py:175-178 (corner
+ *           projection kornia.transform_points(H, four_points) - four_points).
+ *
+ * field [B,2,Hf,Wf] perspective field (x then y displacement); choice [B,N] int64 indices into the
+ * Hf*Wf grid (the torch.multinomial draw); four [4,2] corner points.
+ * fwd -> Hn [B,9] (H / (H33 + 1e-8)), delta [B,4,2], and `saved` [B, BH_DLTN_SAVED] floats for bwd.
+ * bwd: gHn [B,9] or NULL, gDelta [B,4,2] or NULL -> gField [B,2,Hf,Wf] ACCUMULATED (caller zero-fills).
+ * ------------------------------------------------------------------------------------------- */
+#define BH_DLTN_SAVED 192
+int bh_dltn_fwd(const float* field, const int64_t* choice, const float* four, float* Hn, float* delta, float* saved,
+                int B, int N, int Hf, int Wf, bh_stream_t stream);
+int bh_dltn_bwd(const float* field, const int64_t* choice, const float* four, const float* saved, const float* gHn,
+                const float* gDelta, float* gField, int B, int N, int Hf, int Wf, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  synthetic (PD)S-COCO pair generation on the GPU
+ *
+ * replaces: src/data/transforms.py:456-576,724-725 HomographyNetPrep.__call__ (photometric distortion
+ *           :296-330, random patch position and corner offsets, cv2.getPerspectiveTransform,
+ *           cv2.warpPerspective with 1/32-px taps, crop), :344-354 DictToGrayscale,
+ *           :369-378 DictStandardize, :728-743 DictToTensor, train.py:308-309 (.float()).
+ *
+ * images: uint8 [n_img,Hi,Wi,3] RGB pool resident in HBM; index [B] int32 image per sample.
+ * params: double [B, BH_PAIR_NPARAM] per-sample draws, layout (see oracle/pairgen.py pack_params):
+ *   2 x {b_on, b_delta, contrast_first, c_on, c_alpha, s_on, s_alpha, h_on, h_delta, l_on, l_perm},
+ *   pos_x, pos_y, delta[8].
+ * bh_pairgen_draw fills params (and index) from a counter-based generator (seed, step, sample);
+ * bh_pairgen_apply renders patch1, patch2 [B,1,P,P] (grayscale, standardised) and delta [B,4,2].
+ * ------------------------------------------------------------------------------------------- */
+#define BH_PAIR_NPARAM 32
+int bh_pairgen_draw(double* params, int32_t* index, int B, int n_img, int Hi, int Wi, int rho, int P,
+                    float max_delta, uint64_t seed, uint64_t step, bh_stream_t stream);
+int bh_pairgen_apply(const uint8_t* images, const int32_t* index, const double* params, float* patch1,
+                     float* patch2, float* delta, int B, int n_img, int Hi, int Wi, int P, float mean, float std,
+                     bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MACE: mean over B*4 corners of ||delta_gt - delta_hat||_2  (train.py:401-404, eval.py:133-134)
+ * out: 1 float (overwritten).
+ * ------------------------------------------------------------------------------------------- */
+int bh_mace(const float* delta_gt, const float* delta_hat, float* out, int B, bh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIHOME_B200_H_ */
