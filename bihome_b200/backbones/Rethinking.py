@@ -1,0 +1,99 @@
+"""Perspective-field backbone ("Zeng", reference ``src/backbones/Rethinking.py``): an encoder/decoder ResNet that
+maps the two stacked patches [B,2,P,P] to a dense displacement field [B,2,P,P].  Same kwargs, same
+``forward(data) -> data`` dict protocol, same parameter names as the reference (checkpoint compatible)."""
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .blocks import (ResNet34ConvBlock, ResNet34IdentityBlock, ResNet50ConvBlock, ResNet50DeconvBlock,
+                     ResNet50IdentityBlock)
+
+# per stage: ('conv', cin, cout, stride) | ('id', c) | ('up', c); widths for ResNet34; ResNet50 multiplies by 4
+_STAGES = {
+    'layer2': [('conv', 64, 64, 1), ('id', 64), ('id', 64)],
+    'layer3': [('conv', 64, 128, 2)] + [('id', 128)] * 3,
+    'layer4': [('conv', 128, 256, 2)] + [('id', 256)] * 5 + [('up', 256)],
+    'layer5': [('id', 128)] * 3 + [('up', 128)],
+    'layer6': [('id', 64)] * 2 + [('up', 64)],
+    'layer7': [('id', 32), ('up', 32)],
+}
+_RESNET_URLS = {'ResNet50': 'https://download.pytorch.org/models/resnet50-19c8e357.pth',
+                'ResNet34': 'https://download.pytorch.org/models/resnet34-333f7ec4.pth'}
+
+
+class Model(nn.Module):
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.image_size = kwargs['IMAGE_SIZE']
+        self.patch_keys = kwargs['PATCH_KEYS']
+        self.target_keys = kwargs['TARGET_KEYS']
+        self.resnet_block = kwargs['RESNET_BLOCK']
+        self.pretrained_resnet = kwargs['PRETRAINED_RESNET']
+        self.variant = str.lower(kwargs['VARIANT']) if 'VARIANT' in kwargs else 'oneline'
+        assert 'oneline' in self.variant or 'doubleline' in self.variant, 'Only OneLine or DoubleLine variant is supported'
+        assert self.resnet_block in ('ResNet34', 'ResNet50'), 'I know only ResNet50 and ResNet34'
+        wide = self.resnet_block == 'ResNet50'
+        m = 4 if wide else 1
+
+        self.layer1 = nn.Sequential(nn.Conv2d(2, 64, kernel_size=7, padding=3, stride=2, bias=False), nn.BatchNorm2d(64),
+                                    nn.ReLU(), nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
+        for name, stage in _STAGES.items():
+            blocks = []
+            for spec in stage:
+                if spec[0] == 'conv':
+                    cin = spec[1] if (name == 'layer2') else spec[1] * m
+                    if wide:
+                        blocks.append(ResNet50ConvBlock(cin, spec[2] * m, spec[3]))
+                    else:
+                        blocks.append(ResNet34ConvBlock(cin, spec[2], spec[3]))
+                elif spec[0] == 'id':
+                    blocks.append(ResNet50IdentityBlock(spec[1] * m) if wide else ResNet34IdentityBlock(spec[1]))
+                else:
+                    blocks.append(ResNet50DeconvBlock(spec[1] * m))
+            setattr(self, name, nn.Sequential(*blocks))
+        c = 16 * m
+        self.layer8 = nn.Sequential(nn.Conv2d(c, 8 * c, kernel_size=1), nn.BatchNorm2d(8 * c), nn.ReLU(),
+                                    nn.Conv2d(8 * c, 2, kernel_size=1))
+        if self.pretrained_resnet:
+            self._load_pretrained_weights()
+
+    def _load_pretrained_weights(self):
+        """ImageNet weights of torchvision layer1..3 -> layer2..4 (reference :161-289); skipped with a warning offline."""
+        try:
+            from torch.hub import load_state_dict_from_url
+            state = load_state_dict_from_url(_RESNET_URLS[self.resnet_block], progress=True)
+        except Exception as e:  # noqa: BLE001
+            warnings.warn('bihome_b200: pretrained %s weights unavailable (%s); backbone keeps its random init'
+                          % (self.resnet_block, e))
+            return
+        rename = {'conv1': 'upper_branch.0', 'bn1': 'upper_branch.1', 'conv2': 'upper_branch.3', 'bn2': 'upper_branch.4',
+                  'conv3': 'upper_branch.6', 'bn3': 'upper_branch.7', 'downsample': 'lower_branch'}
+        own = self.state_dict()
+        picked = {}
+        for key, value in state.items():
+            for i in (1, 2, 3):
+                if key.startswith('layer%d.' % i):
+                    new = key.replace('layer%d' % i, 'layer%d' % (i + 1))
+                    for a, b in rename.items():
+                        new = new.replace(a, b)
+                    if new in own and own[new].shape == value.shape:
+                        picked[new] = value
+        self.load_state_dict(picked, strict=False)
+
+    def _forward(self, x):
+        for i in range(1, 9):
+            x = getattr(self, 'layer%d' % i)(x)
+        return x
+
+    def forward(self, data):
+        e1, e2 = self.patch_keys
+        p1, p2 = data[e1], data[e2]
+        data[self.target_keys[0]] = self._forward(torch.cat([p1, p2], dim=1))
+        if self.variant == 'doubleline':
+            data[self.target_keys[1]] = self._forward(torch.cat([p2, p1], dim=1))
+        return data
+
+    def predict_homography(self, data):
+        return self.forward(data)

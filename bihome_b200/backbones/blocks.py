@@ -1,0 +1,79 @@
+"""Residual building blocks of the homography backbones.
+
+Same layer graph and the same parameter names (``upper_branch.<i>`` / ``lower_branch.<i>``) as the reference's
+``src/backbones/utils.py`` so that reference checkpoints load unchanged; the dense convolutions stay on cuDNN
+(tensor-core work is out of scope for the custom kernels, BASELINE.json north_star).
+"""
+import torch.nn as nn
+
+
+def _conv(cin, cout, k, stride=1, bias=False):
+    return nn.Conv2d(cin, cout, kernel_size=k, padding=k // 2, stride=stride, bias=bias)
+
+
+def _seq(*specs):
+    """specs: ('c', cin, cout, k, stride) conv+bn | 'r' relu | ('t', cin, cout, bias) 2x2 transposed conv | ('b', c) bn"""
+    layers = []
+    for s in specs:
+        if s == 'r':
+            layers.append(nn.ReLU())
+        elif s[0] == 'c':
+            layers += [_conv(s[1], s[2], s[3], s[4]), nn.BatchNorm2d(s[2])]
+        elif s[0] == 't':
+            layers.append(nn.ConvTranspose2d(s[1], s[2], kernel_size=2, padding=0, stride=2, bias=s[3]))
+        elif s[0] == 'b':
+            layers.append(nn.BatchNorm2d(s[1]))
+    return nn.Sequential(*layers)
+
+
+class _Residual(nn.Module):
+    """relu(upper_branch(x) + (lower_branch(x) or x))"""
+
+    def __init__(self, upper, lower=None):
+        super().__init__()
+        self.upper_branch = upper
+        if lower is not None:
+            self.lower_branch = lower
+        self.lower_is_identity = lower is None
+
+    def forward(self, x):
+        skip = x if self.lower_is_identity else self.lower_branch(x)
+        return nn.functional.relu(self.upper_branch(x) + skip)
+
+
+class ResNet34ConvBlock(_Residual):
+    def __init__(self, input_channels, output_channels, stride):
+        upper = _seq(('c', input_channels, output_channels, 3, stride), 'r', ('c', output_channels, output_channels, 3, 1))
+        lower = None
+        if input_channels != output_channels:
+            lower = _seq(('c', input_channels, output_channels, 1, stride))
+        super().__init__(upper, lower)
+
+
+class ResNet34IdentityBlock(_Residual):
+    def __init__(self, input_channels):
+        c = input_channels
+        super().__init__(_seq(('c', c, c, 3, 1), 'r', ('c', c, c, 3, 1)))
+
+
+class ResNet50ConvBlock(_Residual):
+    def __init__(self, input_channels, output_channels, stride):
+        mid = input_channels // stride
+        upper = _seq(('c', input_channels, mid, 1, stride), 'r', ('c', mid, mid, 3, 1), 'r', ('c', mid, output_channels, 1, 1))
+        super().__init__(upper, _seq(('c', input_channels, output_channels, 1, stride)))
+
+
+class ResNet50IdentityBlock(_Residual):
+    def __init__(self, input_channels):
+        c, m = input_channels, input_channels // 4
+        super().__init__(_seq(('c', c, m, 1, 1), 'r', ('c', m, m, 3, 1), 'r', ('c', m, c, 1, 1)))
+
+
+class ResNet50DeconvBlock(_Residual):
+    """x2 up-sampling block: channels halve."""
+
+    def __init__(self, input_channels):
+        c = input_channels
+        upper = _seq(('t', c, c, True), ('c', c, c, 3, 1), 'r', ('c', c, c // 2, 1, 1))
+        lower = _seq(('t', c, c // 2, False), ('b', c // 2))
+        super().__init__(upper, lower)

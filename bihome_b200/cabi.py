@@ -6,6 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbihome_b200.so')
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_d = ctypes.c_double
 _u64 = ctypes.c_uint64
 
 # name -> (restype, argtypes); mirrors include/bihome_b200.h one to one
@@ -20,10 +21,10 @@ SIGNATURES = {
     'bh_warp_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     'bh_bihome_fwd_bwd': (_i, [_vp] * 10 + [_f] + [_vp] * 10 + [_i, _i, _i, _i, _i, _vp]),
     'bh_bihome_rescale': (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
-    'bh_dltn_fwd': (_i, [_vp] * 6 + [_i, _i, _i, _i, _vp]),
-    'bh_dltn_bwd': (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
+    'bh_dltn_fwd': (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
+    'bh_dltn_bwd': (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
     'bh_pairgen_draw': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
-    'bh_pairgen_apply': (_i, [_vp] * 6 + [_i, _i, _i, _i, _i, _f, _f, _vp]),
+    'bh_pairgen_apply': (_i, [_vp] * 6 + [_i, _i, _i, _i, _i, _d, _d, _vp]),
     'bh_mace': (_i, [_vp, _vp, _vp, _i, _vp]),
 }
 
@@ -40,8 +41,6 @@ def lib():
                 '`python -c "import __graft_entry__ as g; g.build()"`; there is no CPU fallback.' % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            if not hasattr(handle, name):    # TEMP while K4/K5 are being written
-                continue
             fn = getattr(handle, name)       # AttributeError here == header/library mismatch
             fn.restype = res
             fn.argtypes = args

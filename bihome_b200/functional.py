@@ -7,6 +7,8 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   warp(src, H, out_h, out_w, pool=None)                    K2   warp_image(inverse=True)   (src/data/utils.py:54-59)
   coverage_mask(H, src_hw, out_hw, pool)                   K2   warp(ones) + AvgPool2d     (PerceptualHead.py:380-382,447-459)
   bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu)    K3   double-line biHomE loss    (PerceptualHead.py:559-561,609-665)
+  dltn(p1, p2, choice) / dltn_field(field, choice, four)   K4   find_homography_dlt        (ransac_utils.py:58-72, PerceptualHead.py:164-178)
+  pairgen_draw(...) / pairgen_apply(...)                   K5   HomographyNetPrep pipeline (src/data/transforms.py:456-576)
   mace(delta_gt, delta_hat)                                     train.py:401-404
 """
 import ctypes
@@ -97,6 +99,7 @@ def dlt4(delta, corners=None, size=None):
 class _Warp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, H, out_h, out_w, pool, src_hw):
+        ctx.set_materialize_grads(False)
         _need_cuda_f32('homography', H)
         Hc = H.contiguous().view(-1, 9)
         B = Hc.shape[0]
@@ -180,6 +183,7 @@ def coverage_mask(H, src_hw, out_hw, pool=1):
 class _BihomeLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f1, f2, f1w, f2w, m1, m2, m1w, m2w, H12, H21, mu):
+        ctx.set_materialize_grads(False)
         for n, t in (('f1', f1), ('f2', f2), ('f1w', f1w), ('f2w', f2w), ('m1w', m1w), ('m2w', m2w), ('H12', H12), ('H21', H21)):
             _need_cuda_f32(n, t)
         nhwc = all(_is_nhwc(t) for t in (f1, f2, f1w, f2w))
@@ -215,6 +219,8 @@ class _BihomeLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _g_parts):
+        if g_loss is None:
+            return (None,) * 11
         if ctx.grads is None:
             raise RuntimeError('bihome_loss: the fused loss stores its gradients once; backward twice is not supported')
         g_f1w, g_f2w, g_f1, g_f2, g_m1w, g_m2w, gH12, gH21 = ctx.grads
@@ -235,6 +241,109 @@ def bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu, m1=None, m2=None):
     Returns (loss_b [B], parts [B,5] = ln1, ln2, den1 (unclamped), den2, ln3); the reference's scalar is loss_b.sum().
     """
     return _BihomeLoss.apply(f1, f2, f1w, f2w, m1, m2, m1w, m2w, H12, H21, float(mu))
+
+
+# ------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------
+class _DltN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p1, p2, field, choice, four):
+        ctx.set_materialize_grads(False)
+        src = field if field is not None else p2
+        _need_cuda_f32('correspondences', src)
+        if field is not None:
+            field = field.contiguous()
+            B, _, Hf, Wf = field.shape
+            N = Hf * Wf
+        else:
+            _need_cuda_f32('points1', p1)
+            p1, p2 = p1.detach().contiguous(), p2.contiguous()
+            B, N = p2.shape[0], p2.shape[1]
+            Wf = 0
+        if choice is not None:
+            choice = choice.to(torch.int64).contiguous().view(B, -1)
+            M = choice.shape[1]
+        else:
+            M = N
+        Hn = torch.empty(B, 3, 3, device=src.device, dtype=torch.float32)
+        delta = None
+        if four is not None:
+            four = four.detach().to(torch.float32).contiguous().view(4, 2)
+            delta = torch.empty(B, 4, 2, device=src.device, dtype=torch.float32)
+        with torch.cuda.device(src.device):
+            cabi.check(cabi.lib().bh_dltn_fwd(_ptr(p1), _ptr(p2), _ptr(field), _ptr(choice), _ptr(four), _ptr(Hn), _ptr(delta),
+                                              B, N, M, Wf, _stream()), 'bh_dltn_fwd')
+        ctx.save_for_backward(p1, p2, field, choice, four)
+        ctx.dims = (B, N, M, Wf)
+        if four is None:
+            return Hn
+        return Hn, delta
+
+    @staticmethod
+    def backward(ctx, gHn, gDelta=None):
+        p1, p2, field, choice, four = ctx.saved_tensors
+        B, N, M, Wf = ctx.dims
+        gHn = None if gHn is None else gHn.contiguous()
+        gDelta = None if gDelta is None else gDelta.contiguous()
+        g_p2 = g_field = None
+        if field is not None:
+            g_field = torch.zeros_like(field)
+        else:
+            g_p2 = torch.zeros_like(p2)
+        if gHn is not None or gDelta is not None:
+            with torch.cuda.device((field if field is not None else p2).device):
+                cabi.check(cabi.lib().bh_dltn_bwd(_ptr(p1), _ptr(p2), _ptr(field), _ptr(choice), _ptr(four), _ptr(gHn),
+                                                  _ptr(gDelta), _ptr(g_p2), _ptr(g_field), B, N, M, Wf, _stream()),
+                           'bh_dltn_bwd')
+        return None, g_p2, g_field, None, None
+
+
+def dltn(points1, points2, choice=None):
+    """Normalised N-point DLT: points [B,N,2], choice [B,M] sampled indices (None = all) -> H [B,3,3] with
+    H[2,2] = 1/(1+1e-8) normalisation as kornia.find_homography_dlt.  Gradient flows to points2 only."""
+    return _DltN.apply(points1, points2, None, choice, None)
+
+
+def dltn_field(field, choice, four_points):
+    """Perspective field [B,2,Hf,Wf] + sampled indices [B,M] -> (H [B,3,3], delta_hat [B,4,2]) in one launch
+    (forward_map_field + gather + find_homography_dlt + corner projection of the reference head)."""
+    return _DltN.apply(None, None, field, choice, four_points)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5
+# ------------------------------------------------------------------------------------------------
+PAIR_NPARAM = 32
+
+
+def pairgen_draw(batch, n_img, image_hw, rho, patch_size, max_delta, seed, step, device):
+    """Counter-based draws of HomographyNetPrep's random parameters for `batch` samples:
+    (params float64 [B,32] in the oracle/pairgen.py pack_params layout, image index int32 [B])."""
+    params = torch.empty(batch, PAIR_NPARAM, device=device, dtype=torch.float64)
+    index = torch.empty(batch, device=device, dtype=torch.int32)
+    with torch.cuda.device(device):
+        cabi.check(cabi.lib().bh_pairgen_draw(_ptr(params), _ptr(index), batch, n_img, image_hw[0], image_hw[1], rho, patch_size,
+                                              float(max_delta), int(seed) & (2 ** 64 - 1), int(step), _stream()), 'bh_pairgen_draw')
+    return params, index
+
+
+def pairgen_apply(images, index, params, patch_size, mean=0.443, std=0.129):
+    """images uint8 [n,Hi,Wi,3] (RGB, on the GPU), index int32 [B], params float64 [B,32] ->
+    (patch_1, patch_2 [B,1,P,P] float32 standardised grayscale, delta [B,4,2]).  The two patch tensors are the two
+    halves of one buffer, so the head batches them through the warp without a copy."""
+    if not images.is_cuda or images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3:
+        raise TypeError('images must be a CUDA uint8 tensor [n, H, W, 3]')
+    images = images.contiguous()
+    B, P = index.shape[0], int(patch_size)
+    buf = torch.empty(2 * B, 1, P, P, device=images.device, dtype=torch.float32)
+    delta = torch.empty(B, 4, 2, device=images.device, dtype=torch.float32)
+    p1, p2 = buf[:B], buf[B:]
+    with torch.cuda.device(images.device):
+        cabi.check(cabi.lib().bh_pairgen_apply(_ptr(images), _ptr(index.contiguous()), _ptr(params.contiguous()), _ptr(p1), _ptr(p2),
+                                               _ptr(delta), B, images.shape[0], images.shape[1], images.shape[2], P,
+                                               float(mean), float(std), _stream()), 'bh_pairgen_apply')
+    return p1, p2, delta
 
 
 # ------------------------------------------------------------------------------------------------

@@ -114,16 +114,20 @@ int bh_bihome_rescale(const float* gscale, float* g_f1w, float* g_f2w, float* g_
  *           A^T A, torch.svd, denormalise, /H33) and src/heads/PerceptualHead.py:175-178 (corner
  *           projection kornia.transform_points(H, four_points) - four_points).
  *
- * field [B,2,Hf,Wf] perspective field (x then y displacement); choice [B,N] int64 indices into the
- * Hf*Wf grid (the torch.multinomial draw); four [4,2] corner points.
- * fwd -> Hn [B,9] (H / (H33 + 1e-8)), delta [B,4,2], and `saved` [B, BH_DLTN_SAVED] floats for bwd.
- * bwd: gHn [B,9] or NULL, gDelta [B,4,2] or NULL -> gField [B,2,Hf,Wf] ACCUMULATED (caller zero-fills).
+ * Correspondences come either as point lists p1, p2 [B,N,2] (field == NULL) or, fused with the reference's
+ * forward_map_field (PerceptualHead.py:125-146), as a perspective field [B,2,Hf,Wf] (p1, p2 == NULL, N = Hf*Wf,
+ * Wf = field width): p1 = pixel grid (x, y), p2 = p1 + field[b,:,y,x].  choice [B,M] int64 = the sampled indices
+ * into the N points (the torch.multinomial draw; NULL = all N points in order, M == N).  four [4,2] corner points.
+ * fwd -> Hn [B,9] (H / (H33 + 1e-8)) and, if delta != NULL, delta [B,4,2] = proj(Hn, four) - four.
+ * bwd: gHn [B,9] or NULL, gDelta [B,4,2] or NULL -> d/d p2 ACCUMULATED (atomics; caller zero-fills) into
+ *      gP2 [B,N,2] (point mode) or gField [B,2,Hf,Wf] (field mode).  p1 carries no gradient (constants in the
+ *      reference).  The solve runs in float64 internally; the adjoint recomputes the forward.
  * ------------------------------------------------------------------------------------------- */
-#define BH_DLTN_SAVED 192
-int bh_dltn_fwd(const float* field, const int64_t* choice, const float* four, float* Hn, float* delta, float* saved,
-                int B, int N, int Hf, int Wf, bh_stream_t stream);
-int bh_dltn_bwd(const float* field, const int64_t* choice, const float* four, const float* saved, const float* gHn,
-                const float* gDelta, float* gField, int B, int N, int Hf, int Wf, bh_stream_t stream);
+int bh_dltn_fwd(const float* p1, const float* p2, const float* field, const int64_t* choice, const float* four,
+                float* Hn, float* delta, int B, int N, int M, int Wf, bh_stream_t stream);
+int bh_dltn_bwd(const float* p1, const float* p2, const float* field, const int64_t* choice, const float* four,
+                const float* gHn, const float* gDelta, float* gP2, float* gField, int B, int N, int M, int Wf,
+                bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  synthetic (PD)S-COCO pair generation on the GPU
@@ -144,7 +148,7 @@ int bh_dltn_bwd(const float* field, const int64_t* choice, const float* four, co
 int bh_pairgen_draw(double* params, int32_t* index, int B, int n_img, int Hi, int Wi, int rho, int P,
                     float max_delta, uint64_t seed, uint64_t step, bh_stream_t stream);
 int bh_pairgen_apply(const uint8_t* images, const int32_t* index, const double* params, float* patch1,
-                     float* patch2, float* delta, int B, int n_img, int Hi, int Wi, int P, float mean, float std,
+                     float* patch2, float* delta, int B, int n_img, int Hi, int Wi, int P, double mean, double std,
                      bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

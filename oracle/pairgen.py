@@ -143,3 +143,20 @@ def pack_params(qs):
         r += [float(q['pos_x']), float(q['pos_y'])] + [float(v) for v in q['delta'].reshape(-1)]
         rows.append(r)
     return np.asarray(rows, dtype=np.float64)
+
+
+def rounding_ties(q, patch_size, tol=1e-6):
+    """Patch pixels whose cv2.warpPerspective source coordinate sits on a 1/32-px rounding tie.
+
+    Integer corners and integer offsets make 32*u exactly half-integral at a handful of pixels; which way cv2 rounds
+    there depends on the last bit of the (twice inverted) homography, i.e. on the LAPACK build.  Parity checks
+    compare everything but these pixels.
+    """
+    c = patch_corners(q, patch_size)
+    H = cv2.getPerspectiveTransform(np.float32(c), np.float32(c + q['delta']))
+    ys, xs = np.mgrid[c[0, 1]:c[3, 1], c[0, 0]:c[1, 0]].astype(np.float64)
+    w = H[2, 0] * xs + H[2, 1] * ys + H[2, 2]
+    fx = 32.0 * (H[0, 0] * xs + H[0, 1] * ys + H[0, 2]) / w
+    fy = 32.0 * (H[1, 0] * xs + H[1, 1] * ys + H[1, 2]) / w
+    tie = lambda f: np.abs(f - np.floor(f) - 0.5) < tol
+    return tie(fx) | tie(fy)
