@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- training throughput of the biHomE hot path on N B200s (BASELINE.json metric / configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, oracle port, host cores)
+
+A step = one training iteration of pds-coco/zeng-bihome at 128x128, B=256 per GPU: GPU pair generation (K5) ->
+Zeng backbone (cuDNN) -> N-point DLT (K4) -> DLT-4 (K1) -> warp + pooled masks (K2) -> frozen ResNet-34 stem x4 (cuDNN)
+-> fused biHomE loss fwd+bwd (K3) -> backward (K2b, K1/K4 adjoints, cuDNN) -> Adam.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIG = os.path.join(ROOT, 'config', 'pds-coco', 'zeng-bihome-lr-1e-3.yaml')
+METRIC = 'train_image_pairs_per_sec'
+UNIT = 'image-pairs/s'
+# algorithmic bytes per image pair of the fused loss kernel (SURVEY.md 8d / DESIGN.md 4): 4 feature reads + 2 gradient
+# writes of C*h*w fp32 + 2 pooled masks in + 2 mask gradients out, C=64, h=w=32
+LOSS_BYTES_PER_PAIR = (4 + 2) * 64 * 32 * 32 * 4 + 4 * 32 * 32 * 4
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except Exception:  # noqa: BLE001
+        return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def cpu_oracle_run(steps, warmup, batch, threads):
+    """the reference's CPU path for the same config: torch backbone on CPU + oracle head (oracle/ref_train.py)"""
+    from bihome_b200 import engine
+    from bihome_b200.backbones import Rethinking
+    from oracle.ref_train import OracleModel
+    torch.set_num_threads(threads)
+    cfg = engine.load_config(CONFIG)
+    bcfg = dict(cfg['MODEL']['BACKBONE'])
+    bcfg['PRETRAINED_RESNET'] = False
+    torch.manual_seed(0)
+    model = OracleModel(Rethinking.Model(**bcfg), cfg['MODEL']['HEAD'])
+    model.train()
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=cfg['SOLVER']['LR'])
+    g = torch.Generator().manual_seed(1)
+    lo = torch.rand(batch, 1, 18, 18, generator=g)
+    p1 = torch.nn.functional.interpolate(lo, size=(128, 128), mode='bicubic', align_corners=True)
+    p2 = torch.roll(p1, shifts=(3, -2), dims=(2, 3)) + 0.05 * torch.randn(batch, 1, 128, 128, generator=g)
+
+    def step():
+        opt.zero_grad()
+        loss, _, _ = model({'patch_1': p1, 'patch_2': p2})
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 8
+    value, spp = cpu_oracle_run(args.steps, args.warmup, batch, threads)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': spp * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'pds-coco zeng-bihome-lr-1e-3 training step, 128x128 patches (reference CPU path: '
+                                   'torch CPU backbone + oracle kornia-0.5.0 head), B=%d per step' % batch},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': '%d steps of B=%d (bounded sample of the B=256 workload)' % (args.steps, batch)},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from bihome_b200 import cabi, engine
+    from bihome_b200 import functional as F
+    from bihome_b200.data import gpu_pairs
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cabi.lib()  # fail loudly if the extension is missing
+    cfg = engine.load_config(CONFIG)
+    B = args.batch
+    torch.manual_seed(0)
+    model = engine.build_model(cfg, pretrained=False).to(dev)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    opt, sched = engine.build_optimizer(cfg, model)
+    t = gpu_pairs.transform_args(cfg['DATA']['TRANSFORMS'])
+    pool = gpu_pairs.synthetic_pool(args.pool, device=dev)
+    loader = gpu_pairs.GpuPairLoader(pool, B, B * (args.steps + args.warmup + 8) * 4, seed=cfg['DATA']['SAMPLER']['TRAIN_SEED'],
+                                     rank=rank, **t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        x = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return float(x.item())
+
+    # ---------------- device-resident throughput: `value` ----------------
+    for _ in range(args.warmup):
+        engine.train_step(net, loader.next_batch(), opt, sched)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    F.enable_timing(True)
+    launches0 = cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _, _ = engine.train_step(net, loader.next_batch(), opt, sched)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = cabi.launch_count() - launches0
+    kt = F.timings()
+    F.enable_timing(False)
+    clk = clocks.stop() if rank == 0 else None
+    value = B * world * args.steps / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---------------- end to end through the public API with HOST buffers: `e2e` ----------------
+    host = []
+    for _ in range(4):
+        b = loader.next_batch()
+        host.append({k: v.cpu().pin_memory() for k, v in b.items()})
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def e2e_step(i):
+        hb = host[i % len(host)]
+        for k in stage:
+            stage[k].copy_(hb[k], non_blocking=True)
+        l, _, _ = engine.train_step(net, dict(stage), opt, sched)
+        return float(l.item())          # device -> host read of the step's loss
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant custom kernel (fused loss), timed in situ ----------------
+    peak, peak_kind = measured_peak()
+    loss_ms = kt.get('bh_bihome_fwd_bwd', [])
+    avg = sum(loss_ms) / max(len(loss_ms), 1)
+    achieved = LOSS_BYTES_PER_PAIR * B / (avg * 1e-3) / 1e9 if avg > 0 else None
+    roofline = {'bound': 'hbm', 'kernel': 'bihome_kernel<4,false> (bh_bihome_fwd_bwd)', 'achieved': achieved, 'peak': peak,
+                'peak_source': peak_kind, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
+                'traffic': args.loss_traffic, 'launch_ms': avg,
+                'algorithmic_bytes_per_launch': LOSS_BYTES_PER_PAIR * B}
+    kernels = {k: {'launches': len(v), 'avg_ms': sum(v) / len(v)} for k, v in sorted(kt.items())}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, spp = cpu_oracle_run(steps=2, warmup=1, batch=8, threads=threads)
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                        'sample': '2 steps of B=8 after 1 warm-up (%.1f s/step): torch CPU backbone + oracle kornia-0.5.0 head' % spp}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'pds-coco zeng-bihome-lr-1e-3 training step (Zeng ResNet34 perspective-field backbone + biHomE '
+                                   'loss, ResNet-34 stem extractor), 128x128 patches, B=%d per GPU, fp32 (cuDNN TF32 convs = torch default), '
+                                   'random-init weights, synthetic uint8 image pool (%d x 240x320) resident in HBM' % (B, args.pool),
+                       'global_batch': B * world, 'parallelism': 'dp%d' % world, 'channels_last': bool(args.channels_last),
+                       'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clk,
+            'kernels': kernels, 'final_loss': final_loss}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='image pairs per GPU per step')
+    ap.add_argument('--pool', type=int, default=256, help='synthetic uint8 images resident on each GPU')
+    ap.add_argument('--nchw', dest='channels_last', action='store_false',
+                    help='keep the conv stack in NCHW (default: channels-last, 2.5x faster cuDNN path on B200)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -58,8 +58,27 @@ constexpr int kLossThreads = 256;
 constexpr int kLanes = 64;  // pixel-vectors per chunk; kLossThreads / kLanes channel groups
 constexpr int kGroups = kLossThreads / kLanes;
 
-// V = pixels per thread-vector (4: NCHW with hw % 4 == 0; 1: any strides)
-template <int V, bool kInputGrads>
+// one feature element: distances, gradients
+template <bool kInputGrads>
+__device__ __forceinline__ void feat_elem(float p1w, float p2, float p2w, float p1, float k1, float k2, float& d1, float& d2,
+                                          float& ga, float& gb, float& gc, float& gd) {
+    const float e1 = p1w - p2, e2 = p2w - p1, e3 = p1 - p2;
+    const float a3 = fabsf(e3);
+    d1 += fabsf(e1) - a3;
+    d2 += fabsf(e2) - a3;
+    ga = k1 * sgn(e1);
+    gb = k2 * sgn(e2);
+    if (kInputGrads) {
+        const float s3 = (k1 + k2) * sgn(e3);
+        gc = -gb - s3;  // d/df1
+        gd = -ga + s3;  // d/df2
+    }
+}
+
+// V = pixels per thread-vector for the mask passes and the NCHW feature pass (4: hw % 4 == 0; 1: any strides).
+// kNHWC: features are channels-last with C % 4 == 0 and C/4 a power of two: a group of min(32, C/4) lanes owns a pixel,
+// every lane streams float4 channel quads (512 contiguous bytes per warp), the channel sum is a shuffle reduction.
+template <int V, bool kInputGrads, bool kNHWC>
 __global__ void __launch_bounds__(kLossThreads) bihome_kernel(const LossArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = static_cast<int>(cluster.num_blocks());
@@ -107,79 +126,118 @@ __global__ void __launch_bounds__(kLossThreads) bihome_kernel(const LossArgs a) 
 
     // ---- phase 1: the streaming pass ---------------------------------------------------------------
     float num[2] = {0.0f, 0.0f};
-    for (int cb = v0; cb < v1; cb += kLanes) {
-        const int pv = cb + lane;
-        const bool live = pv < v1;
-        float W1[V], W2[V], d1[V], d2[V];
-#pragma unroll
-        for (int i = 0; i < V; ++i) W1[i] = W2[i] = d1[i] = d2[i] = 0.0f;
-        if (live) {
-            float x1[V], x2[V], y1[V], y2[V];
-            ldv_cached<V>(a.m1w + mbase + pv * V, x1);
-            ldv_cached<V>(a.m2w + mbase + pv * V, x2);
-#pragma unroll
-            for (int i = 0; i < V; ++i) y1[i] = y2[i] = 1.0f;
-            if (a.m1) ldv_cached<V>(a.m1 + mbase + pv * V, y1);
-            if (a.m2) ldv_cached<V>(a.m2 + mbase + pv * V, y2);
-#pragma unroll
-            for (int i = 0; i < V; ++i) { W1[i] = x1[i] * y2[i]; W2[i] = x2[i] * y1[i]; }
-            const long long poff = fbase + static_cast<long long>(pv) * V * a.sp;
+    if (kNHWC) {
+        const int quads = a.C >> 2;
+        const int tpp = quads < 32 ? quads : 32;          // lanes per pixel (power of two)
+        const int per_lane = quads / tpp;                 // channel quads per lane
+        const int gl = tid & (tpp - 1), pg = tid / tpp, gpp = kLossThreads / tpp;
+        const int p0 = v0 * V, p1e = v1 * V;
+        const int iters = (p1e - p0 + gpp - 1) / gpp;
+        for (int it = 0; it < iters; ++it) {
+            const int p = p0 + it * gpp + pg;
+            const bool live = p < p1e;
+            float W1 = 0.0f, W2 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+            if (live) {
+                const float x1 = __ldg(a.m1w + mbase + p), x2 = __ldg(a.m2w + mbase + p);
+                const float y1 = a.m1 ? __ldg(a.m1 + mbase + p) : 1.0f, y2 = a.m2 ? __ldg(a.m2 + mbase + p) : 1.0f;
+                W1 = x1 * y2;
+                W2 = x2 * y1;
+                const float k1 = W1 * inv1, k2 = W2 * inv2;
+                const long long poff = fbase + static_cast<long long>(p) * a.C;
 #pragma unroll 2
-            for (int c = grp; c < a.C; c += kGroups) {
-                const long long o = poff + c * a.sc;
-                float p1w[V], p2[V], p2w[V], p1[V];
-                ldv<V>(a.f1w + o, p1w);
-                ldv<V>(a.f2 + o, p2);
-                ldv<V>(a.f2w + o, p2w);
-                ldv<V>(a.f1 + o, p1);
-                float ga[V], gb[V], gc[V], gd[V];
+                for (int k = 0; k < per_lane; ++k) {
+                    const long long o = poff + (gl + k * tpp) * 4;
+                    float p1w[4], p2[4], p2w[4], p1[4], ga[4], gb[4], gc[4], gd[4];
+                    ldv<4>(a.f1w + o, p1w);
+                    ldv<4>(a.f2 + o, p2);
+                    ldv<4>(a.f2w + o, p2w);
+                    ldv<4>(a.f1 + o, p1);
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    const float e1 = p1w[i] - p2[i], e2 = p2w[i] - p1[i], e3 = p1[i] - p2[i];
-                    const float a3 = fabsf(e3);
-                    d1[i] += fabsf(e1) - a3;
-                    d2[i] += fabsf(e2) - a3;
-                    const float k1 = W1[i] * inv1, k2 = W2[i] * inv2;
-                    ga[i] = k1 * sgn(e1);
-                    gb[i] = k2 * sgn(e2);
+                    for (int i = 0; i < 4; ++i)
+                        feat_elem<kInputGrads>(p1w[i], p2[i], p2w[i], p1[i], k1, k2, d1, d2, ga[i], gb[i], gc[i], gd[i]);
+                    stv<4>(a.g_f1w + o, ga);
+                    stv<4>(a.g_f2w + o, gb);
                     if (kInputGrads) {
-                        const float s3 = (k1 + k2) * sgn(e3);
-                        gc[i] = -gb[i] - s3;  // d/df1
-                        gd[i] = -ga[i] + s3;  // d/df2
+                        stv<4>(a.g_f1 + o, gc);
+                        stv<4>(a.g_f2 + o, gd);
                     }
                 }
-                stv<V>(a.g_f1w + o, ga);
-                stv<V>(a.g_f2w + o, gb);
-                if (kInputGrads) {
-                    stv<V>(a.g_f1 + o, gc);
-                    stv<V>(a.g_f2 + o, gd);
+            }
+            for (int o = tpp >> 1; o > 0; o >>= 1) {
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (live && gl == 0) {
+                num[0] = fmaf(W1, d1, num[0]);
+                num[1] = fmaf(W2, d2, num[1]);
+                a.g_m1w[mbase + p] = d1;  // parked D, see phase 3
+                a.g_m2w[mbase + p] = d2;
+            }
+        }
+    } else {
+        for (int cb = v0; cb < v1; cb += kLanes) {
+            const int pv = cb + lane;
+            const bool live = pv < v1;
+            float W1[V], W2[V], d1[V], d2[V];
+    #pragma unroll
+            for (int i = 0; i < V; ++i) W1[i] = W2[i] = d1[i] = d2[i] = 0.0f;
+            if (live) {
+                float x1[V], x2[V], y1[V], y2[V];
+                ldv_cached<V>(a.m1w + mbase + pv * V, x1);
+                ldv_cached<V>(a.m2w + mbase + pv * V, x2);
+    #pragma unroll
+                for (int i = 0; i < V; ++i) y1[i] = y2[i] = 1.0f;
+                if (a.m1) ldv_cached<V>(a.m1 + mbase + pv * V, y1);
+                if (a.m2) ldv_cached<V>(a.m2 + mbase + pv * V, y2);
+    #pragma unroll
+                for (int i = 0; i < V; ++i) { W1[i] = x1[i] * y2[i]; W2[i] = x2[i] * y1[i]; }
+                const long long poff = fbase + static_cast<long long>(pv) * V * a.sp;
+    #pragma unroll 2
+                for (int c = grp; c < a.C; c += kGroups) {
+                    const long long o = poff + c * a.sc;
+                    float p1w[V], p2[V], p2w[V], p1[V];
+                    ldv<V>(a.f1w + o, p1w);
+                    ldv<V>(a.f2 + o, p2);
+                    ldv<V>(a.f2w + o, p2w);
+                    ldv<V>(a.f1 + o, p1);
+                    float ga[V], gb[V], gc[V], gd[V];
+    #pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        feat_elem<kInputGrads>(p1w[i], p2[i], p2w[i], p1[i], W1[i] * inv1, W2[i] * inv2, d1[i], d2[i], ga[i], gb[i],
+                                               gc[i], gd[i]);
+                    stv<V>(a.g_f1w + o, ga);
+                    stv<V>(a.g_f2w + o, gb);
+                    if (kInputGrads) {
+                        stv<V>(a.g_f1 + o, gc);
+                        stv<V>(a.g_f2 + o, gd);
+                    }
                 }
             }
-        }
-#pragma unroll
-        for (int i = 0; i < V; ++i) { dsm[grp][lane][i] = d1[i]; dsm[grp][lane][V + i] = d2[i]; }
-        __syncthreads();
-        if (grp == 0 && live) {
-            float D1[V], D2[V];
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-                float t1 = 0.0f, t2 = 0.0f;
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) { t1 += dsm[g][lane][i]; t2 += dsm[g][lane][V + i]; }
-                D1[i] = t1; D2[i] = t2;
-                num[0] = fmaf(W1[i], t1, num[0]);
-                num[1] = fmaf(W2[i], t2, num[1]);
+    #pragma unroll
+            for (int i = 0; i < V; ++i) { dsm[grp][lane][i] = d1[i]; dsm[grp][lane][V + i] = d2[i]; }
+            __syncthreads();
+            if (grp == 0 && live) {
+                float D1[V], D2[V];
+    #pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float t1 = 0.0f, t2 = 0.0f;
+    #pragma unroll
+                    for (int g = 0; g < kGroups; ++g) { t1 += dsm[g][lane][i]; t2 += dsm[g][lane][V + i]; }
+                    D1[i] = t1; D2[i] = t2;
+                    num[0] = fmaf(W1[i], t1, num[0]);
+                    num[1] = fmaf(W2[i], t2, num[1]);
+                }
+                // park D in the mask-gradient buffers; phase 3 turns it into the gradient in place
+                if (V == 4) {
+                    *reinterpret_cast<float4*>(a.g_m1w + mbase + pv * V) = make_float4(D1[0], D1[1], D1[2], D1[3]);
+                    *reinterpret_cast<float4*>(a.g_m2w + mbase + pv * V) = make_float4(D2[0], D2[1], D2[2], D2[3]);
+                } else {
+                    a.g_m1w[mbase + pv] = D1[0];
+                    a.g_m2w[mbase + pv] = D2[0];
+                }
             }
-            // park D in the mask-gradient buffers; phase 3 turns it into the gradient in place
-            if (V == 4) {
-                *reinterpret_cast<float4*>(a.g_m1w + mbase + pv * V) = make_float4(D1[0], D1[1], D1[2], D1[3]);
-                *reinterpret_cast<float4*>(a.g_m2w + mbase + pv * V) = make_float4(D2[0], D2[1], D2[2], D2[3]);
-            } else {
-                a.g_m1w[mbase + pv] = D1[0];
-                a.g_m2w[mbase + pv] = D2[0];
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- phase 2: numerators of the whole sample via DSMEM -------------------------------------------
@@ -257,7 +315,7 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-template <int V, bool G>
+template <int V, bool G, bool N>
 int launch_bihome(const LossArgs& a, int CL, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(a.B) * CL);
@@ -271,7 +329,7 @@ int launch_bihome(const LossArgs& a, int CL, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, bihome_kernel<V, G>, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, bihome_kernel<V, G, N>, a);
     ++g_launch_count;
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaGetLastError();
@@ -297,7 +355,7 @@ extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* 
     a.g_m1w = g_m1w; a.g_m2w = g_m2w; a.gH12 = gH12; a.gH21 = gH21; a.B = B; a.C = C; a.hw = h * w;
     a.sc = channels_last ? 1 : a.hw;
     a.sp = channels_last ? C : 1;
-    const bool vec = !channels_last && (a.hw % 4) == 0 && aligned16(f1) && aligned16(f2) && aligned16(f1w) && aligned16(f2w) &&
+    const bool vec = (a.hw % 4) == 0 && aligned16(f1) && aligned16(f2) && aligned16(f1w) && aligned16(f2w) &&
                      aligned16(g_f1w) && aligned16(g_f2w) && aligned16(m1w) && aligned16(m2w) && aligned16(g_m1w) &&
                      aligned16(g_m2w) && (!m1 || aligned16(m1)) && (!m2 || aligned16(m2)) && (!g_f1 || aligned16(g_f1)) &&
                      (!g_f2 || aligned16(g_f2));
@@ -306,8 +364,14 @@ extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* 
     int CL = (B >= 2 * kNumSMs) ? 2 : (B >= kNumSMs ? 4 : 8);
     while (CL > 1 && nvec / CL < kLanes) CL >>= 1;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    if (vec) return g_f1 ? launch_bihome<4, true>(a, CL, stream) : launch_bihome<4, false>(a, CL, stream);
-    return g_f1 ? launch_bihome<1, true>(a, CL, stream) : launch_bihome<1, false>(a, CL, stream);
+    if (channels_last) {
+        const int quads = C / 4;
+        const bool pow2 = (C % 4) == 0 && quads > 0 && (quads & (quads - 1)) == 0 && quads <= 256;
+        if (vec && pow2) return g_f1 ? launch_bihome<4, true, true>(a, CL, stream) : launch_bihome<4, false, true>(a, CL, stream);
+        return g_f1 ? launch_bihome<1, true, false>(a, CL, stream) : launch_bihome<1, false, false>(a, CL, stream);
+    }
+    if (vec) return g_f1 ? launch_bihome<4, true, false>(a, CL, stream) : launch_bihome<4, false, false>(a, CL, stream);
+    return g_f1 ? launch_bihome<1, true, false>(a, CL, stream) : launch_bihome<1, false, false>(a, CL, stream);
 }
 
 extern "C" int bh_bihome_rescale(const float* gscale, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2, float* g_m1w,

@@ -1,0 +1,53 @@
+"""Config-driven model factory and training step (reference train.py:544-757 main, :284-429 train_one_epoch).
+
+The YAML contract is the reference's: MODEL.BACKBONE / MODEL.HEAD are passed as **kwargs to
+``<package>.backbones.<NAME>.Model`` and ``<package>.heads.<NAME>.Model(backbone, **kwargs)``; the model is
+``nn.Sequential(backbone, head)`` and the batch is one dict flowing through both.
+"""
+import importlib
+
+import torch
+import yaml
+
+
+def load_config(path):
+    with open(path, 'r') as f:
+        return yaml.full_load(f)
+
+
+def build_model(config, pretrained=None):
+    """nn.Sequential(backbone, head) from a reference-style config dict.  ``pretrained=False`` forces random init
+    of both the backbone trunk and the frozen extractor (no network on the GPU boxes)."""
+    bcfg, hcfg = dict(config['MODEL']['BACKBONE']), dict(config['MODEL']['HEAD'])
+    if pretrained is not None:
+        bcfg['PRETRAINED_RESNET'] = bool(pretrained) and bcfg.get('PRETRAINED_RESNET', False)
+        hcfg['AUXILIARY_RESNET_PRETRAINED'] = bool(pretrained)
+    backbone = importlib.import_module('bihome_b200.backbones.{}'.format(bcfg['NAME'])).Model(**bcfg)
+    head = importlib.import_module('bihome_b200.heads.{}'.format(hcfg['NAME'])).Model(backbone, **hcfg)
+    return torch.nn.Sequential(backbone, head)
+
+
+def build_optimizer(config, model, capturable=False):
+    s = config['SOLVER']
+    if s['OPTIMIZER'] != 'Adam':
+        raise NotImplementedError('I do not have this solver implemented yet.')
+    wd = float(s['L2_WEIGHT_DECAY']) if 'L2_WEIGHT_DECAY' in s else 0
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=s['LR'], betas=(s['MOMENTUM_1'], s['MOMENTUM_2']), weight_decay=wd,
+                           capturable=capturable, foreach=True)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=s['MILESTONES'], gamma=s['LR_DECAY'])
+    return opt, sched
+
+
+def train_step(model, data, optimizer, scheduler=None, gradient_clip=-1):
+    """one iteration of the reference's hot loop (train.py:305-387) for the string losses ('biHomE', ...):
+    returns (loss, delta_gt, delta_hat) as device tensors -- no host sync."""
+    optimizer.zero_grad(set_to_none=True)
+    loss, delta_gt, delta_hat = model(data)
+    loss.backward()
+    if gradient_clip > 0:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), gradient_clip)
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    return loss, delta_gt, delta_hat

@@ -22,6 +22,41 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# In-situ kernel timing for bench.py: when enabled, every C-ABI launch is bracketed by CUDA events recorded on the
+# launching stream; timings() returns {entry point: [ms, ...]} after a synchronize.  Off by default (zero overhead).
+_TIMING = None
+
+
+def enable_timing(on=True):
+    global _TIMING
+    _TIMING = [] if on else None
+
+
+def timings():
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in (_TIMING or []):
+        out.setdefault(name, []).append(e0.elapsed_time(e1))
+    return out
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _TIMING.append((self.name, self.e0, e1))
+        return False
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -59,7 +94,7 @@ class _Dlt4(torch.autograd.Function):
             corners = corners.contiguous()
         B = delta.shape[0]
         H = torch.empty(B, 3, 3, device=delta.device, dtype=torch.float32)
-        with torch.cuda.device(delta.device):
+        with torch.cuda.device(delta.device), _timed('bh_dlt4_fwd'):
             cabi.check(cabi.lib().bh_dlt4_fwd(_ptr(corners), _ptr(delta), _ptr(H), B, float(W), float(Hh), _stream()),
                        'bh_dlt4_fwd')
         ctx.save_for_backward(delta, corners, H)
@@ -74,7 +109,7 @@ class _Dlt4(torch.autograd.Function):
         g_delta = torch.empty_like(delta)
         want_c = corners is not None and ctx.needs_input_grad[1]
         g_corners = torch.empty_like(corners) if want_c else None
-        with torch.cuda.device(delta.device):
+        with torch.cuda.device(delta.device), _timed('bh_dlt4_bwd'):
             cabi.check(cabi.lib().bh_dlt4_bwd(_ptr(corners), _ptr(delta), _ptr(H), _ptr(gH), _ptr(g_delta), _ptr(g_corners),
                                               B, ctx.size[0], ctx.size[1], _stream()), 'bh_dlt4_bwd')
         return g_delta, g_corners, None, None
@@ -120,7 +155,7 @@ class _Warp(torch.autograd.Function):
             Hs, Ws = src_hw
         if pool:
             mask = torch.empty((B, out_h // pool, out_w // pool), device=Hc.device, dtype=torch.float32)
-        with torch.cuda.device(Hc.device):
+        with torch.cuda.device(Hc.device), _timed('bh_warp_fwd'):
             cabi.check(lib.bh_warp_fwd(_ptr(src), _ptr(Hc), _ptr(out), _ptr(mask), B, C, Hs, Ws, out_h, out_w,
                                        int(pool or 0), nhwc, _stream()), 'bh_warp_fwd')
         ctx.save_for_backward(src, Hc)
@@ -154,7 +189,7 @@ class _Warp(torch.autograd.Function):
             g_src = torch.zeros_like(src)
         nbytes = lib.bh_warp_bwd_workspace_bytes(B, C, Hs, Ws, Ho, Wo, nhwc)
         ws = torch.empty(max(int(nbytes), 16), device=Hc.device, dtype=torch.uint8)
-        with torch.cuda.device(Hc.device):
+        with torch.cuda.device(Hc.device), _timed('bh_warp_bwd'):
             cabi.check(lib.bh_warp_bwd(_ptr(src if g_out is not None else None), _ptr(Hc), _ptr(g_out), _ptr(g_mask), _ptr(gH),
                                        _ptr(g_src), B, C, Hs, Ws, Ho, Wo, pool, nhwc, _ptr(ws), int(nbytes), _stream()),
                        'bh_warp_bwd')
@@ -207,7 +242,7 @@ class _BihomeLoss(torch.autograd.Function):
         g_m1w, g_m2w = torch.empty_like(m1w), torch.empty_like(m2w)
         gH12 = torch.empty(B, 9, device=dev, dtype=torch.float32)
         gH21 = torch.empty(B, 9, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed('bh_bihome_fwd_bwd'):
             cabi.check(cabi.lib().bh_bihome_fwd_bwd(
                 _ptr(f1), _ptr(f2), _ptr(f1w), _ptr(f2w), _ptr(m1), _ptr(m2), _ptr(m1w), _ptr(m2w), _ptr(H12c), _ptr(H21c),
                 float(mu), _ptr(loss), _ptr(parts), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_m1w),
@@ -227,7 +262,7 @@ class _BihomeLoss(torch.autograd.Function):
         ctx.grads = None
         B, C, h, w = ctx.dims
         g_loss = g_loss.contiguous().float()
-        with torch.cuda.device(g_f1w.device):
+        with torch.cuda.device(g_f1w.device), _timed('bh_bihome_rescale'):
             cabi.check(cabi.lib().bh_bihome_rescale(_ptr(g_loss), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_m1w),
                                                     _ptr(g_m2w), _ptr(gH12), _ptr(gH21), B, C, h, w, _stream()),
                        'bh_bihome_rescale')
@@ -271,7 +306,7 @@ class _DltN(torch.autograd.Function):
         if four is not None:
             four = four.detach().to(torch.float32).contiguous().view(4, 2)
             delta = torch.empty(B, 4, 2, device=src.device, dtype=torch.float32)
-        with torch.cuda.device(src.device):
+        with torch.cuda.device(src.device), _timed('bh_dltn_fwd'):
             cabi.check(cabi.lib().bh_dltn_fwd(_ptr(p1), _ptr(p2), _ptr(field), _ptr(choice), _ptr(four), _ptr(Hn), _ptr(delta),
                                               B, N, M, Wf, _stream()), 'bh_dltn_fwd')
         ctx.save_for_backward(p1, p2, field, choice, four)
@@ -292,7 +327,7 @@ class _DltN(torch.autograd.Function):
         else:
             g_p2 = torch.zeros_like(p2)
         if gHn is not None or gDelta is not None:
-            with torch.cuda.device((field if field is not None else p2).device):
+            with torch.cuda.device((field if field is not None else p2).device), _timed('bh_dltn_bwd'):
                 cabi.check(cabi.lib().bh_dltn_bwd(_ptr(p1), _ptr(p2), _ptr(field), _ptr(choice), _ptr(four), _ptr(gHn),
                                                   _ptr(gDelta), _ptr(g_p2), _ptr(g_field), B, N, M, Wf, _stream()),
                            'bh_dltn_bwd')
@@ -322,7 +357,7 @@ def pairgen_draw(batch, n_img, image_hw, rho, patch_size, max_delta, seed, step,
     (params float64 [B,32] in the oracle/pairgen.py pack_params layout, image index int32 [B])."""
     params = torch.empty(batch, PAIR_NPARAM, device=device, dtype=torch.float64)
     index = torch.empty(batch, device=device, dtype=torch.int32)
-    with torch.cuda.device(device):
+    with torch.cuda.device(device), _timed('bh_pairgen_draw'):
         cabi.check(cabi.lib().bh_pairgen_draw(_ptr(params), _ptr(index), batch, n_img, image_hw[0], image_hw[1], rho, patch_size,
                                               float(max_delta), int(seed) & (2 ** 64 - 1), int(step), _stream()), 'bh_pairgen_draw')
     return params, index
@@ -339,7 +374,7 @@ def pairgen_apply(images, index, params, patch_size, mean=0.443, std=0.129):
     buf = torch.empty(2 * B, 1, P, P, device=images.device, dtype=torch.float32)
     delta = torch.empty(B, 4, 2, device=images.device, dtype=torch.float32)
     p1, p2 = buf[:B], buf[B:]
-    with torch.cuda.device(images.device):
+    with torch.cuda.device(images.device), _timed('bh_pairgen_apply'):
         cabi.check(cabi.lib().bh_pairgen_apply(_ptr(images), _ptr(index.contiguous()), _ptr(params.contiguous()), _ptr(p1), _ptr(p2),
                                                _ptr(delta), B, images.shape[0], images.shape[1], images.shape[2], P,
                                                float(mean), float(std), _stream()), 'bh_pairgen_apply')
@@ -353,6 +388,6 @@ def mace(delta_gt, delta_hat):
     _need_cuda_f32('delta_hat', delta_hat)
     a, b = delta_gt.detach().contiguous(), delta_hat.detach().contiguous()
     out = torch.empty(1, device=a.device, dtype=torch.float32)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _timed('bh_mace'):
         cabi.check(cabi.lib().bh_mace(_ptr(a), _ptr(b), _ptr(out), a.numel() // 8, _stream()), 'bh_mace')
     return out[0]

@@ -64,7 +64,12 @@ class AuxiliaryResnet(nn.Module):
             # reference: x.repeat(1, 3, 1, 1) then conv1 (:52-55).  conv1 over three identical channels equals a
             # one-channel conv with the kernel summed over its input channels: a third of the bytes and FLOPs.
             c = r.conv1
-            x = nn.functional.conv2d(x, c.weight.sum(dim=1, keepdim=True), c.bias, c.stride, c.padding, c.dilation)
+            w = c.weight.sum(dim=1, keepdim=True)
+            if c.weight.is_contiguous(memory_format=torch.channels_last) and not c.weight.is_contiguous():
+                # keep the extractor in NHWC when the model was converted: a [64,1,7,7] tensor is layout-ambiguous
+                w = w.contiguous(memory_format=torch.channels_last)
+                x = x.contiguous(memory_format=torch.channels_last)
+            x = nn.functional.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation)
         else:
             x = r.conv1(x)
         x = r.maxpool(r.relu(r.bn1(x)))

@@ -259,7 +259,10 @@ def _loss_oracle(f, m1w, m2w, m1, m2, H12, H21, mu):
     (150, 16, 16, 16, False, False, False),   # cluster of 4
     (300, 8, 16, 16, False, True, False),     # cluster of 2, user masks
     (4, 5, 7, 9, False, False, True),         # odd: scalar path, gradients w.r.t. f1/f2 too
-    (4, 16, 8, 8, True, True, True),          # channels-last (scalar strides)
+    (4, 16, 8, 8, True, True, True),          # channels-last vec4, 4 lanes per pixel
+    (5, 64, 32, 32, True, False, False),      # channels-last, north-star shape (16 lanes per pixel)
+    (3, 256, 8, 8, True, False, False),       # channels-last, 2 quads per lane
+    (3, 24, 6, 6, True, False, True),         # channels-last, C/4 not a power of two -> scalar strides
 ])
 def test_bihome_loss_vs_oracle(F, B, C, h, w, nhwc, user_masks, in_grads):
     mu = 0.01
