@@ -191,11 +191,11 @@ def run_ours(args):
 
     # ---------------- end to end through the public API with HOST buffers: `e2e` ----------------
     host = []
-    for _ in range(4):
+    for _ in range(0 if args.no_e2e else 4):
         b = loader.next_batch()
         host.append({k: v.cpu().pin_memory() for k, v in b.items()})
-    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()} if host else {}
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values()) if host else 0
 
     def e2e_step(i):
         hb = host[i % len(host)]
@@ -203,16 +203,18 @@ def run_ours(args):
             stage[k].copy_(hb[k], non_blocking=True)
         l, _, _ = engine.train_step(net, dict(stage), opt, sched)
         return float(l.item())          # device -> host read of the step's loss
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+    ms_e2e, e2e_value = None, None
+    if host:
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -246,7 +248,7 @@ def run_ours(args):
                        'global_batch': B * world, 'parallelism': 'dp%d' % world, 'channels_last': bool(args.channels_last),
                        'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': ms_e2e / args.steps},
+                    'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clk,
             'kernels': kernels, 'final_loss': final_loss}
     print(json.dumps(line))
@@ -265,6 +267,7 @@ def main():
     ap.add_argument('--nchw', dest='channels_last', action='store_false',
                     help='keep the conv stack in NCHW (default: channels-last, 2.5x faster cuDNN path on B200)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer phase (profiling runs)')
     ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

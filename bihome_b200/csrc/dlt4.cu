@@ -12,51 +12,6 @@
 
 namespace bh {
 
-// Solve the 8x8 system whose row `sub` = (a[0..7] | rhs) lives in lane `sub` of an aligned 8-lane group.
-// On return x[0..7] holds the solution in every lane of the group.
-__device__ __forceinline__ void solve8(double (&a)[8], double rhs, int sub, double (&x)[8]) {
-    constexpr unsigned kFull = 0xffffffffu;
-    bool used = false;
-    int piv_lane[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        // partial pivoting: largest |a[r][k]| among rows not yet used as a pivot (lowest lane wins ties)
-        double best = used ? -1.0 : fabs(a[k]);
-        int who = sub;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            const double ob = __shfl_xor_sync(kFull, best, o, 8);
-            const int ow = __shfl_xor_sync(kFull, who, o, 8);
-            if (ob > best || (ob == best && ow < who)) {
-                best = ob;
-                who = ow;
-            }
-        }
-        piv_lane[k] = who;
-        double prow[8];
-#pragma unroll
-        for (int j = k; j < 8; ++j) prow[j] = __shfl_sync(kFull, a[j], who, 8);
-        const double prhs = __shfl_sync(kFull, rhs, who, 8);
-        if (sub == who) {
-            used = true;
-        } else if (!used) {
-            const double f = a[k] / prow[k];
-#pragma unroll
-            for (int j = k + 1; j < 8; ++j) a[j] = fma(-f, prow[j], a[j]);
-            rhs = fma(-f, prhs, rhs);
-            a[k] = 0.0;
-        }
-    }
-    // back substitution: the row that was pivot k has zeros left of column k
-#pragma unroll
-    for (int k = 7; k >= 0; --k) {
-        double acc = rhs;
-#pragma unroll
-        for (int j = k + 1; j < 8; ++j) acc = fma(-a[j], x[j], acc);
-        x[k] = __shfl_sync(kFull, acc / a[k], piv_lane[k], 8);
-    }
-}
-
 __device__ __forceinline__ void load_corner(const float* __restrict__ corners, int b, int i, float W, float Hh, float& x,
                                             float& y) {
     if (corners != nullptr) {

@@ -65,7 +65,7 @@ __device__ __forceinline__ void photometric(const Photo& q, float& r, float& g, 
         r = g = b = v;
     } else {
         float hh = h * 0.016666668f;  // 6/360 as float
-        hh = fmodf(hh, 6.0f);
+        if (hh >= 6.0f) hh -= 6.0f;  // == fmodf(hh, 6) on [0, 12): h is in [0, 360] here
         int sector = static_cast<int>(floorf(hh));
         hh -= static_cast<float>(sector);
         if (static_cast<unsigned>(sector) >= 6u) { sector = 0; hh = 0.0f; }
@@ -100,34 +100,6 @@ __device__ __forceinline__ float to_input(float r, float g, float b, double mean
     return static_cast<float>((static_cast<double>(scaled) - mean) / stdv);
 }
 
-// cv2.getPerspectiveTransform: 8x8 system in double, Gaussian elimination with partial pivoting (thread 0 only)
-__device__ void perspective_from_corners(const double* cx, const double* cy, const double* ux, const double* uy, double* M) {
-    double A[8][9];
-    for (int i = 0; i < 4; ++i) {
-        double* a = A[i];
-        double* c = A[i + 4];
-        a[0] = cx[i]; a[1] = cy[i]; a[2] = 1; a[3] = 0; a[4] = 0; a[5] = 0; a[6] = -cx[i] * ux[i]; a[7] = -cy[i] * ux[i]; a[8] = ux[i];
-        c[0] = 0; c[1] = 0; c[2] = 0; c[3] = cx[i]; c[4] = cy[i]; c[5] = 1; c[6] = -cx[i] * uy[i]; c[7] = -cy[i] * uy[i]; c[8] = uy[i];
-    }
-    for (int k = 0; k < 8; ++k) {
-        int piv = k;
-        for (int r = k + 1; r < 8; ++r)
-            if (fabs(A[r][k]) > fabs(A[piv][k])) piv = r;
-        if (piv != k)
-            for (int j = 0; j < 9; ++j) { const double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
-        for (int r = k + 1; r < 8; ++r) {
-            const double f = A[r][k] / A[k][k];
-            for (int j = k; j < 9; ++j) A[r][j] -= f * A[k][j];
-        }
-    }
-    for (int k = 7; k >= 0; --k) {
-        double acc = A[k][8];
-        for (int j = k + 1; j < 8; ++j) acc -= A[k][j] * M[j];
-        M[k] = acc / A[k][k];
-    }
-    M[8] = 1.0;
-}
-
 __global__ void __launch_bounds__(256)
     pairgen_apply_kernel(const uint8_t* __restrict__ images, const int32_t* __restrict__ index, const double* __restrict__ params,
                          float* __restrict__ patch1, float* __restrict__ patch2, float* __restrict__ delta, int n_img, int Hi,
@@ -139,12 +111,20 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const int pos_x = static_cast<int>(prm[22]), pos_y = static_cast<int>(prm[23]);
     const int x0 = pos_x - P / 2, y0 = pos_y - P / 2;
-    if (threadIdx.x == 0) {
-        const double cx[4] = {double(x0), double(x0 + P), double(x0 + P), double(x0)};
-        const double cy[4] = {double(y0), double(y0), double(y0 + P), double(y0 + P)};
-        double ux[4], uy[4];
-        for (int i = 0; i < 4; ++i) { ux[i] = cx[i] + prm[24 + 2 * i]; uy[i] = cy[i] + prm[25 + 2 * i]; }
-        perspective_from_corners(cx, cy, ux, uy, M);
+    if (threadIdx.x < 32) {
+        // cv2.getPerspectiveTransform twin: 8x8 system in float64, partial pivoting, rows spread over 8 lanes
+        const int sub = threadIdx.x & 7, i = sub >> 1;
+        const double cx = (i == 1 || i == 2) ? double(x0 + P) : double(x0), cy = (i >= 2) ? double(y0 + P) : double(y0);
+        const double ux = cx + prm[24 + 2 * i], uy = cy + prm[25 + 2 * i];
+        double a[8], rhs, sol[8];
+        if ((sub & 1) == 0) { a[0] = cx; a[1] = cy; a[2] = 1; a[3] = 0; a[4] = 0; a[5] = 0; a[6] = -cx * ux; a[7] = -cy * ux; rhs = ux; }
+        else { a[0] = 0; a[1] = 0; a[2] = 0; a[3] = cx; a[4] = cy; a[5] = 1; a[6] = -cx * uy; a[7] = -cy * uy; rhs = uy; }
+        solve8(a, rhs, sub, sol);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) M[k] = sol[k];
+            M[8] = 1.0;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < 8) delta[b * 8 + threadIdx.x] = static_cast<float>(prm[24 + threadIdx.x]);
     __syncthreads();
@@ -283,7 +263,7 @@ extern "C" int bh_pairgen_apply(const uint8_t* images, const int32_t* index, con
                                 bh_stream_t stream) {
     if (!images || !index || !params || !patch1 || !patch2 || !delta) return BH_E_NULL;
     if (B <= 0 || n_img <= 0 || Hi <= 0 || Wi <= 0 || P <= 0 || std == 0.0) return BH_E_SHAPE;
-    int gx = (P * P + 255) / 256;
+    int gx = (P * P + 256 * 8 - 1) / (256 * 8);  // ~8 pixels per thread: the per-block homography solve is amortised
     if (gx > 64) gx = 64;
     dim3 grid(gx, B);
     bh::pairgen_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(images, index, params, patch1, patch2,

@@ -52,6 +52,11 @@ def load_pool(directory, device='cuda', limit=None):
     return torch.from_numpy(np.stack(arrs)).to(device)
 
 
+def rank_seed(seed, rank):
+    """rank-seeded generator key: ranks of a data-parallel job draw disjoint streams"""
+    return (int(seed) * 1000003 + int(rank)) & (2 ** 63 - 1)
+
+
 class GpuPairLoader:
     """Iterable of batch dicts; ``len`` = steps per epoch (reference DatasetSampler.__len__)."""
 
@@ -62,7 +67,7 @@ class GpuPairLoader:
         self.batch_size = int(batch_size)
         self.steps = int(samples_per_epoch) // self.batch_size
         self.cfg = dict(rho=int(rho), patch_size=int(patch_size), max_delta=float(max_delta), mean=float(mean), std=float(std))
-        self.seed = (int(seed) * 1000003 + int(rank)) & (2 ** 63 - 1)   # rank-seeded: ranks draw disjoint streams
+        self.seed = rank_seed(seed, rank)
         self.step = 0
 
     def __len__(self):

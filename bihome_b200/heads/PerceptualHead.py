@@ -66,9 +66,10 @@ class AuxiliaryResnet(nn.Module):
             c = r.conv1
             w = c.weight.sum(dim=1, keepdim=True)
             if c.weight.is_contiguous(memory_format=torch.channels_last) and not c.weight.is_contiguous():
-                # keep the extractor in NHWC when the model was converted: a [64,1,7,7] tensor is layout-ambiguous
-                w = w.contiguous(memory_format=torch.channels_last)
-                x = x.contiguous(memory_format=torch.channels_last)
+                # keep the extractor in NHWC when the model was converted: a [64,1,k,k] tensor is layout-ambiguous,
+                # explicit channels-last strides make cuDNN pick its NHWC kernels (and bn1/maxpool follow)
+                k_h, k_w = w.shape[-2], w.shape[-1]
+                w = w.as_strided(w.shape, (k_h * k_w, 1, k_w, 1))
             x = nn.functional.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation)
         else:
             x = r.conv1(x)

@@ -1,0 +1,155 @@
+"""Warp + biHomE-loss kernel microbenchmark (BASELINE.json configs[3]): batch 64-4096, patch 128-512, C = 64-256.
+
+    python tools/microbench.py                 # north-star shape + a small sweep, JSON lines
+    python tools/microbench.py --sweep         # the full sweep (shapes over ~60 GB footprint are skipped)
+    python tools/microbench.py --once          # one launch of every kernel at B=256, P=128 (the command ncu profiles)
+
+Every timing: CUDA events on the launching stream, >= 3 warm-up launches, the L2 flushed (256 MB memset) before each
+timed launch, mean of `--iters` launches.  Algorithmic bytes are those of SURVEY.md 8(d) / DESIGN.md section 4.
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bihome_b200.functional as F
+
+PEAK = 6460.5
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:  # noqa: BLE001
+    pass
+
+
+class Timer:
+    def __init__(self, iters, flush=True):
+        self.iters = iters
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda') if flush else None
+
+    def __call__(self, fn, warm=3):
+        for _ in range(warm):
+            fn()
+        tot = 0.0
+        for _ in range(self.iters):
+            if self.flush is not None:
+                self.flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / self.iters
+
+
+def report(name, shape, ms, nbytes):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({'kernel': name, **shape, 'ms': round(ms, 5), 'algorithmic_MB': round(nbytes / 1e6, 2), 'GB/s': round(gbs, 1),
+                      'frac_of_measured_peak': round(gbs / PEAK, 3)}), flush=True)
+
+
+def rand_h(B, P):
+    d = (torch.rand(B, 4, 2, device='cuda') * 2 - 1) * (P / 4)
+    return F.dlt4(d, size=(P, P)), d
+
+
+def bench_image_warp(B, P, t):
+    """north-star path: 1-channel patches, both directions batched (2B planes), pooled 4x4 mask fused"""
+    img = torch.rand(2 * B, 1, P, P, device='cuda')
+    H, _ = rand_h(2 * B, P)
+    H = H.detach().requires_grad_(True)
+    out, mask = F.warp(img, H, P, P, pool=4)
+    gO, gM = torch.randn_like(out), torch.randn_like(mask)
+    pair = 2 * (4 * P * P + 4 * P * P + 4 * (P // 4) ** 2)            # read src + write out + write pooled mask, 2 directions
+    report('warp_fwd(image+mask)', {'B': B, 'P': P}, t(lambda: F.warp(img, H, P, P, pool=4)), pair * B)
+    pairb = 2 * (4 * P * P + 4 * P * P + 4 * (P // 4) ** 2 + 36)
+    report('warp_bwd(dH)', {'B': B, 'P': P}, t(lambda: torch.autograd.grad([out, mask], H, [gO, gM], retain_graph=True)), pairb * B)
+
+
+def bench_feature_warp(B, P, C, t):
+    x = torch.rand(B, C, P, P, device='cuda').contiguous(memory_format=torch.channels_last)
+    H, _ = rand_h(B, P)
+    H = H.detach().requires_grad_(True)
+    out = F.warp(x, H, P, P)
+    gO = torch.randn_like(out)
+    report('warp_fwd(nhwc features)', {'B': B, 'P': P, 'C': C}, t(lambda: F.warp(x, H, P, P)), 2 * 4 * C * P * P * B)
+    report('warp_bwd(nhwc, dH)', {'B': B, 'P': P, 'C': C}, t(lambda: torch.autograd.grad(out, H, gO, retain_graph=True)),
+           2 * 4 * C * P * P * B)
+
+
+def bench_loss(B, P, C, t, nhwc):
+    h = P // 4
+    mk = lambda: (torch.rand(B, C, h, h, device='cuda').contiguous(memory_format=torch.channels_last) if nhwc
+                  else torch.rand(B, C, h, h, device='cuda'))
+    f1, f2, f1w, f2w = mk(), mk(), mk(), mk()
+    m1w, m2w = torch.rand(B, h, h, device='cuda'), torch.rand(B, h, h, device='cuda')
+    H12, _ = rand_h(B, P)
+    H21, _ = rand_h(B, P)
+    nbytes = ((4 + 2) * C * h * h * 4 + 4 * h * h * 4) * B
+    report('bihome_loss fwd+bwd (%s)' % ('nhwc' if nhwc else 'nchw'), {'B': B, 'P': P, 'C': C, 'h': h},
+           t(lambda: F.bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, 0.01)), nbytes)
+
+
+def bench_small(B, P, t):
+    H, d = rand_h(B, P)
+    d = d.requires_grad_(True)
+    gH = torch.randn(B, 3, 3, device='cuda')
+    report('dlt4_fwd', {'B': B}, t(lambda: F.dlt4(d, size=(P, P))), 68 * B)
+    Hd = F.dlt4(d, size=(P, P))
+    report('dlt4_bwd', {'B': B}, t(lambda: torch.autograd.grad(Hd, d, gH, retain_graph=True)), 68 * B)
+    field = torch.randn(B, 2, P, P, device='cuda', requires_grad=True)
+    choice = torch.randint(1, P * P, (B, 128), device='cuda')
+    four = torch.tensor([[0., 0.], [P, 0.], [P, P], [0., P]], device='cuda')
+    report('dltn_fwd(field, 128 pts)', {'B': B}, t(lambda: F.dltn_field(field, choice, four)), (128 * 8 + 128 * 8 + 68) * B)
+    _, dh = F.dltn_field(field, choice, four)
+    gd = torch.randn_like(dh)
+    report('dltn_bwd', {'B': B}, t(lambda: torch.autograd.grad(dh, field, gd, retain_graph=True)), (128 * 16 + 128 * 8) * B)
+    pool = torch.randint(0, 256, (64, 240, 320, 3), dtype=torch.uint8, device='cuda')
+    params, index = F.pairgen_draw(B, 64, (240, 320), 32, P if P <= 128 else 128, 32.0, 1, 0, 'cuda')
+    report('pairgen_apply', {'B': B}, t(lambda: F.pairgen_apply(pool, index, params, 128)),
+           (2 * 3 * (128 + 64) ** 2 + 2 * 4 * 128 * 128) * B)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--sweep', action='store_true')
+    ap.add_argument('--once', action='store_true')
+    ap.add_argument('--iters', type=int, default=20)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    if a.once:
+        t = lambda fn, warm=1: (fn(), fn(), torch.cuda.synchronize(), 1.0)[-1]
+        bench_image_warp(256, 128, t)
+        bench_loss(256, 128, 64, t, True)
+        bench_loss(256, 128, 64, t, False)
+        bench_feature_warp(64, 128, 64, t)
+        bench_small(256, 128, t)
+        return
+    t = Timer(a.iters)
+    print(json.dumps({'peak_GBps_measured': PEAK, 'timing': 'cuda events, L2 flushed before every launch, mean of %d' % a.iters}))
+    shapes = [(256, 128, 64)]
+    if a.sweep:
+        shapes = [(B, P, C) for B in (64, 256, 1024, 4096) for P in (128, 256, 512) for C in (64, 128, 256)]
+    else:
+        shapes += [(1024, 128, 64), (4096, 128, 64), (256, 256, 64), (64, 512, 64), (256, 128, 256)]
+    done_img, done_small = set(), set()
+    for B, P, C in shapes:
+        h = P // 4
+        if (B, P) not in done_img and 2 * B * P * P * 4 * 4 < 60e9:
+            done_img.add((B, P))
+            bench_image_warp(B, P, t)
+        if 6 * B * C * h * h * 4 < 60e9:
+            bench_loss(B, P, C, t, True)
+            bench_loss(B, P, C, t, False)
+        if 4 * B * C * P * P * 4 < 60e9:
+            bench_feature_warp(B, P, C, t)
+        if B not in done_small and P == 128:
+            done_small.add(B)
+            bench_small(B, P, t)
+        torch.cuda.empty_cache()
+
+
+if __name__ == '__main__':
+    main()
