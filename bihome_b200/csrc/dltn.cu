@@ -56,8 +56,15 @@ struct Fwd {
     double Hd[9], Hn[9], den;  // den = Hd[8] + 1e-8
 };
 
-// cyclic Jacobi on the warp's 9x9 symmetric matrix A (destroyed: eigenvalues on its diagonal), V = eigenvectors
+// Parallel-ordered Jacobi on the warp's 9x9 symmetric matrix A (destroyed: eigenvalues end up on its diagonal),
+// V = eigenvectors.  A round-robin tournament over 10 slots (9 indices + a bye) gives 9 rounds of 4 disjoint (p,q)
+// pairs per sweep; the 4 rotations of a round commute, so their parameters are computed by 4 lanes at once and
+// applied as A <- J^T (A J), V <- V J with the 72 + 36 element updates spread over the warp.
 __device__ __forceinline__ void jacobi9(double* A, double* V, int lane) {
+    __shared__ double rot_cs[kDltnWarps][4][2];
+    __shared__ int rot_pq[kDltnWarps][4][2];
+    double(*cs)[2] = rot_cs[threadIdx.x >> 5];
+    int(*pq)[2] = rot_pq[threadIdx.x >> 5];
     for (int i = lane; i < 81; i += 32) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
     __syncwarp();
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
@@ -68,34 +75,49 @@ __device__ __forceinline__ void jacobi9(double* A, double* V, int lane) {
         }
         off = warp_sum(off);
         dia = warp_sum(dia);
-        if (off <= 1e-32 * dia) break;
-        for (int p = 0; p < 8; ++p) {
-            for (int q = p + 1; q < 9; ++q) {
+        if (off <= 1e-28 * dia) break;  // off-diagonal mass below 1e-14 relative: converged in float64
+        for (int round = 0; round < 9; ++round) {
+            if (lane < 4) {
+                // circle method: slot 0 is fixed (the bye, index 9), slots 1..9 hold indices rotated by `round`
+                // pairs: (slot k, slot 9-k) for k = 1..4; slot 0 pairs with slot 9... use 10 slots: 0..9
+                // slot s (1..9) holds index (s - 1 + round) % 9; slot 0 holds the bye
+                const int k = lane + 1;                       // 1..4
+                int p = (k - 1 + round) % 9, q = (9 - k - 1 + round + 9) % 9;   // slots k and 9-k
+                if (p > q) { const int t = p; p = q; q = t; }
                 const double apq = A[p * 9 + q], app = A[p * 9 + p], aqq = A[q * 9 + q];
-                __syncwarp();
+                double c = 1.0, s = 0.0;
                 if (fabs(apq) > 1e-300) {
                     const double theta = (aqq - app) / (2.0 * apq);
                     const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                    if (lane < 9) {
-                        const int k = lane;
-                        if (k != p && k != q) {
-                            const double akp = A[k * 9 + p], akq = A[k * 9 + q];
-                            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
-                            A[k * 9 + p] = np_; A[p * 9 + k] = np_;
-                            A[k * 9 + q] = nq_; A[q * 9 + k] = nq_;
-                        } else if (k == p) {
-                            A[p * 9 + p] = app - t * apq;
-                            A[q * 9 + q] = aqq + t * apq;
-                            A[p * 9 + q] = 0.0; A[q * 9 + p] = 0.0;
-                        }
-                        const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
-                        V[k * 9 + p] = c * vkp - s * vkq;
-                        V[k * 9 + q] = s * vkp + c * vkq;
-                    }
+                    c = 1.0 / sqrt(t * t + 1.0);
+                    s = t * c;
                 }
-                __syncwarp();
+                cs[lane][0] = c; cs[lane][1] = s;
+                pq[lane][0] = p; pq[lane][1] = q;
             }
+            __syncwarp();
+            // phase 1: columns of A and of V:  X[:, p], X[:, q] <- X[:, p] c - X[:, q] s,  X[:, p] s + X[:, q] c
+            for (int w = lane; w < 72; w += 32) {
+                double* X = (w < 36) ? A : V;
+                const int e = (w < 36) ? w : w - 36;
+                const int row = e >> 2, k = e & 3;
+                const int p = pq[k][0], q = pq[k][1];
+                const double c = cs[k][0], s = cs[k][1];
+                const double xp = X[row * 9 + p], xq = X[row * 9 + q];
+                X[row * 9 + p] = c * xp - s * xq;
+                X[row * 9 + q] = s * xp + c * xq;
+            }
+            __syncwarp();
+            // phase 2: rows of A:  A[p, :], A[q, :] <- c A[p, :] - s A[q, :],  s A[p, :] + c A[q, :]
+            for (int w = lane; w < 36; w += 32) {
+                const int col = w >> 2, k = w & 3;
+                const int p = pq[k][0], q = pq[k][1];
+                const double c = cs[k][0], s = cs[k][1];
+                const double xp = A[p * 9 + col], xq = A[q * 9 + col];
+                A[p * 9 + col] = c * xp - s * xq;
+                A[q * 9 + col] = s * xp + c * xq;
+            }
+            __syncwarp();
         }
     }
     __syncwarp();

@@ -13,8 +13,21 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes
+
 import torch
 import bihome_b200.functional as F
+from bihome_b200 import cabi
+
+LIB = cabi.lib()
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 PEAK = 6460.5
 try:
@@ -56,16 +69,27 @@ def rand_h(B, P):
 
 
 def bench_image_warp(B, P, t):
-    """north-star path: 1-channel patches, both directions batched (2B planes), pooled 4x4 mask fused"""
+    """north-star path: 1-channel patches, both directions batched (2B planes), pooled 4x4 mask fused.
+    Timed as raw C-ABI calls on preallocated buffers (the autograd wrapper costs ~50 us of CPU per call)."""
     img = torch.rand(2 * B, 1, P, P, device='cuda')
     H, _ = rand_h(2 * B, P)
-    H = H.detach().requires_grad_(True)
-    out, mask = F.warp(img, H, P, P, pool=4)
+    H = H.detach().contiguous()
+    out, mask = torch.empty_like(img), torch.empty(2 * B, P // 4, P // 4, device='cuda')
     gO, gM = torch.randn_like(out), torch.randn_like(mask)
+    gH = torch.empty(2 * B, 9, device='cuda')
+    nws = LIB.bh_warp_bwd_workspace_bytes(2 * B, 1, P, P, P, P, 0)
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device='cuda')
+    st = stream()
+
+    def fwd():
+        cabi.check(LIB.bh_warp_fwd(ptr(img), ptr(H), ptr(out), ptr(mask), 2 * B, 1, P, P, P, P, 4, 0, st), 'fwd')
+
+    def bwd():
+        cabi.check(LIB.bh_warp_bwd(ptr(img), ptr(H), ptr(gO), ptr(gM), ptr(gH), None, 2 * B, 1, P, P, P, P, 4, 0, ptr(ws), nws, st), 'bwd')
     pair = 2 * (4 * P * P + 4 * P * P + 4 * (P // 4) ** 2)            # read src + write out + write pooled mask, 2 directions
-    report('warp_fwd(image+mask)', {'B': B, 'P': P}, t(lambda: F.warp(img, H, P, P, pool=4)), pair * B)
+    report('warp_fwd(image+mask)', {'B': B, 'P': P}, t(fwd), pair * B)
     pairb = 2 * (4 * P * P + 4 * P * P + 4 * (P // 4) ** 2 + 36)
-    report('warp_bwd(dH)', {'B': B, 'P': P}, t(lambda: torch.autograd.grad([out, mask], H, [gO, gM], retain_graph=True)), pairb * B)
+    report('warp_bwd(dH)', {'B': B, 'P': P}, t(bwd), pairb * B)
 
 
 def bench_feature_warp(B, P, C, t):
