@@ -41,14 +41,42 @@ def synthetic_pool(n_images, height=240, width=320, seed=1234, device='cuda'):
     return im.clamp_(0, 255).round_().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 
 
-def load_pool(directory, device='cuda', limit=None):
-    """uint8 [n,H,W,3] pool from a directory of preprocessed ``.npy`` images (reference preprocess_offline.py output)."""
-    names = sorted(f for f in os.listdir(directory) if f.endswith('.npy'))
+def rescale_center_crop(image, size=(320, 240)):
+    """the reference's offline preprocessing (``Rescale((320, 240))`` + ``CenterCrop((320, 240))``,
+    src/data/transforms.py:11-46, 87-122): the shorter side is matched, the longer one is cropped around the centre."""
+    import cv2
+    h, w = image.shape[:2]
+    tw, th = size
+    ratio = h / w
+    if ratio < th / tw:
+        nw, nh = int(np.round(th / ratio)), th
+    else:
+        nw, nh = tw, int(np.round(tw * ratio))
+    image = cv2.resize(image, (nw, nh))
+    top = (nh - th) // 2 if nh != th else 0
+    left = (nw - tw) // 2 if nw != tw else 0
+    return image[top:top + th, left:left + tw]
+
+
+def load_pool(directory, device='cuda', limit=None, size=(320, 240)):
+    """uint8 [n,H,W,3] RGB pool from a directory of ``.npy`` images (reference preprocess_offline.py output) and / or
+    ``.jpg`` files (read like ``Dataset.load_image``, src/data/coco/dataset.py:95-103, then rescaled and cropped)."""
+    names = sorted(f for f in os.listdir(directory) if f.endswith(('.npy', '.jpg')))
     if limit:
         names = names[:limit]
     if not names:
-        raise FileNotFoundError('no .npy images under %s' % directory)
-    arrs = [np.load(os.path.join(directory, f), allow_pickle=True) for f in names]
+        raise FileNotFoundError('no .npy / .jpg images under %s' % directory)
+    arrs = []
+    for f in names:
+        path = os.path.join(directory, f)
+        if f.endswith('.npy'):
+            a = np.load(path, allow_pickle=True)
+        else:
+            import cv2
+            a = cv2.cvtColor(cv2.imread(path), cv2.COLOR_BGR2RGB)
+        if a.shape[:2] != (size[1], size[0]):
+            a = rescale_center_crop(a, size)
+        arrs.append(np.ascontiguousarray(a, dtype=np.uint8))
     return torch.from_numpy(np.stack(arrs)).to(device)
 
 
@@ -85,3 +113,22 @@ class GpuPairLoader:
     def __iter__(self):
         for _ in range(self.steps):
             yield self.next_batch()
+
+
+def loader_from_config(config, split, device, rank=0, batch_size=None, synthetic_images=256, pool_limit=None):
+    """GPU pair source for DATA.TRAIN_SPLIT / DATA.TEST_SPLIT (reference make_coco_dataloader, train.py:80-137)."""
+    data = config['DATA']
+    train = split == 'train'
+    directory = data['TRAIN_SPLIT' if train else 'TEST_SPLIT']
+    transforms = data['TRANSFORMS'] if train or 'TEST_TRANSFORM' not in data else data['TEST_TRANSFORM']
+    sampler = data['SAMPLER']
+    bs = int(batch_size or sampler['BATCH_SIZE'])
+    samples = int(sampler['TRAIN_SAMPLES_PER_EPOCH' if train else 'TEST_SAMPLES_PER_EPOCH'])
+    seed = int(sampler['TRAIN_SEED' if train else 'TEST_SEED'])
+    if os.path.isdir(directory) and any(f.endswith(('.npy', '.jpg')) for f in os.listdir(directory)):
+        pool = load_pool(directory, device=device, limit=pool_limit)
+    else:
+        if rank == 0:
+            print('bihome_b200: %s holds no images; using a synthetic pool of %d images' % (directory, synthetic_images))
+        pool = synthetic_pool(synthetic_images, seed=1234 if train else 4321, device=device)
+    return GpuPairLoader(pool, bs, samples, seed=seed, rank=rank, **transform_args(transforms))

@@ -43,6 +43,7 @@ def _install_shims():
                 def build(pretrained=False, progress=True, **kw):
                     state = torch.random.get_rng_state()
                     torch.manual_seed(1234)
+                    kw.pop('weights', None)
                     try:
                         return orig_fn(weights=None, **kw)
                     finally:

@@ -1,0 +1,92 @@
+"""BASELINE.json configs[4]: MACE of the reference path vs the B200 path on one fixed synthetic PDS-COCO set, same
+random-init weights, same multinomial draws (north_star: |MACE difference| <= 0.01 px)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIG = os.path.join(ROOT, 'config', 'pds-coco', 'zeng-bihome-lr-1e-3.yaml')
+
+
+def reference_pairs(n, seed=42):
+    """pairs made by the CPU restatement of the reference transform pipeline (oracle/pairgen.py)"""
+    from oracle import pairgen
+    rs = np.random.RandomState(seed)
+    p1, p2, d = [], [], []
+    for i in range(n):
+        q = pairgen.draw_params(rs, 240, 320, 32, 128, 32)
+        out = pairgen.make_pair(pairgen.synthetic_image(i % 8), q, 128)
+        p1.append(pairgen.to_network_input(out['patch_1']))
+        p2.append(pairgen.to_network_input(out['patch_2']))
+        d.append(q['delta'].astype(np.float32))
+    return np.stack(p1), np.stack(p2), np.stack(d)
+
+
+def test_mace_matches_reference_path(tmp_path):
+    from conftest import load_entry
+    ev = load_entry('eval')
+    from bihome_b200 import engine
+    from oracle import ref_path as R
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n, bs = 48, 16
+    p1, p2, delta = reference_pairs(n)
+    cfg = engine.load_config(CONFIG)
+    torch.manual_seed(0)
+    seq = engine.build_model(cfg, pretrained=False)
+    # a random-init field is pure noise: give the last layer a gain so the field carries a few pixels of structure
+    with torch.no_grad():
+        seq[0].layer8[-1].weight.mul_(20.0)
+    seq.eval()
+    M = cfg['MODEL']['HEAD']['POINTS_PER_HYPOTHESIS']
+    g = torch.Generator().manual_seed(7)
+    choices = [R.multinomial_choice(128 * 128, bs * M, generator=g) for _ in range(n // bs)]
+
+    # reference path on the CPU: torch backbone + oracle DSAC/DLT/corner projection (PerceptualHead.py:716-767)
+    ref_maces, ref_hats = [], []
+    with torch.no_grad():
+        for i in range(n // bs):
+            sl = slice(i * bs, (i + 1) * bs)
+            data = seq[0]({'patch_1': torch.from_numpy(p1[sl]), 'patch_2': torch.from_numpy(p2[sl])})
+            dh, _, _ = R.zeng_delta_hat(data['pf_hat_12'].double(), M, 1, choice=choices[i])
+            ref_hats.append(dh.reshape(bs, 4, 2).numpy())
+            ref_maces.append(R.mace(delta[sl], ref_hats[-1]))
+
+    # B200 path through eval.py's own evaluate()
+    model = ev.ModelWrapper(seq[0], seq[1]).cuda()
+    model.eval()
+    it = iter(choices)
+    head = model[1]
+    orig = head._field_to_delta
+
+    def forced(pf, which):
+        head.forced_choice = [next(it).cuda(), None]
+        return orig(pf, which)
+    head._field_to_delta = forced
+    path = os.path.join(str(tmp_path), 'pairs.npz')
+    np.savez(path, patch_1=p1, patch_2=p2, delta=delta)
+    mean_mace, maces, _ = ev.evaluate(model, ev.fixed_batches(path, bs, 'cuda'))
+    assert len(maces) == n // bs
+    assert abs(mean_mace - float(np.mean(ref_maces))) <= 0.01, (mean_mace, np.mean(ref_maces))
+    for a, b in zip(maces, ref_maces):
+        assert abs(a - b) <= 0.01, (a, b)
+    assert mean_mace > 1.0          # a random-init model is far from the ground truth: the comparison is not vacuous
+
+
+def test_train_entry_point_runs_and_resumes(tmp_path):
+    """train.py main(): a few steps of the shipped Zeng config, checkpoint, resume from last_checkpoint.txt"""
+    from conftest import load_entry
+    train = load_entry('train')
+    log_dir = os.path.join(str(tmp_path), 'log')
+    train.main(CONFIG, batch_size=8, max_steps=3, synthetic_pool=8, log_dir=log_dir)
+    assert os.path.isfile(os.path.join(log_dir, 'model_000003.pth'))
+    blob = torch.load(os.path.join(log_dir, 'model_000003.pth'), map_location='cpu', weights_only=False)
+    assert blob['step'] == 3 and blob['scheduler']['last_epoch'] == 3
+    train.main(CONFIG, batch_size=8, max_steps=5, synthetic_pool=8, log_dir=log_dir)
+    assert os.path.isfile(os.path.join(log_dir, 'model_000005.pth'))
+    ev = load_entry('eval')
+    mace = ev.main(CONFIG, os.path.join(log_dir, 'model_000005.pth'), batch_size=8, samples=32)
+    assert np.isfinite(mace)

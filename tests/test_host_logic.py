@@ -79,3 +79,53 @@ def test_dsac_scores_single_hypothesis_are_ones():
     d = DSACSoftmax()
     s = d.score_hypotheses(torch.zeros(3, 10, 2), torch.zeros(3, 10, 2), torch.eye(3).repeat(3, 1, 1, 1))
     assert torch.equal(s, torch.ones(3, 1))
+
+
+def test_checkpointer_round_trip_in_reference_format(tmp_path):
+    """reference src/utils/checkpoint.py:31-85: model_%06d.pth + last_checkpoint.txt, {'model','optimizer','scheduler','step'}"""
+    from bihome_b200 import engine
+    from bihome_b200.utils.checkpoint import CheckPointer
+    c = cfg('s-coco/detone-bihome-lr-5e-3.yaml')
+    torch.manual_seed(1)
+    model = engine.build_model(c, pretrained=False)
+    opt, sched = engine.build_optimizer(c, model)
+    for _ in range(3):
+        sched.step()
+    ck = CheckPointer(model, opt, sched, str(tmp_path), save_to_disk=True)
+    assert ck.load() == {} and not ck.has_checkpoint()
+    path = ck.save('model_{:06d}'.format(3), step=3)
+    assert os.path.basename(path) == 'model_000003.pth'
+    assert open(os.path.join(str(tmp_path), 'last_checkpoint.txt')).read() == path
+    blob = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(blob) == {'model', 'optimizer', 'scheduler', 'step'}
+    assert any(k.startswith('1.auxiliary_resnet.resnet.') for k in blob['model'])
+    torch.manual_seed(2)
+    model2 = engine.build_model(c, pretrained=False)
+    opt2, sched2 = engine.build_optimizer(c, model2)
+    extra = CheckPointer(model2, opt2, sched2, str(tmp_path)).load()
+    assert extra == {'step': 3} and sched2.last_epoch == 3
+    for a, b in zip(model.state_dict().values(), model2.state_dict().values()):
+        assert torch.equal(a, b)
+    # rank > 0 never writes
+    assert CheckPointer(model, save_dir=str(tmp_path), save_to_disk=False).save('x') is None
+
+
+def test_entry_points_keep_the_reference_contract():
+    import inspect
+    from conftest import load_entry
+    train, ev = load_entry('train'), load_entry('eval')
+    assert list(inspect.signature(train.main).parameters)[0] == 'config_file_path'
+    assert list(inspect.signature(ev.main).parameters)[:5] == ['config_file_path', 'ckpt_file_path', 'batch_size', 'visualize',
+                                                              'log_filepath']
+    for name in ('do_train', 'train_one_epoch', 'eval_one_epoch'):
+        assert callable(getattr(train, name))
+    assert callable(ev.evaluate) and hasattr(ev.ModelWrapper, 'predict_homography')
+    with pytest.raises(SystemExit, match='no CPU fallback'):
+        train.main(os.path.join(ROOT, 'config', 'pds-coco', 'zeng-bihome-lr-1e-3.yaml'))
+
+
+def test_rescale_center_crop_matches_reference_rule():
+    from bihome_b200.data.gpu_pairs import rescale_center_crop
+    for h, w in ((480, 640), (640, 480), (240, 320), (500, 333), (427, 640)):
+        out = rescale_center_crop(np.zeros((h, w, 3), np.uint8))
+        assert out.shape == (240, 320, 3)
