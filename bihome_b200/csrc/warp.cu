@@ -6,13 +6,9 @@
 // The sampling grid never exists in memory here: coordinates live in registers.
 //
 // Three code paths, chosen by shape (see bh_warp_fwd / bh_warp_bwd at the bottom):
-//   block  : NCHW.  CTA = (plane, 64x64 block of output pixels); the source box that block can touch (bounding box
-//            of its four projected corners) is staged row by row with 1-D bulk TMA copies (cp.async.bulk ->
-//            UBLKCP) on one mbarrier while the threads classify their tiles; 4 CTAs per SM so the copies of one
-//            block overlap the sampling of the others; taps are read from shared memory; each thread owns 4x4
-//            output pixels (float4 row stores, the pooled 4x4 coverage mask falls out in-thread); tiles are
-//            compacted into interior / border lists so that warps never diverge, and interior tiles skip every
-//            bounds test.
+//   ring   : NCHW (the biHomE path: 1-channel patches).  Persistent warp-specialised kernels: a producer warp stages
+//            the source box of every 64x64 output block with bulk TMA row copies into a zero-framed shared-memory
+//            window while eight consumer warps sample the previous block; see the section comment below.
 //   nhwc   : channels-last, C % 4 == 0: one thread per (pixel, 4 channels), 128-bit coalesced tap loads.
 //   generic: anything else (scalar, strided).
 // Backward produces dH by a fixed-order per-sample reduction (bit-reproducible, no atomics); the image
@@ -70,27 +66,153 @@ __device__ __forceinline__ void store9(const float (&acc)[9], float* dst) {
 }
 
 // =================================================================================================
-// block path (NCHW): CTA = (plane, 64x64 block of output pixels); only the source box that block can touch is staged
+// ring path (NCHW, the default): persistent, warp-specialised, TMA-pipelined.
+//
+//   work item  = (plane, 64x64 block of output pixels); grid = 3 CTAs per SM walking the items round-robin.
+//   warp 8     = PRODUCER.  For the item after the one being sampled it loads H, computes the source box the block can
+//                touch (bounding box of its four projected corners), classifies the 8 x 4 groups of 32x4 output pixels
+//                (one group per lane, convexity argument on the group's corners), writes the ZERO FRAME of the staging
+//                window, publishes all of it as an item header in shared memory and issues one bulk TMA copy per source
+//                row of the box (cp.async.bulk -> UBLKCP) into the free stage, completing on full[stage].
+//   warps 0..7 = CONSUMERS.  Wait full[stage], read the header (~20 LDS instead of hundreds of set-up instructions per
+//                thread), sample, arrive on empty[stage].  The lanes of a warp sit on 32 CONSECUTIVE output columns and
+//                walk down 16 rows in groups of 4: with a window pitch that is a multiple of 32 floats the four tap
+//                loads of a warp are conflict-free LDS, output stores / upstream-gradient loads are 128-byte rows.
+//   zero frame = 1 row above, 2 below, 4 columns left and right of the staged box: grid_sample's "zeros" padding is a
+//                clamp of (u, v) to [-1, W] x [-1, H] followed by the same four unpredicated LDS an interior pixel does.
+//   floor      = add.rm.f32 with 1.5 * 2^23: cell index and fraction come out of the FMA pipe (no FRND / F2I).
+// The copies of item k+1 are in flight while item k is sampled, so no warp waits on the DRAM latency of its own box.
+// Blocks whose box exceeds the stage (local scale > ~1.4, strong down-sampling) read the plane through the read-only
+// cache with predicated taps inside the same kernel.
 // =================================================================================================
-constexpr int kBlkThreads = 256;
-constexpr int kBlk = 64;                      // output block side: 16 x 16 tiles of 4x4 pixels = one tile per thread
-constexpr int kBlkSmemBytes = 48 * 1024;      // staging budget per CTA (4 CTAs per SM)
-
-// Per output row: numerators/denominator at x = 0, so that a pixel costs 3 FMA + one reciprocal.
-struct RowProj {
-    float nx0, ny0, w0;
+constexpr int kStripRows = 16;    // rows walked by one consumer warp per strip (32 columns x 16 rows)
+constexpr int kPadL = 4, kPadT = 1, kPadB = 2;   // the 4 floats in front of a window row are also the right pad of the row above
+// Two item sizes.  kBlk = 128: the source plane (<= 128x128) always fits one stage, so a whole plane is staged once and
+// its 32 strips are sampled by 16 consumer warps, 1 CTA per SM; the copies of the next plane have a full plane-time to
+// land.  kBlk = 64: larger sources, 8 consumer warps, 3 stages, 2 CTAs per SM.
+template <int kBlk>
+struct RingCfg {
+    static constexpr int kStages = kBlk == 128 ? 2 : 3;
+    static constexpr int kStageBytes = kBlk == 128 ? 72 * 1024 : 36 * 1024;
+    static constexpr int kConsumers = kBlk == 128 ? 512 : 256;
+    static constexpr int kThreads = kConsumers + 32;
+    static constexpr int kCtasPerSm = kBlk == 128 ? 1 : 2;
+    static constexpr int kStripsX = kBlk / 32, kStripsY = kBlk / kStripRows, kStrips = kStripsX * kStripsY;
+    static constexpr int kStripsPerWarp = kStrips / (kConsumers / 32);
+    static constexpr int kSmem = kStages * kStageBytes;
 };
-__device__ __forceinline__ RowProj row_proj(const Hmat& m, float y) {
-    RowProj r;
-    r.nx0 = fmaf(m.h[1], y, m.h[2]);
-    r.ny0 = fmaf(m.h[4], y, m.h[5]);
-    r.w0 = fmaf(m.h[7], y, m.h[8]);
+constexpr float kMagic = 12582912.0f;            // 1.5 * 2^23: ulp == 1, add.rm.f32 leaves floor(t) in the mantissa
+constexpr int kMagicBits = 0x4B400000;
+
+enum GroupClass { kInside = 0, kBorder = 1, kOutside = 2, kSkip = 3 };
+
+struct ItemHeader {
+    float h[9];
+    int c0, r0, ncols, nrows, pitch, ok;
+    int plane, b, c, blk, x_lo, y_lo, x_hi, y_hi;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// wait with a hardware suspend hint (consumers) / with a sleep between polls (producer): spinning warps must not eat the
+// issue slots of the warps that sample
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITH_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONEH_%=;\n"
+        "nanosleep.u32 64;\n"
+        "bra WAITH_%=;\n"
+        "DONEH_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(1000000u)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITS_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONES_%=;\n"
+        "nanosleep.u32 200;\n"
+        "bra WAITS_%=;\n"
+        "DONES_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(1000000u)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float add_rm(float a, float b) {
+    float r;
+    asm("add.rm.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
+}
+__device__ __forceinline__ void st_stream1(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// geometry of the block an item covers
+struct BlockGeom {
+    int x_lo, y_lo, x_hi, y_hi;  // [x_lo, x_hi) x [y_lo, y_hi), multiples of 4
+};
+__device__ __forceinline__ BlockGeom block_geom(int blk, int blocks_x, int Ho, int Wo, int side) {
+    BlockGeom g;
+    const int by = blk / blocks_x, bxi = blk - by * blocks_x;
+    g.x_lo = bxi * side;
+    g.y_lo = by * side;
+    g.x_hi = min(Wo, g.x_lo + side);
+    g.y_hi = min(Ho, g.y_lo + side);
+    return g;
+}
+
+// (u, v) = proj(H [x, y, 1]) by reciprocal only: set-up quantities (boxes, classes) that carry their own guard bands
+__device__ __forceinline__ void project_rcp(const Hmat& m, float x, float y, float& u, float& v, float& w) {
+    w = fmaf(m.h[6], x, fmaf(m.h[7], y, m.h[8]));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
+    u = fmaf(m.h[0], x, fmaf(m.h[1], y, m.h[2])) * r;
+    v = fmaf(m.h[3], x, fmaf(m.h[4], y, m.h[5])) * r;
+}
+// min / max / and over the aligned group of 4 lanes
+__device__ __forceinline__ float quad_min(float v) {
+    v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ bool quad_all(bool p) {
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    return ((m >> ((threadIdx.x & 31u) & ~3u)) & 0xfu) == 0xfu;
+}
+
+// Per-column projection state of a consumer lane: numerators / denominator at y = 0.
+struct ColProj {
+    float ax, ay, aw;
+};
+__device__ __forceinline__ ColProj col_proj(const Hmat& m, float x) {
+    ColProj c;
+    c.ax = fmaf(m.h[0], x, m.h[2]);
+    c.ay = fmaf(m.h[3], x, m.h[5]);
+    c.aw = fmaf(m.h[6], x, m.h[8]);
+    return c;
 }
 // (u, v) = (nx, ny) * rcp(w) with one residual correction per quotient: the textbook division sequence without its
 // special-case branches (w > 0 on every valid pixel); error well below 1 ulp of a 128-px coordinate
-__device__ __forceinline__ void project_fast(const Hmat& m, const RowProj& rp, float x, float& u, float& v, float& rw) {
-    const float w = fmaf(m.h[6], x, rp.w0), nx = fmaf(m.h[0], x, rp.nx0), ny = fmaf(m.h[3], x, rp.ny0);
+__device__ __forceinline__ void project_col(const Hmat& m, const ColProj& cp, float y, float& u, float& v, float& rw) {
+    const float w = fmaf(m.h[7], y, cp.aw), nx = fmaf(m.h[1], y, cp.ax), ny = fmaf(m.h[4], y, cp.ay);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
     float q = nx * r;
@@ -99,6 +221,54 @@ __device__ __forceinline__ void project_fast(const Hmat& m, const RowProj& rp, f
     v = fmaf(fmaf(-q, w, ny), r, q);
     rw = r;
 }
+
+// Where the taps of an item live: the framed shared window, or the whole plane in global memory.
+struct Window {
+    const float* taps;     // global: plane base.  shared: unused
+    uint32_t base_s32;     // shared: byte address of source pixel (0, 0) minus the magic-number bias (may wrap)
+    int pitch;             // floats
+    bool shared;
+    bool xpred;            // shared window without side pads: border pixels predicate their x taps
+};
+// bilinear cell of (u, v), |u|, |v| < 2^22: fractions and the four taps, no bounds tests (interior pixels, or any pixel of
+// a framed window after the clamp)
+struct Cell4 {
+    float fx, fy, nw, ne, sw, se;
+    int ix;   // floor(u)
+};
+template <bool kShared>
+__device__ __forceinline__ Cell4 cell_at(float u, float v, const Window& wd) {
+    Cell4 c;
+    const float tx = add_rm(u, kMagic), ty = add_rm(v, kMagic);
+    c.fx = u - (tx - kMagic);
+    c.fy = v - (ty - kMagic);
+    c.ix = __float_as_int(tx) - kMagicBits;
+    // biased by kMagicBits * (pitch + 1); unsigned arithmetic: the bias wraps and is taken out again below / in base_s32
+    const uint32_t lin = static_cast<uint32_t>(__float_as_int(ty)) * static_cast<uint32_t>(wd.pitch) + static_cast<uint32_t>(__float_as_int(tx));
+    if (kShared) {
+        const uint32_t a0 = wd.base_s32 + lin * 4u, a1 = a0 + static_cast<uint32_t>(wd.pitch) * 4u;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.nw) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(c.ne) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.sw) : "r"(a1));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(c.se) : "r"(a1));
+    } else {
+        const float* p = wd.taps + static_cast<int>(lin - static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(wd.pitch + 1));
+        c.nw = __ldg(p);
+        c.ne = __ldg(p + 1);
+        c.sw = __ldg(p + wd.pitch);
+        c.se = __ldg(p + wd.pitch + 1);
+    }
+    return c;
+}
+// dense window (no side pads): taps left / right of the source read the neighbouring row -- replace them by zeros
+__device__ __forceinline__ void zero_x_taps(Cell4& c, int Ws) {
+    const bool l = static_cast<unsigned>(c.ix) < static_cast<unsigned>(Ws), r = static_cast<unsigned>(c.ix + 1) < static_cast<unsigned>(Ws);
+    c.nw = l ? c.nw : 0.0f;
+    c.sw = l ? c.sw : 0.0f;
+    c.ne = r ? c.ne : 0.0f;
+    c.se = r ? c.se : 0.0f;
+}
+// predicated taps for the global-memory fallback (no frame there)
 __device__ __forceinline__ Taps make_taps_fast(float u, float v, int Ws, int Hs) {
     Taps t;
     t.x0 = __float2int_rd(u);  // floor with saturation: far-away coordinates stay out of range
@@ -114,423 +284,513 @@ __device__ __forceinline__ Taps make_taps_fast(float u, float v, int Ws, int Hs)
     t.iny1 = static_cast<unsigned>(t.y0) + 1u < static_cast<unsigned>(Hs);
     return t;
 }
-
-// Source box [c0, c1] x [r0, r1] that the output block [x_lo, x_hi) x [y_lo, y_hi) can sample (bilinear footprint
-// included, columns aligned to 4 pixels for the 16-byte bulk copies).  A projective map with w > 0 sends the block to a
-// convex quadrilateral, so the extremes sit at its four corners.  Returns false when the box is not bounded that way.
-struct Box {
-    int c0, c1, r0, r1;
-};
-__device__ __forceinline__ bool block_source_box(const Hmat& m, int x_lo, int x_hi, int y_lo, int y_hi, int Ws, int Hs, Box& bx) {
-    float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float x = static_cast<float>((k & 1) ? x_hi - 1 : x_lo), y = static_cast<float>((k & 2) ? y_hi - 1 : y_lo);
-        float u, v, rw;
-        project(m, x, y, u, v, rw);
-        ok = ok && (rw > 0.0f) && (fabsf(u) < 1.0e6f) && (fabsf(v) < 1.0e6f);
-        umin = fminf(umin, u); umax = fmaxf(umax, u);
-        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-    }
-    if (!ok) return false;
-    bx.c0 = max(0, (static_cast<int>(floorf(umin)) - 1) & ~3);
-    bx.c1 = min(Ws - 1, ((static_cast<int>(floorf(umax)) + 2) | 3));
-    bx.r0 = max(0, static_cast<int>(floorf(vmin)) - 1);
-    bx.r1 = min(Hs - 1, static_cast<int>(floorf(vmax)) + 2);
-    return true;
+__device__ __forceinline__ void global_taps(const Taps& t, const float* plane, int pitch, float& nw, float& ne, float& sw, float& se) {
+    const float* p = plane + t.y0 * pitch + t.x0;
+    nw = (t.inx0 && t.iny0) ? __ldg(p) : 0.0f;
+    ne = (t.inx1 && t.iny0) ? __ldg(p + 1) : 0.0f;
+    sw = (t.inx0 && t.iny1) ? __ldg(p + pitch) : 0.0f;
+    se = (t.inx1 && t.iny1) ? __ldg(p + pitch + 1) : 0.0f;
+}
+// coverage of warp(ones) along one axis, and its derivative: m(t) = clamp(min(t + 1, n - t), 0, 1)
+__device__ __forceinline__ float cover1(float t, float n) { return __saturatef(fminf(t + 1.0f, n - t)); }
+__device__ __forceinline__ float cover1_grad(float t, float n) {
+    const float a = t + 1.0f, b = n - t, m = fminf(a, b);
+    return (m > 0.0f && m < 1.0f) ? (a < b ? 1.0f : -1.0f) : 0.0f;
 }
 
-// Where does the 4x4 output tile at (xt, yt) sample?  The tile maps to a convex quadrilateral (w > 0), so its four
-// corners decide: kInside = every bilinear footprint lies strictly inside the source (no bounds tests, coverage 1),
-// kOutside = no footprint touches the source (zeros, coverage 0), kBorder = anything else (predicated taps).
-enum TileClass { kInside = 0, kBorder = 1, kOutside = 2 };
-__device__ __forceinline__ int classify_tile(const Hmat& m, int xt, int yt, int Ws, int Hs) {
-    bool in = true, pos = true;
-    float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float x = static_cast<float>(xt + ((k & 1) ? 3 : 0)), y = static_cast<float>(yt + ((k & 2) ? 3 : 0));
-        const float w = fmaf(m.h[6], x, fmaf(m.h[7], y, m.h[8]));
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
-        const float u = fmaf(m.h[0], x, fmaf(m.h[1], y, m.h[2])) * r, v = fmaf(m.h[3], x, fmaf(m.h[4], y, m.h[5])) * r;
-        pos = pos && (w > 0.0f);
-        in = in && (u >= 0.001f) && (v >= 0.001f) && (u < static_cast<float>(Ws - 1) - 0.001f) && (v < static_cast<float>(Hs - 1) - 0.001f);
-        umin = fminf(umin, u); umax = fmaxf(umax, u);
-        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+// ---- producer ------------------------------------------------------------------------------------------------
+// Window layout (floats): row pitch = ncols + 4 (rounded up to a multiple of 32 when the stage has room: conflict-free
+// LDS); source pixel (c, r) of the box sits at [(r - r0 + 1) * pitch + 4 + (c - c0)].  Row 0, rows nrows + 1 and
+// nrows + 2 and the floats between the data of consecutive rows are the zero frame.
+// kBlk == 128 stages the whole source plane (constant geometry: the frame is written once per stage);
+// kBlk == 64 stages the bounding box of the block's four projected corners.
+// kStage = false: coverage-only items (mask backward), nothing to copy.
+template <int kBlk, bool kStage>
+__device__ __forceinline__ void ring_produce(const float* __restrict__ src, const float* __restrict__ H, int it, int n_blocks,
+                                             int blocks_x, int C, ItemHeader* hd, float* stage, uint64_t* full, int Hs, int Ws,
+                                             int Ho, int Wo, bool frame_written, const float* __restrict__ l2_prefetch) {
+    using Cfg = RingCfg<kBlk>;
+    const int lane = threadIdx.x & 31;
+    const int plane = it / n_blocks, blk = it - plane * n_blocks;
+    const int b = plane / C, c = plane - b * C;
+    const BlockGeom g = block_geom(blk, blocks_x, Ho, Wo, kBlk);
+    int c0 = 0, r0 = 0, ncols = 0, nrows = 0, pitch = 0;
+    bool ok = false;
+    if (kStage && kBlk == 128) {
+        // dense plane: pitch == Ws, no side pads (the border path predicates its x taps instead)
+        ncols = Ws; nrows = Hs; pitch = Ws;
+        ok = (Ws & 3) == 0;   // the host picked this item size because the plane fits the stage
+    } else if (kStage) {
+        // source box of the block: lanes 4q..4q+3 each project one corner
+        const Hmat hm = load_h(H, b);
+        const int k = lane & 3;
+        float u, v, w;
+        project_rcp(hm, static_cast<float>((k & 1) ? g.x_hi - 1 : g.x_lo), static_cast<float>((k & 2) ? g.y_hi - 1 : g.y_lo), u, v, w);
+        const bool good = quad_all(w > 0.0f && fabsf(u) < 1.0e6f && fabsf(v) < 1.0e6f);
+        const float umin = quad_min(u), umax = quad_max(u), vmin = quad_min(v), vmax = quad_max(v);
+        c0 = max(0, (static_cast<int>(floorf(umin)) - 1) & ~3);
+        const int c1 = min(Ws - 1, ((static_cast<int>(floorf(umax)) + 2) | 3));
+        r0 = max(0, static_cast<int>(floorf(vmin)) - 1);
+        const int r1 = min(Hs - 1, static_cast<int>(floorf(vmax)) + 2);
+        ncols = c1 - c0 + 1;
+        nrows = r1 - r0 + 1;
+        const int rows_all = nrows + kPadT + kPadB;
+        pitch = (ncols + kPadL + 31) & ~31;
+        if (rows_all * pitch * 4 > Cfg::kStageBytes) pitch = ncols + kPadL;   // large box: accept a few bank conflicts
+        ok = good && (Ws & 3) == 0 && ncols > 0 && nrows > 0 && rows_all * pitch * 4 <= Cfg::kStageBytes;
     }
-    if (!pos) return kBorder;  // also catches NaN
-    if (in) return kInside;
-    // 0.001 px guard bands: the corner coordinates above carry ~2 ulp of error
-    if (umax < -1.001f || vmax < -1.001f || umin > static_cast<float>(Ws) + 0.001f || vmin > static_cast<float>(Hs) + 0.001f) return kOutside;
-    return kBorder;
-}
-
-// Staged source box: taps[y * pitch + x] addresses source pixel (x, y) for every pixel of the box (shared memory), or of
-// the whole plane when the box does not fit / is not 16-byte friendly (global memory through the read-only cache).
-struct Stage {
-    const float* taps;
-    int pitch;
-    bool shared, pending;
-};
-// issue: one bulk TMA copy per source row of the box (cp.async.bulk -> UBLKCP), spread over the lanes of warp 0, all
-// completing on one mbarrier.  Only warp 0 computes the box and issues; it publishes {r0, c0, ncols, shared} in `pub`
-// and every thread picks the result up with stage_get() after the block's next __syncthreads.  Nothing waits here:
-// the CTA classifies its tiles while the copies are in flight.
-struct StagePub {
-    int r0, c0, ncols, shared;
-};
-__device__ __forceinline__ void stage_issue_warp0(const Hmat& hm, const float* plane_ptr, float* smem, uint64_t* bar, int Ws, int Hs,
-                                                  int x_lo, int x_hi, int y_lo, int y_hi, bool aligned, StagePub* pub) {
-    Box bx;
-    const bool have_box = block_source_box(hm, x_lo, x_hi, y_lo, y_hi, Ws, Hs, bx);
-    const int ncols = bx.c1 - bx.c0 + 1, nrows = bx.r1 - bx.r0 + 1;
-    const bool ok = have_box && aligned && ncols > 0 && nrows > 0 && ncols * nrows * 4 <= kBlkSmemBytes;
-    if (ok) {
-        if (threadIdx.x == 0) mbar_expect_tx(bar, static_cast<uint32_t>(ncols) * nrows * 4u);
-        __syncwarp();
-        for (int r = threadIdx.x; r < nrows; r += 32)
-            bulk_g2s(smem + r * ncols, plane_ptr + static_cast<size_t>(bx.r0 + r) * Ws + bx.c0, static_cast<uint32_t>(ncols) * 4u, bar);
-    }
-    if (threadIdx.x == 0) {
-        pub->r0 = bx.r0; pub->c0 = bx.c0; pub->ncols = ncols; pub->shared = ok ? 1 : 0;
-    }
-}
-__device__ __forceinline__ Stage stage_get(const StagePub* pub, const float* plane_ptr, const float* smem, int Ws) {
-    Stage st;
-    st.shared = pub->shared != 0;
-    st.pending = st.shared;
-    if (st.shared) {
-        st.pitch = pub->ncols;
-        st.taps = smem - static_cast<ptrdiff_t>(pub->r0) * pub->ncols - pub->c0;
-    } else {  // box too large / unaligned / block samples nothing: whole plane through the read-only cache
-        st.pitch = Ws;
-        st.taps = plane_ptr;
-    }
-    return st;
-}
-__device__ __forceinline__ void stage_wait(Stage& st, uint64_t* bar, uint32_t parity) {
-    if (st.pending) mbar_wait(bar, parity);
-    st.pending = false;
-}
-
-// Divergence-free scheduling of the block's tiles: every thread classifies one tile, interior and border tiles are
-// compacted into two shared-memory lists, and the lists are then processed with all lanes of a warp on the same code
-// path (a warp's 32 tiles otherwise nearly always straddle the warped image border somewhere).
-struct TileLists {
-    int n_in, n_bd;
-    unsigned short in[kBlkThreads], bd[kBlkThreads];
-};
-__device__ __forceinline__ void lists_reset(TileLists& L) {
-    __syncthreads();  // previous use fully consumed
-    if (threadIdx.x == 0) { L.n_in = 0; L.n_bd = 0; }
-    __syncthreads();
-}
-__device__ __forceinline__ void lists_push(TileLists& L, int cls, int tile) {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned m_in = __ballot_sync(0xffffffffu, cls == kInside), m_bd = __ballot_sync(0xffffffffu, cls == kBorder);
-    int base_in = 0, base_bd = 0;
+    if (lane < 9) hd->h[lane] = __ldg(H + 9 * b + lane);
     if (lane == 0) {
-        if (m_in) base_in = atomicAdd(&L.n_in, __popc(m_in));
-        if (m_bd) base_bd = atomicAdd(&L.n_bd, __popc(m_bd));
+        hd->c0 = c0; hd->r0 = r0; hd->ncols = ncols; hd->nrows = nrows; hd->pitch = pitch; hd->ok = ok ? 1 : 0;
+        hd->plane = plane; hd->b = b; hd->c = c; hd->blk = blk;
+        hd->x_lo = g.x_lo; hd->y_lo = g.y_lo; hd->x_hi = g.x_hi; hd->y_hi = g.y_hi;
     }
-    base_in = __shfl_sync(0xffffffffu, base_in, 0);
-    base_bd = __shfl_sync(0xffffffffu, base_bd, 0);
-    const unsigned below = (1u << lane) - 1u;
-    if (cls == kInside) L.in[base_in + __popc(m_in & below)] = static_cast<unsigned short>(tile);
-    if (cls == kBorder) L.bd[base_bd + __popc(m_bd & below)] = static_cast<unsigned short>(tile);
-    __syncthreads();
+    if (ok && kBlk == 128) {
+        if (!frame_written) {
+            // zero rows above / below the dense plane (+ 4 floats of slack in front), written once per stage
+            const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4* w4 = reinterpret_cast<float4*>(stage);
+            const int p4 = pitch >> 2;
+            for (int i = lane; i <= p4; i += 32) w4[i] = z;                                        // slack + row 0
+            for (int i = lane; i < 2 * p4 + 1; i += 32) w4[1 + (nrows + 1) * p4 + i] = z;          // rows nrows+1, nrows+2 + slack
+        }
+    } else if (ok) {
+        // zero frame, 16 bytes at a time (addresses disjoint from what the bulk copies write)
+        const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4* w4 = reinterpret_cast<float4*>(stage);
+        const int p4 = pitch >> 2;
+        for (int i = lane; i < p4; i += 32) {
+            w4[i] = z;
+            w4[(nrows + 1) * p4 + i] = z;
+            w4[(nrows + 2) * p4 + i] = z;
+        }
+        // in front of every data row (= behind the previous one), and everything right of the data up to the pitch
+        const int tail4 = (pitch - kPadL - ncols) >> 2;
+        for (int r = lane; r < nrows; r += 32) {
+            w4[(r + kPadT) * p4] = z;
+            for (int t = 0; t < tail4; ++t) w4[(r + kPadT) * p4 + 1 + (ncols >> 2) + t] = z;
+        }
+    }
+    __syncwarp();  // header and frame written by all lanes before lane 0 releases them
+    if (ok) {
+        const uint32_t total = static_cast<uint32_t>(ncols) * nrows * 4u;
+        if (lane == 0) mbar_expect_tx(full, total);
+        __syncwarp();
+        const float* plane_ptr = src + static_cast<size_t>(plane) * Hs * Ws;
+        if (kBlk == 128) {
+            // the TMA unit spends ~50 cycles per request whatever its size: the contiguous plane goes in <= 4 requests
+            const uint32_t chunk = ((total / 4u) + 15u) & ~15u;
+            const uint32_t off = static_cast<uint32_t>(lane) * chunk;
+            if (lane < 4 && off < total)
+                bulk_g2s(reinterpret_cast<char*>(stage + kPadT * pitch + kPadL) + off, reinterpret_cast<const char*>(plane_ptr) + off,
+                         min(chunk, total - off), full);
+        } else {
+            for (int r = lane; r < nrows; r += 32)
+                bulk_g2s(stage + (r + kPadT) * pitch + kPadL, plane_ptr + static_cast<size_t>(r0 + r) * Ws + c0,
+                         static_cast<uint32_t>(ncols) * 4u, full);
+        }
+    } else if (lane == 0) {
+        mbar_arrive(full);
+    }
+    // backward: pull the plane of the upstream gradient towards L2 while the consumers still sample the previous item
+    if (kBlk == 128 && l2_prefetch != nullptr && lane == 0 && n_blocks == 1 && ((Ho * Wo) & 3) == 0)
+        prefetch_l2_bulk(l2_prefetch + static_cast<size_t>(plane) * Ho * Wo, static_cast<uint32_t>(Ho * Wo) * 4u);
 }
 
-template <bool kShared>
-__device__ __forceinline__ float ld_tap(const float* p) {
-    return kShared ? *p : __ldg(p);
-}
-
-// Interior pixel: coordinates, cell and the four taps with ~25 instructions.
-//   cell by FRND.FLOOR, tap index y0 * pitch + x0 formed in float (exact below 2^24) and converted once.
-struct Cell {
-    float u, v, rw, fx, fy, nw, ne, sw, se;
+// ---- consumers -----------------------------------------------------------------------------------------------
+struct ItemView {
+    Hmat hm;
+    Window wd;
+    int plane, b, c, blk;
+    int x, y0;          // this lane's output column, first row of its warp's strip
+    bool xin;
+    unsigned cls4;
 };
-template <bool kShared>
-__device__ __forceinline__ Cell interior_cell(const Hmat& m, const RowProj& rp, float x, const float* taps, uint32_t taps_s32,
-                                              int pitch, float pitchf) {
-    Cell c;
-    project_fast(m, rp, x, c.u, c.v, c.rw);
-    const float x0f = floorf(c.u), y0f = floorf(c.v);
-    c.fx = c.u - x0f;
-    c.fy = c.v - y0f;
-    const int idx = __float2int_rn(fmaf(y0f, pitchf, x0f));
-    if (kShared) {
-        // explicit shared-window addresses: LDS with immediate offsets instead of generic loads
-        const uint32_t a0 = taps_s32 + static_cast<uint32_t>(idx) * 4u, a1 = a0 + static_cast<uint32_t>(pitch) * 4u;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.nw) : "r"(a0));
-        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(c.ne) : "r"(a0));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.sw) : "r"(a1));
-        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(c.se) : "r"(a1));
+// Classes of the 32x4 groups this warp owns in the item (kStripsPerWarp strips x 4 groups), 4 bits each: every lane
+// projects ONE corner of one group, quads combine them (convexity: a group maps to a convex quadrilateral when w > 0).
+// kInsideIsSkip: groups that sample strictly inside carry no work (mask backward: coverage is constant 1 there).
+template <int kBlk, bool kInsideIsSkip>
+__device__ __forceinline__ unsigned ring_classify(const ItemHeader* hd, const Hmat& hm, int warp, int Hs, int Ws) {
+    using Cfg = RingCfg<kBlk>;
+    const int lane = threadIdx.x & 31;
+    const int gidx = lane >> 2, k = lane & 3;                 // group 0..7 = (strip of this warp) * 4 + group in strip
+    const int q = gidx >> 2, gq = gidx & 3;
+    const int sidx = warp + (q < Cfg::kStripsPerWarp ? q : 0) * (Cfg::kConsumers / 32);
+    const int x_hi = hd->x_hi, y_hi = hd->y_hi;
+    const int xa = hd->x_lo + (sidx % Cfg::kStripsX) * 32, xb = min(xa + 31, x_hi - 1);
+    const int ya = hd->y_lo + (sidx / Cfg::kStripsX) * kStripRows + gq * 4, yb = ya + 3;
+    float u, v, w;
+    project_rcp(hm, static_cast<float>((k & 1) ? xb : xa), static_cast<float>((k & 2) ? yb : ya), u, v, w);
+    const bool pos = quad_all(w > 0.0f);
+    // 0.001 px guard bands: the corner coordinates carry a few ulp of error
+    const bool in = quad_all((u >= 0.001f) && (v >= 0.001f) && (u < static_cast<float>(Ws - 1) - 0.001f) &&
+                             (v < static_cast<float>(Hs - 1) - 0.001f));
+    const float umin = quad_min(u), umax = quad_max(u), vmin = quad_min(v), vmax = quad_max(v);
+    int cls;
+    if (!(xa < x_hi && ya < y_hi) || q >= Cfg::kStripsPerWarp) cls = kSkip;
+    else if (!pos) cls = kBorder;  // also catches NaN
+    else if (in) cls = kInsideIsSkip ? kSkip : kInside;
+    else if (umax < -1.001f || vmax < -1.001f || umin > static_cast<float>(Ws) + 0.001f || vmin > static_cast<float>(Hs) + 0.001f)
+        cls = kInsideIsSkip ? kSkip : kOutside;
+    else cls = kBorder;
+    return __reduce_or_sync(0xffffffffu, k == 0 ? static_cast<unsigned>(cls) << (4 * gidx) : 0u);
+}
+// the part of the view that changes from strip to strip of one item (q = which of this warp's strips)
+template <int kBlk>
+__device__ __forceinline__ void ring_view_strip(ItemView& v, const ItemHeader* hd, int warp, int q, unsigned classes, int Wo) {
+    const int sidx = warp + q * (RingCfg<kBlk>::kConsumers / 32);
+    v.x = hd->x_lo + (sidx % RingCfg<kBlk>::kStripsX) * 32 + static_cast<int>(threadIdx.x & 31u);
+    v.y0 = hd->y_lo + (sidx / RingCfg<kBlk>::kStripsX) * kStripRows;
+    v.xin = v.x < Wo;
+    v.cls4 = (classes >> (16 * q)) & 0xffffu;
+}
+__device__ __forceinline__ ItemView ring_view(const ItemHeader* hd, const float* __restrict__ src, const float* stage, int Hs, int Ws) {
+    ItemView v;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v.hm.h[i] = hd->h[i];
+    v.plane = hd->plane; v.b = hd->b; v.c = hd->c; v.blk = hd->blk;
+    v.x = 0; v.y0 = 0; v.xin = false; v.cls4 = 0u;
+    v.wd.shared = hd->ok != 0;
+    v.wd.xpred = hd->pitch == hd->ncols;
+    if (v.wd.shared) {
+        v.wd.pitch = hd->pitch;
+        // byte address of source pixel (0, 0) inside the window, minus the bias the magic-number floor leaves in `lin`
+        const uint32_t origin = static_cast<uint32_t>((kPadT - hd->r0) * v.wd.pitch + (kPadL - hd->c0)) -
+                                static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(v.wd.pitch + 1);
+        v.wd.base_s32 = smem_u32(stage) + origin * 4u;
+        v.wd.taps = nullptr;
     } else {
-        const float* p = taps + idx;
-        c.nw = __ldg(p);
-        c.ne = __ldg(p + 1);
-        c.sw = __ldg(p + pitch);
-        c.se = __ldg(p + pitch + 1);
+        v.wd.pitch = Ws;
+        v.wd.base_s32 = 0u;
+        v.wd.taps = src + static_cast<size_t>(v.plane) * Hs * Ws;
     }
-    return c;
-}
-// border pixel: predicated taps
-template <bool kShared>
-__device__ __forceinline__ void border_taps(const Taps& t, const float* taps, int pitch, float& nw, float& ne, float& sw, float& se) {
-    const float* p = taps + t.y0 * pitch + t.x0;
-    nw = (t.inx0 && t.iny0) ? ld_tap<kShared>(p) : 0.0f;
-    ne = (t.inx1 && t.iny0) ? ld_tap<kShared>(p + 1) : 0.0f;
-    sw = (t.inx0 && t.iny1) ? ld_tap<kShared>(p + pitch) : 0.0f;
-    se = (t.inx1 && t.iny1) ? ld_tap<kShared>(p + pitch + 1) : 0.0f;
+    return v;
 }
 
-// geometry of the block a CTA owns
-struct BlockGeom {
-    int x_lo, y_lo, tiles_x, tiles_y;  // tiles of 4x4 pixels inside the block (edge blocks are partial)
-};
-__device__ __forceinline__ BlockGeom block_geom(int blk, int blocks_x, int Ho, int Wo) {
-    BlockGeom g;
-    const int by = blk / blocks_x, bxi = blk - by * blocks_x;
-    g.x_lo = bxi * kBlk;
-    g.y_lo = by * kBlk;
-    g.tiles_x = (min(Wo, g.x_lo + kBlk) - g.x_lo) >> 2;
-    g.tiles_y = (min(Ho, g.y_lo + kBlk) - g.y_lo) >> 2;
-    return g;
-}
-
-template <bool kMask, bool kShared>
-__device__ __forceinline__ void fwd_block_lists(const Hmat& hm, const Stage& st, float* __restrict__ op, float* __restrict__ mp,
-                                                const BlockGeom& g, int Hs, int Ws, int Wo, const TileLists& L) {
-    const float pitchf = static_cast<float>(st.pitch);
-    // taps may point below the shared window (the box origin sits at its start): 32-bit arithmetic wraps back into it
-    const uint32_t taps_s32 = kShared ? smem_u32(st.taps) : 0u;
-    const int mask_w = Wo >> 2;
-    for (int k = threadIdx.x; k < L.n_in; k += kBlkThreads) {
-        const int tile = L.in[k];
-        const int xt = g.x_lo + (tile & 15) * 4, yt = g.y_lo + (tile >> 4) * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const RowProj rp = row_proj(hm, static_cast<float>(yt + j));
+// one 32x4 group of the forward pass.  kWo > 0: compile-time output pitch (immediate store offsets)
+template <bool kMask, bool kShared, int kWo>
+__device__ __forceinline__ void fwd_group(const ItemView& iv, const ColProj& cp, int cls, float yg, float* __restrict__ og,
+                                          float* __restrict__ mcell, int Hs, int Ws, int Wo_rt) {
+    const int Wo = kWo > 0 ? kWo : Wo_rt;
+    const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
+    if (cls == kInside) {
+        if (iv.xin) {
             float o4[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const Cell c = interior_cell<kShared>(hm, rp, static_cast<float>(xt + i), st.taps, taps_s32, st.pitch, pitchf);
+            for (int j = 0; j < 4; ++j) {
+                float u, v, rw;
+                project_col(iv.hm, cp, yg + static_cast<float>(j), u, v, rw);
+                const Cell4 c = cell_at<kShared>(u, v, iv.wd);
                 const float top = fmaf(c.fx, c.ne - c.nw, c.nw), bot = fmaf(c.fx, c.se - c.sw, c.sw);
-                o4[i] = fmaf(c.fy, bot - top, top);
+                o4[j] = fmaf(c.fy, bot - top, top);
             }
-            stg_stream(reinterpret_cast<float4*>(op + (yt + j) * Wo + xt), make_float4(o4[0], o4[1], o4[2], o4[3]));
-        }
-        if (kMask && mp != nullptr) mp[(yt >> 2) * mask_w + (xt >> 2)] = 1.0f;
-    }
-    for (int k = threadIdx.x; k < L.n_bd; k += kBlkThreads) {
-        const int tile = L.bd[k];
-        const int xt = g.x_lo + (tile & 15) * 4, yt = g.y_lo + (tile >> 4) * 4;
-        float msum = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const RowProj rp = row_proj(hm, static_cast<float>(yt + j));
+            for (int j = 0; j < 4; ++j) st_stream1(og + j * Wo, o4[j]);
+            if (kMask && mcell != nullptr) *mcell = 1.0f;
+        }
+    } else if (cls == kBorder) {
+        float msum = 0.0f;
+        if (iv.xin) {  // lanes right of the output would sample outside the staged box
             float o4[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float u, v, rw, nw, ne, sw, se;
-                project_fast(hm, rp, static_cast<float>(xt + i), u, v, rw);
-                const Taps t = make_taps_fast(u, v, Ws, Hs);
-                border_taps<kShared>(t, st.taps, st.pitch, nw, ne, sw, se);
-                o4[i] = blend(t, nw, ne, sw, se);
-                if (kMask) msum += cover(t);
+            for (int j = 0; j < 4; ++j) {
+                float u, v, rw;
+                project_col(iv.hm, cp, yg + static_cast<float>(j), u, v, rw);
+                if (kShared) {
+                    // zero frame: clamp, then the unpredicated interior sequence (fmaxf / fminf also absorb NaN)
+                    u = fminf(fmaxf(u, -1.0f), Wsf);
+                    v = fminf(fmaxf(v, -1.0f), Hsf);
+                    Cell4 c = cell_at<true>(u, v, iv.wd);
+                    if (iv.wd.xpred) zero_x_taps(c, Ws);
+                    const float top = fmaf(c.fx, c.ne - c.nw, c.nw), bot = fmaf(c.fx, c.se - c.sw, c.sw);
+                    o4[j] = fmaf(c.fy, bot - top, top);
+                    if (kMask) msum = fmaf(cover1(u, Wsf), cover1(v, Hsf), msum);
+                } else {
+                    float nw, ne, sw, se;
+                    const Taps t = make_taps_fast(u, v, Ws, Hs);
+                    global_taps(t, iv.wd.taps, iv.wd.pitch, nw, ne, sw, se);
+                    o4[j] = blend(t, nw, ne, sw, se);
+                    if (kMask) msum += cover(t);
+                }
             }
-            stg_stream(reinterpret_cast<float4*>(op + (yt + j) * Wo + xt), make_float4(o4[0], o4[1], o4[2], o4[3]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_stream1(og + j * Wo, o4[j]);
         }
-        if (kMask && mp != nullptr) mp[(yt >> 2) * mask_w + (xt >> 2)] = msum * 0.0625f;
+        if (kMask) {
+            msum += __shfl_xor_sync(0xffffffffu, msum, 1);
+            msum += __shfl_xor_sync(0xffffffffu, msum, 2);
+            if (mcell != nullptr && iv.xin) *mcell = msum * 0.0625f;
+        }
+    } else if (cls == kOutside) {
+        if (iv.xin) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_stream1(og + j * Wo, 0.0f);
+            if (kMask && mcell != nullptr) *mcell = 0.0f;
+        }
     }
 }
 
-// kMask: also emit the 4x4-pooled coverage mask (written by the CTAs of channel 0)
-template <bool kMask>
-__global__ void __launch_bounds__(kBlkThreads)
-    warp_fwd_block_kernel(const float* __restrict__ src, const float* __restrict__ H, float* __restrict__ out,
-                          float* __restrict__ mask_pooled, int C, int Hs, int Ws, int Ho, int Wo, int blocks_x, int n_blocks) {
+template <bool kMask, bool kShared, int kWo>
+__device__ __forceinline__ void fwd_item(const ItemView& iv, float* __restrict__ out, float* __restrict__ mask_pooled, int Hs, int Ws,
+                                         int Ho, int Wo_rt) {
+    const int Wo = kWo > 0 ? kWo : Wo_rt;
+    const ColProj cp = col_proj(iv.hm, static_cast<float>(iv.x));
+    float* og = out + static_cast<size_t>(iv.plane) * Ho * Wo + iv.y0 * Wo + iv.x;
+    // pooled-mask cell of group 0 (written by the lanes with (lane & 3) == 0 of channel 0)
+    float* mcell = nullptr;
+    if (kMask && iv.c == 0 && (threadIdx.x & 3) == 0)
+        mcell = mask_pooled + static_cast<size_t>(iv.b) * (Ho >> 2) * (Wo >> 2) + (iv.y0 >> 2) * (Wo >> 2) + (iv.x >> 2);
+    const float y0f = static_cast<float>(iv.y0);
+#pragma unroll 1
+    for (int gq = 0; gq < 4; ++gq) {
+        const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
+        fwd_group<kMask, kShared, kWo>(iv, cp, cls, y0f + static_cast<float>(4 * gq), og + gq * 4 * Wo,
+                                       mcell ? mcell + gq * (Wo >> 2) : nullptr, Hs, Ws, Wo_rt);
+    }
+}
+
+// kMask: also emit the 4x4-pooled coverage mask (written by the items of channel 0)
+template <int kBlk, bool kMask, int kWo>
+__global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasPerSm)
+    warp_fwd_ring_kernel(const float* __restrict__ src, const float* __restrict__ H, float* __restrict__ out,
+                         float* __restrict__ mask_pooled, int C, int Hs, int Ws, int Ho, int Wo, int blocks_x, int n_blocks,
+                         int n_items) {
+    using Cfg = RingCfg<kBlk>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    __shared__ TileLists lists;
-    __shared__ StagePub pub;
-    const int blk = blockIdx.x, b = blockIdx.z, plane = b * C + blockIdx.y;
+    __shared__ uint64_t full[Cfg::kStages], empty[Cfg::kStages];
+    __shared__ ItemHeader header[Cfg::kStages];
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], Cfg::kConsumers / 32);
+        }
         fence_mbar_init();
-        lists.n_in = 0;
-        lists.n_bd = 0;
     }
     __syncthreads();
-    const Hmat hm = load_h(H, b);
-    const BlockGeom g = block_geom(blk, blocks_x, Ho, Wo);
-    const float* plane_ptr = src + static_cast<size_t>(plane) * Hs * Ws;
-    if (threadIdx.x < 32)
-        stage_issue_warp0(hm, plane_ptr, reinterpret_cast<float*>(smem_raw), &bar, Ws, Hs, g.x_lo, g.x_lo + g.tiles_x * 4, g.y_lo,
-                          g.y_lo + g.tiles_y * 4, (Ws & 3) == 0, &pub);
-    float* op = out + static_cast<size_t>(plane) * Ho * Wo;
-    float* mp = (kMask && blockIdx.y == 0) ? mask_pooled + static_cast<size_t>(b) * (Ho >> 2) * (Wo >> 2) : nullptr;
-    // classification (and the zero fill of tiles that sample nothing) overlaps the copies in flight
-    {
-        const int tile = threadIdx.x, tx = tile & 15, ty = tile >> 4;
-        int cls = kOutside;
-        if (tx < g.tiles_x && ty < g.tiles_y) {
-            const int xt = g.x_lo + tx * 4, yt = g.y_lo + ty * 4;
-            cls = classify_tile(hm, xt, yt, Ws, Hs);
-            if (cls == kOutside) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    stg_stream(reinterpret_cast<float4*>(op + (yt + j) * Wo + xt), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-                if (kMask && mp != nullptr) mp[(yt >> 2) * (Wo >> 2) + (xt >> 2)] = 0.0f;
+    const int warp = threadIdx.x >> 5;
+    const bool producer = warp == Cfg::kConsumers / 32;
+    int k = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        const int s = k % Cfg::kStages;
+        const uint32_t round = static_cast<uint32_t>(k / Cfg::kStages);
+        float* stage = reinterpret_cast<float*>(smem_raw + s * Cfg::kStageBytes);
+        if (producer) {
+            if (k >= Cfg::kStages) mbar_wait_sleep(&empty[s], (round - 1u) & 1u);  // consumers released the stage
+            ring_produce<kBlk, true>(src, H, it, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
+                                     nullptr);
+        } else {
+            mbar_wait_hint(&full[s], round & 1u);
+            ItemView iv = ring_view(&header[s], src, stage, Hs, Ws);
+            const unsigned classes = ring_classify<kBlk, false>(&header[s], iv.hm, warp, Hs, Ws);
+#pragma unroll 1
+            for (int q = 0; q < Cfg::kStripsPerWarp; ++q) {
+                ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
+                if (iv.wd.shared) fwd_item<kMask, true, kWo>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
+                else fwd_item<kMask, false, kWo>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
             }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
         }
-        lists_push(lists, cls, tile);  // ends with __syncthreads: `pub` is visible
     }
-    Stage st = stage_get(&pub, plane_ptr, reinterpret_cast<const float*>(smem_raw), Ws);
-    stage_wait(st, &bar, 0u);
-    if (st.shared) fwd_block_lists<kMask, true>(hm, st, op, mp, g, Hs, Ws, Wo, lists);
-    else fwd_block_lists<kMask, false>(hm, st, op, mp, g, Hs, Ws, Wo, lists);
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------
+// dH sums of one strip.  A lane keeps its column fixed, so the x factor of the nine sums is applied once at the end:
+// per pixel only  sum a, sum a*y, sum b, sum b*y, sum c, sum c*y  are advanced.
+struct StripSums {
+    float sa, say, sb, sby, sc, scy;
+};
+__device__ __forceinline__ void sums_add(StripSums& t, float gu, float gv, float u, float v, float rw, float y) {
+    const float a = gu * rw, b = gv * rw, c = -fmaf(gu, u, gv * v) * rw;
+    t.sa += a; t.say = fmaf(a, y, t.say);
+    t.sb += b; t.sby = fmaf(b, y, t.sby);
+    t.sc += c; t.scy = fmaf(c, y, t.scy);
 }
 
 template <bool kImage, bool kMask, bool kShared>
-__device__ __forceinline__ void bwd_block_lists(const Hmat& hm, const Stage& st, const float* __restrict__ gp,
-                                                const float* __restrict__ gmp, float (&acc)[9], const BlockGeom& g, int Hs, int Ws,
-                                                int Wo, const TileLists& L) {
-    const float pitchf = static_cast<float>(st.pitch);
-    const uint32_t taps_s32 = kShared ? smem_u32(st.taps) : 0u;
-    const int mask_w = Wo >> 2;
-    if (kImage) {
-        for (int k = threadIdx.x; k < L.n_in; k += kBlkThreads) {
-            const int tile = L.in[k];
-            const int xt = g.x_lo + (tile & 15) * 4, yt = g.y_lo + (tile >> 4) * 4;
-            float4 g4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) g4[j] = ldg_stream(reinterpret_cast<const float4*>(gp + (yt + j) * Wo + xt));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float y = static_cast<float>(yt + j);
-                const RowProj rp = row_proj(hm, y);
-                const float gj[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float x = static_cast<float>(xt + i);
-                    const Cell c = interior_cell<kShared>(hm, rp, x, st.taps, taps_s32, st.pitch, pitchf);
-                    const float dt = c.ne - c.nw, db = c.se - c.sw, dl = c.sw - c.nw, dr = c.se - c.ne;
-                    const float du = fmaf(c.fy, db - dt, dt), dv = fmaf(c.fx, dr - dl, dl);
-                    accum_gh(acc, gj[i] * du, gj[i] * dv, c.u, c.v, c.rw, x, y);
-                }
-            }
-        }
-    }
-    for (int k = threadIdx.x; k < L.n_bd; k += kBlkThreads) {
-        const int tile = L.bd[k];
-        const int xt = g.x_lo + (tile & 15) * 4, yt = g.y_lo + (tile >> 4) * 4;
-        float4 g4[4];
+__device__ __forceinline__ void bwd_group(const ItemView& iv, const ColProj& cp, int cls, float yg, const float (&g4)[4], float gm,
+                                          StripSums& t, int Hs, int Ws) {
+    const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
+    if (!iv.xin) return;
+    if (cls == kInside) {
         if (kImage) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) g4[j] = ldg_stream(reinterpret_cast<const float4*>(gp + (yt + j) * Wo + xt));
+            for (int j = 0; j < 4; ++j) {
+                const float y = yg + static_cast<float>(j);
+                float u, v, rw;
+                project_col(iv.hm, cp, y, u, v, rw);
+                const Cell4 c = cell_at<kShared>(u, v, iv.wd);
+                const float dt = c.ne - c.nw, db = c.se - c.sw, dl = c.sw - c.nw, dr = c.se - c.ne;
+                const float du = fmaf(c.fy, db - dt, dt), dv = fmaf(c.fx, dr - dl, dl);
+                sums_add(t, g4[j] * du, g4[j] * dv, u, v, rw, y);
+            }
         }
-        const float gm = (kMask && gmp != nullptr) ? __ldg(gmp + (yt >> 2) * mask_w + (xt >> 2)) * 0.0625f : 0.0f;
+    } else if (cls == kBorder) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float y = static_cast<float>(yt + j);
-            const RowProj rp = row_proj(hm, y);
-            const float gj[4] = {kImage ? g4[j].x : 0.0f, kImage ? g4[j].y : 0.0f, kImage ? g4[j].z : 0.0f, kImage ? g4[j].w : 0.0f};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float x = static_cast<float>(xt + i);
-                float u, v, rw;
-                project_fast(hm, rp, x, u, v, rw);
-                const Taps t = make_taps_fast(u, v, Ws, Hs);
-                float gu = 0.0f, gv = 0.0f;
+            const float y = yg + static_cast<float>(j);
+            float u, v, rw;
+            project_col(iv.hm, cp, y, u, v, rw);
+            float gu = 0.0f, gv = 0.0f;
+            if (kShared) {
+                const float uc = fminf(fmaxf(u, -1.0f), Wsf), vc = fminf(fmaxf(v, -1.0f), Hsf);
+                if (kImage) {
+                    Cell4 c = cell_at<true>(uc, vc, iv.wd);
+                    if (iv.wd.xpred) zero_x_taps(c, Ws);
+                    const float dt = c.ne - c.nw, db = c.se - c.sw, dl = c.sw - c.nw, dr = c.se - c.ne;
+                    gu = g4[j] * fmaf(c.fy, db - dt, dt);
+                    gv = g4[j] * fmaf(c.fx, dr - dl, dl);
+                }
+                if (kMask) {
+                    gu = fmaf(gm, cover1(vc, Hsf) * cover1_grad(uc, Wsf), gu);
+                    gv = fmaf(gm, cover1(uc, Wsf) * cover1_grad(vc, Hsf), gv);
+                }
+                // a clamped coordinate does not move with H (also true for NaN: the comparison fails)
+                if (!(uc == u && vc == v)) { gu = 0.0f; gv = 0.0f; u = 0.0f; v = 0.0f; rw = 0.0f; }
+            } else {
+                const Taps tp = make_taps_fast(u, v, Ws, Hs);
                 if (kImage) {
                     float nw, ne, sw, se, du, dv;
-                    border_taps<kShared>(t, st.taps, st.pitch, nw, ne, sw, se);
-                    blend_grad(t, nw, ne, sw, se, du, dv);
-                    gu = gj[i] * du;
-                    gv = gj[i] * dv;
+                    global_taps(tp, iv.wd.taps, iv.wd.pitch, nw, ne, sw, se);
+                    blend_grad(tp, nw, ne, sw, se, du, dv);
+                    gu = g4[j] * du;
+                    gv = g4[j] * dv;
                 }
                 if (kMask) {
                     float du, dv;
-                    cover_grad(t, du, dv);
+                    cover_grad(tp, du, dv);
                     gu = fmaf(gm, du, gu);
                     gv = fmaf(gm, dv, gv);
                 }
-                accum_gh(acc, gu, gv, u, v, rw, x, y);
             }
+            sums_add(t, gu, gv, u, v, rw, y);
         }
     }
 }
 
-// Backward: CTA = (sample, 64x64 output block), all C planes in turn; its 9 partial sums go to partials[b][block][9]
-// and warp_bwd_finish_kernel adds the blocks in order (bit reproducible, no atomics).
-// kMask: the pooled-mask upstream (pool == 4) is folded into the same pass (channel 0).
-template <bool kImage, bool kMask>
-__global__ void __launch_bounds__(kBlkThreads)
-    warp_bwd_block_kernel(const float* __restrict__ src, const float* __restrict__ H, const float* __restrict__ gOut,
-                          const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C, int Hs, int Ws, int Ho,
-                          int Wo, int blocks_x, int n_blocks) {
+// sum of nine per-lane values over the warp: butterfly that halves the number of live values at every step
+// (9 + 5 shuffles instead of 45); on return lane 4*i (i < 8) holds total i in r, lane 0 also holds total 8 in r8
+__device__ __forceinline__ void warp_reduce9(const float (&v)[9], float& r, float& r8) {
+    const unsigned lane = threadIdx.x & 31u;
+    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u;
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float c[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b3 ? a[i + 2] : a[i], send = b3 ? a[i] : a[i + 2];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float keep = b2 ? c[1] : c[0], send = b2 ? c[0] : c[1];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    r = d;   // lane L holds total index (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)
+    r8 = warp_sum(v[8]);
+}
+
+template <bool kImage, bool kMask, bool kShared>
+__device__ __forceinline__ void bwd_item(const ItemView& iv, const float* __restrict__ gOut, const float* __restrict__ gMaskPooled,
+                                         float (&acc)[9], int Hs, int Ws, int Ho, int Wo) {
+    const float xf = static_cast<float>(iv.x);
+    const ColProj cp = col_proj(iv.hm, xf);
+    const float* gcol = nullptr;
+    if (kImage) gcol = gOut + static_cast<size_t>(iv.plane) * Ho * Wo + iv.y0 * Wo + iv.x;
+    const float* mcell = nullptr;
+    if (kMask && iv.c == 0) mcell = gMaskPooled + static_cast<size_t>(iv.b) * (Ho >> 2) * (Wo >> 2) + (iv.y0 >> 2) * (Wo >> 2) + (iv.x >> 2);
+    const float y0f = static_cast<float>(iv.y0);
+    StripSums t = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    // the upstream gradients of group gq + 1 are requested before group gq is sampled: their latency hides behind it.
+    // (loops deliberately not unrolled: the body is large and the instruction cache is the scarcer resource)
+    float gcur[4], gnext[4];
+    {
+        const int cls = iv.cls4 & 0xf;
+        const bool need = kImage && iv.xin && (cls == kInside || cls == kBorder);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gcur[j] = need ? ld_stream1(gcol + j * Wo) : 0.0f;
+    }
+#pragma unroll 1
+    for (int gq = 0; gq < 4; ++gq) {
+        const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
+        {
+            const int cn = (iv.cls4 >> (4 * (gq + 1))) & 0xf;   // gq == 3: bits 16.. are zero or the next strip's class; unused
+            const bool need = kImage && iv.xin && gq < 3 && (cn == kInside || cn == kBorder);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gnext[j] = need ? ld_stream1(gcol + ((gq + 1) * 4 + j) * Wo) : 0.0f;
+        }
+        float gm = 0.0f;
+        if (kMask && mcell != nullptr && cls == kBorder && iv.xin) gm = __ldg(mcell + gq * (Wo >> 2)) * 0.0625f;
+        bwd_group<kImage, kMask, kShared>(iv, cp, cls, y0f + static_cast<float>(4 * gq), gcur, gm, t, Hs, Ws);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gcur[j] = gnext[j];
+    }
+    acc[0] = t.sa * xf; acc[1] = t.say; acc[2] = t.sa;
+    acc[3] = t.sb * xf; acc[4] = t.sby; acc[5] = t.sb;
+    acc[6] = t.sc * xf; acc[7] = t.scy; acc[8] = t.sc;
+}
+
+// Every consumer warp writes the nine sums of each of its strips to partials[plane][block][strip][9] (no CTA-wide
+// barrier), warp_bwd_finish_kernel adds them in a fixed order (bit reproducible, no atomics).
+// kImage: gOut given (source staged); false = mask gradient only.  kMask: the pooled-mask upstream (pool == 4) is folded
+// into the same pass (channel 0).
+template <int kBlk, bool kImage, bool kMask>
+__global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasPerSm)
+    warp_bwd_ring_kernel(const float* __restrict__ src, const float* __restrict__ H, const float* __restrict__ gOut,
+                         const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C, int Hs, int Ws, int Ho,
+                         int Wo, int blocks_x, int n_blocks, int n_items) {
+    using Cfg = RingCfg<kBlk>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    __shared__ float red[9 * (kBlkThreads / 32)];
-    __shared__ TileLists lists;
-    __shared__ StagePub pub;
-    const int blk = blockIdx.x, b = blockIdx.y;
+    __shared__ uint64_t full[Cfg::kStages], empty[Cfg::kStages];
+    __shared__ ItemHeader header[Cfg::kStages];
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], Cfg::kConsumers / 32);
+        }
         fence_mbar_init();
-        lists.n_in = 0;
-        lists.n_bd = 0;
     }
     __syncthreads();
-    const Hmat hm = load_h(H, b);
-    const BlockGeom g = block_geom(blk, blocks_x, Ho, Wo);
-    const float* plane0 = kImage ? src + static_cast<size_t>(b) * C * Hs * Ws : nullptr;
-    if (kImage && threadIdx.x < 32)
-        stage_issue_warp0(hm, plane0, reinterpret_cast<float*>(smem_raw), &bar, Ws, Hs, g.x_lo, g.x_lo + g.tiles_x * 4, g.y_lo,
-                          g.y_lo + g.tiles_y * 4, (Ws & 3) == 0, &pub);
-    {
-        const int tile = threadIdx.x, tx = tile & 15, ty = tile >> 4;
-        int cls = kOutside;  // zero taps, zero coverage: no gradient
-        if (tx < g.tiles_x && ty < g.tiles_y) {
-            cls = classify_tile(hm, g.x_lo + tx * 4, g.y_lo + ty * 4, Ws, Hs);
-            if (cls == kInside && !kImage) cls = kOutside;  // coverage is constant 1 inside
-        }
-        lists_push(lists, cls, tile);  // ends with __syncthreads: `pub` is visible
-    }
-    float acc[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.0f;
-    const float* gmp = kMask ? gMaskPooled + static_cast<size_t>(b) * (Ho >> 2) * (Wo >> 2) : nullptr;
-    if (kImage) {
-        for (int c = 0; c < C; ++c) {
-            const size_t plane = static_cast<size_t>(b) * C + c;
-            const float* plane_ptr = src + plane * Hs * Ws;
-            if (c > 0) {
-                __syncthreads();  // the staging buffer is reused
-                if (threadIdx.x < 32)
-                    stage_issue_warp0(hm, plane_ptr, reinterpret_cast<float*>(smem_raw), &bar, Ws, Hs, g.x_lo, g.x_lo + g.tiles_x * 4,
-                                      g.y_lo, g.y_lo + g.tiles_y * 4, (Ws & 3) == 0, &pub);
-                __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const bool producer = warp == Cfg::kConsumers / 32;
+    int k = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
+        const int s = k % Cfg::kStages;
+        const uint32_t round = static_cast<uint32_t>(k / Cfg::kStages);
+        float* stage = reinterpret_cast<float*>(smem_raw + s * Cfg::kStageBytes);
+        if (producer) {
+            if (k >= Cfg::kStages) mbar_wait_sleep(&empty[s], (round - 1u) & 1u);
+            ring_produce<kBlk, kImage>(src, H, it, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
+                                       kImage ? gOut : nullptr);
+        } else {
+            mbar_wait_hint(&full[s], round & 1u);
+            ItemView iv = ring_view(&header[s], src, stage, Hs, Ws);
+            const unsigned classes = ring_classify<kBlk, !kImage>(&header[s], iv.hm, warp, Hs, Ws);
+            const unsigned lane = threadIdx.x & 31u;
+#pragma unroll 1
+            for (int q = 0; q < Cfg::kStripsPerWarp; ++q) {
+                ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
+                float acc[9];
+                if (iv.wd.shared) bwd_item<kImage, kMask, true>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
+                else bwd_item<kImage, kMask, false>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
+                if (q == Cfg::kStripsPerWarp - 1) {
+                    __syncwarp();
+                    if (lane == 0u) mbar_arrive(&empty[s]);   // the window is free while the last sums are reduced
+                }
+                float r, r8;
+                warp_reduce9(acc, r, r8);
+                const int sidx = warp + q * (Cfg::kConsumers / 32);
+                float* dst = partials + ((static_cast<size_t>(iv.plane) * n_blocks + iv.blk) * Cfg::kStrips + sidx) * 9;
+                if ((lane & 3u) == 0u) dst[((lane >> 4) & 1u) * 4u + ((lane >> 3) & 1u) * 2u + ((lane >> 2) & 1u)] = r;
+                if (lane == 0u) dst[8] = r8;
             }
-            Stage st = stage_get(&pub, plane_ptr, reinterpret_cast<const float*>(smem_raw), Ws);
-            stage_wait(st, &bar, static_cast<uint32_t>(c & 1));
-            const float* gp = gOut + plane * Ho * Wo;
-            const float* gm_c = (c == 0) ? gmp : nullptr;
-            if (st.shared) bwd_block_lists<true, kMask, true>(hm, st, gp, gm_c, acc, g, Hs, Ws, Wo, lists);
-            else bwd_block_lists<true, kMask, false>(hm, st, gp, gm_c, acc, g, Hs, Ws, Wo, lists);
         }
-    } else {
-        Stage none;
-        none.taps = nullptr; none.pitch = Ws; none.shared = false; none.pending = false;
-        bwd_block_lists<false, true, false>(hm, none, nullptr, gmp, acc, g, Hs, Ws, Wo, lists);
     }
-    block_sum<9>(acc, red);
-    store9(acc, partials + (static_cast<size_t>(b) * n_blocks + blk) * 9);
 }
 
 // =================================================================================================
@@ -724,20 +984,72 @@ __global__ void warp_bwd_finish_kernel(const float* __restrict__ partials, float
 }
 
 // ---- host-side path selection --------------------------------------------------------------------
-// block path applies to NCHW tensors whose output is made of whole 4x4 tiles; source boxes that do not fit the staging
-// budget (or unaligned row pitches) are read through the read-only cache instead -- same kernel
-inline bool block_ok(int Ho, int Wo, int channels_last) { return !channels_last && (Ho % 4) == 0 && (Wo % 4) == 0; }
-constexpr int kMaxGridYZ = 65535;
-inline int blocks_of(int n) { return (n + kBlk - 1) / kBlk; }
+// ring path: NCHW tensors whose output is made of whole 4x4 tiles and whose coordinates stay below 2^22; everything else
+// (channels-last, odd sizes) goes to the nhwc / generic kernels
+inline bool ring_ok(int Hs, int Ws, int Ho, int Wo, int channels_last) {
+    return !channels_last && (Ho % 4) == 0 && (Wo % 4) == 0 && Hs < (1 << 20) && Ws < (1 << 20) && Ho < (1 << 20) && Wo < (1 << 20) &&
+           static_cast<long long>(Hs) * Ws < (1ll << 30) && static_cast<long long>(Ho) * Wo < (1ll << 30);
+}
+// item size: whole planes when the source fits one 72 KB stage with its frame, 64x64 blocks otherwise
+inline int ring_blk(int Hs, int Ws) {
+    return (static_cast<long long>(Hs + kPadT + kPadB) * Ws * 4 + 32 <= RingCfg<128>::kStageBytes && (Ws & 3) == 0) ? 128 : 64;
+}
+inline int blocks_of(int n, int side) { return (n + side - 1) / side; }
 inline int bwd_chunks(int Ho, int Wo, int C, int vec) {
     const long long work = static_cast<long long>(Ho) * Wo * (vec ? C / 4 : 1);
     long long c = (work + 256 * 16 - 1) / (256 * 16);
     return static_cast<int>(c < 1 ? 1 : (c > 1024 ? 1024 : c));
 }
+template <int kBlk>
+inline int ring_grid(long long n_items) {
+    const long long cap = static_cast<long long>(kNumSMs) * RingCfg<kBlk>::kCtasPerSm;
+    return static_cast<int>(n_items < cap ? n_items : cap);
+}
 inline int grid_for(long long n, int threads) {
     long long g = (n + threads - 1) / threads;
     const long long cap = static_cast<long long>(kNumSMs) * 16;
     return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <int kBlk>
+inline int launch_fwd_ring(const float* src, const float* H, float* out, float* mask_pooled, int B, int C, int Hs, int Ws, int Ho, int Wo,
+                           bool fuse_mask, cudaStream_t stream) {
+    using Cfg = RingCfg<kBlk>;
+    const int blocks_x = blocks_of(Wo, kBlk), n_blocks = blocks_x * blocks_of(Ho, kBlk);
+    const long long n_items = static_cast<long long>(B) * C * n_blocks;
+    void (*kern)(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int);
+    if (Wo == 128) kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 128> : warp_fwd_ring_kernel<kBlk, false, 128>;
+    else kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 0> : warp_fwd_ring_kernel<kBlk, false, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    kern<<<ring_grid<kBlk>(n_items), Cfg::kThreads, Cfg::kSmem, stream>>>(src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo, blocks_x, n_blocks,
+                                                                          static_cast<int>(n_items));
+    return launch_status();
+}
+
+// chunks of nine partial sums per sample that the ring backward writes
+template <int kBlk>
+inline int ring_bwd_chunks(int Cw, int Ho, int Wo) {
+    return Cw * blocks_of(Wo, kBlk) * blocks_of(Ho, kBlk) * RingCfg<kBlk>::kStrips;
+}
+template <int kBlk>
+inline int launch_bwd_ring(const float* src, const float* H, const float* gOut, const float* gMaskPooled, float* partials, int B, int Cw,
+                           int Hs, int Ws, int Ho, int Wo, cudaStream_t stream) {
+    using Cfg = RingCfg<kBlk>;
+    const int blocks_x = blocks_of(Wo, kBlk), n_blocks = blocks_x * blocks_of(Ho, kBlk);
+    const long long n_items = static_cast<long long>(B) * Cw * n_blocks;
+    void (*kern)(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int);
+    if (gOut && gMaskPooled) kern = warp_bwd_ring_kernel<kBlk, true, true>;
+    else if (gOut) kern = warp_bwd_ring_kernel<kBlk, true, false>;
+    else kern = warp_bwd_ring_kernel<kBlk, false, true>;
+    const int smem = gOut ? Cfg::kSmem : 0;
+    if (smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    kern<<<ring_grid<kBlk>(n_items), Cfg::kThreads, smem, stream>>>(src, H, gOut, gMaskPooled, partials, Cw, Hs, Ws, Ho, Wo, blocks_x, n_blocks,
+                                                                    static_cast<int>(n_items));
+    return launch_status();
 }
 
 }  // namespace bh
@@ -755,25 +1067,23 @@ extern "C" int bh_warp_fwd(const float* src, const float* H, float* out, float* 
     int rc = BH_OK;
     bool mask_done = (mask_pooled == nullptr);
     if (src) {
-        if (block_ok(Ho, Wo, channels_last) && C <= kMaxGridYZ && B <= kMaxGridYZ) {
-            const int blocks_x = blocks_of(Wo), n_blocks = blocks_x * blocks_of(Ho);
+        const long long n_items64 = static_cast<long long>(B) * C * blocks_of(Wo, 64) * blocks_of(Ho, 64);
+        if (ring_ok(Hs, Ws, Ho, Wo, channels_last) && n_items64 < (1ll << 31)) {
             const bool fuse_mask = mask_pooled && pool == 4;
-            auto kern = fuse_mask ? warp_fwd_block_kernel<true> : warp_fwd_block_kernel<false>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlkSmemBytes);
-            if (e != cudaSuccess) return static_cast<int>(e);
-            kern<<<dim3(n_blocks, C, B), kBlkThreads, kBlkSmemBytes, stream>>>(src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo,
-                                                                               blocks_x, n_blocks);
+            rc = ring_blk(Hs, Ws) == 128 ? launch_fwd_ring<128>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream)
+                                         : launch_fwd_ring<64>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream);
             mask_done = mask_done || fuse_mask;
         } else if (channels_last && (C % 4) == 0) {
             const long long n = static_cast<long long>(B) * Ho * Wo * (C / 4);
             warp_fwd_nhwc_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, H, out, B, C, Hs, Ws, Ho, Wo);
+            rc = launch_status();
         } else {
             const long long n = static_cast<long long>(B) * Ho * Wo;
             warp_fwd_generic_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, H, out, B, C, Hs, Ws, Ho, Wo,
                                                                           make_layout(C, Hs, Ws, channels_last),
                                                                           make_layout(C, Ho, Wo, channels_last));
+            rc = launch_status();
         }
-        rc = launch_status();
         if (rc != BH_OK) return rc;
     }
     if (!mask_done) {
@@ -789,8 +1099,10 @@ extern "C" size_t bh_warp_bwd_workspace_bytes(int B, int C, int Hs, int Ws, int 
     if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
     const int vec = channels_last && C > 0 && (C % 4) == 0;
     const size_t generic = static_cast<size_t>(B) * bwd_chunks(Ho, Wo, C > 0 ? C : 1, vec) * 9 * sizeof(float);
-    const size_t blocks = static_cast<size_t>(B) * blocks_of(Wo) * blocks_of(Ho) * 9 * sizeof(float);
-    return generic > blocks ? generic : blocks;
+    const int Cw = C > 0 ? C : 1;
+    const int rc64 = ring_bwd_chunks<64>(Cw, Ho, Wo), rc128 = ring_bwd_chunks<128>(Cw, Ho, Wo);
+    const size_t ring = static_cast<size_t>(B) * (rc64 > rc128 ? rc64 : rc128) * 9 * sizeof(float);
+    return generic > ring ? generic : ring;
 }
 
 extern "C" int bh_warp_bwd(const float* src, const float* H, const float* gOut, const float* gMaskPooled, float* gH,
@@ -806,24 +1118,18 @@ extern "C" int bh_warp_bwd(const float* src, const float* H, const float* gOut, 
     if (gMaskPooled && (pool <= 0 || Ho % pool || Wo % pool)) return BH_E_SHAPE;
     if (gOut && (!aligned16(src) || !aligned16(gOut))) return BH_E_ALIGN;
     const bool mask4 = gMaskPooled == nullptr || pool == 4;
-    if (!gSrc && mask4 && B <= kMaxGridYZ && block_ok(Ho, Wo, gOut ? channels_last : 0)) {
-        const int blocks_x = blocks_of(Wo), n_blocks = blocks_x * blocks_of(Ho);
-        const size_t need = static_cast<size_t>(B) * n_blocks * 9 * sizeof(float);
+    const int Cw = gOut ? C : 1;   // coverage-only work has one "plane" per sample
+    const long long n_items64 = static_cast<long long>(B) * Cw * blocks_of(Wo, 64) * blocks_of(Ho, 64);
+    if (!gSrc && mask4 && ring_ok(Hs, Ws, Ho, Wo, gOut ? channels_last : 0) && n_items64 < (1ll << 31)) {
+        const bool planes = ring_blk(Hs, Ws) == 128;
+        const int chunks = planes ? ring_bwd_chunks<128>(Cw, Ho, Wo) : ring_bwd_chunks<64>(Cw, Ho, Wo);
+        const size_t need = static_cast<size_t>(B) * chunks * 9 * sizeof(float);
         if (!workspace || workspace_bytes < need) return BH_E_WORKSPACE;
         float* partials = static_cast<float*>(workspace);
-        const size_t smem = gOut ? kBlkSmemBytes : 0;
-        void (*kern)(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int);
-        if (gOut && gMaskPooled) kern = warp_bwd_block_kernel<true, true>;
-        else if (gOut) kern = warp_bwd_block_kernel<true, false>;
-        else kern = warp_bwd_block_kernel<false, true>;
-        if (smem) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (e != cudaSuccess) return static_cast<int>(e);
-        }
-        kern<<<dim3(n_blocks, B), kBlkThreads, smem, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, blocks_x, n_blocks);
-        int rc = launch_status();
+        int rc = planes ? launch_bwd_ring<128>(src, H, gOut, gMaskPooled, partials, B, Cw, Hs, Ws, Ho, Wo, stream)
+                        : launch_bwd_ring<64>(src, H, gOut, gMaskPooled, partials, B, Cw, Hs, Ws, Ho, Wo, stream);
         if (rc != BH_OK) return rc;
-        warp_bwd_finish_kernel<<<(B * 9 + 127) / 128, 128, 0, stream>>>(partials, gH, B, n_blocks);
+        warp_bwd_finish_kernel<<<(B * 9 + 127) / 128, 128, 0, stream>>>(partials, gH, B, chunks);
         return launch_status();
     }
     const int vec = gOut && channels_last && (C % 4) == 0;

@@ -121,10 +121,13 @@ def _rand_h(B, P, gen, scale=0.25):
 
 
 WARP_SHAPES = [
-    (5, 1, 128, 128, 128, 128, False),     # plane path, north-star shape
-    (300, 1, 128, 128, 128, 128, False),   # more planes than SMs: ring wrap-around
-    (2, 3, 64, 96, 32, 48, False),         # plane path, C>1, rectangular, resampling
-    (2, 1, 240, 320, 240, 320, False),     # plane too large for shared memory -> generic
+    (5, 1, 128, 128, 128, 128, False),     # ring path, north-star shape
+    (300, 1, 128, 128, 128, 128, False),   # more items than resident CTAs: every CTA walks several items through both stages
+    (2, 3, 64, 96, 32, 48, False),         # ring path, C>1, rectangular, resampling
+    (2, 1, 240, 320, 240, 320, False),     # large plane: every block stages its own source box
+    (2, 2, 256, 256, 64, 64, False),       # 4x down-sampling: the box of a block exceeds the stage -> read-only cache taps
+    (3, 1, 128, 128, 192, 160, False),     # 1.5x up-sampling, several blocks per plane, partial blocks
+    (3, 1, 128, 128, 36, 44, False),       # partial strips (36 = 2 x 16 + 4 rows, 44 = 32 + 12 columns)
     (3, 2, 37, 53, 29, 31, False),         # odd sizes -> generic
     (2, 8, 40, 40, 40, 40, True),          # channels-last vec4
     (2, 6, 33, 20, 17, 24, True),          # channels-last generic

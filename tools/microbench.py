@@ -141,6 +141,7 @@ def main():
     ap.add_argument('--sweep', action='store_true')
     ap.add_argument('--once', action='store_true')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--warp-only', action='store_true', help='time only the 1-channel image warp (forward + backward)')
     a = ap.parse_args()
     torch.manual_seed(0)
     if a.once:
@@ -152,6 +153,10 @@ def main():
         bench_small(256, 128, t)
         return
     t = Timer(a.iters)
+    if a.warp_only:
+        for B, P in ((256, 128), (1024, 128), (4096, 128), (256, 256), (64, 512)):
+            bench_image_warp(B, P, t)
+        return
     print(json.dumps({'peak_GBps_measured': PEAK, 'timing': 'cuda events, L2 flushed before every launch, mean of %d' % a.iters}))
     shapes = [(256, 128, 64)]
     if a.sweep:
