@@ -1,0 +1,34 @@
+# usage (through gpurun): bash tools/gpu_round.sh <tag> [stages]     outputs under gpurun_out/
+# stages: any of t(ests) b(ench) r(eference arm) m(icrobench) l(aunch list) n(cu full) s(moke); default "tsbmln"
+# Every stage runs under its own `timeout` so a hung kernel cannot hold the box.
+TAG=${1:-r01}
+ST=${2:-tsbmln}
+mkdir -p gpurun_out
+has() { case "$ST" in *$1*) return 0;; *) return 1;; esac; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi_$TAG.txt 2>&1
+if has t; then
+  timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
+  tail -5 gpurun_out/pytest_$TAG.log
+fi
+if has s; then
+  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_$TAG.log
+fi
+if has b; then
+  timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_$TAG.json
+fi
+if has r; then
+  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"; cat gpurun_out/bench_ref_$TAG.json
+fi
+if has m; then
+  timeout 600 python tools/microbench.py > gpurun_out/microbench_$TAG.jsonl 2>&1; echo "microbench rc=$?"; head -14 gpurun_out/microbench_$TAG.jsonl
+fi
+if has l; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches_$TAG.csv \
+      python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "launch list rc=$?"
+fi
+if has n; then
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:"bihome_kernel|warp_fwd_ring|warp_bwd_ring|dltn_fwd|dltn_bwd|pairgen_apply|warp_fwd_nhwc|warp_bwd_generic" -c 24 -f \
+      -o gpurun_out/prof_kernels_$TAG python tools/microbench.py --once > gpurun_out/once_$TAG.log 2>&1; echo "ncu full rc=$?"
+fi
+ls -la gpurun_out
