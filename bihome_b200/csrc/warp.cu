@@ -162,6 +162,45 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
     return r;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2) ----------------------------------------------------------
+// The ring kernels are bound by instruction issue, not by a pipe: the two rows a lane handles at a time share one
+// instruction.  A value of type f2 is a 64-bit register pair (lo, hi) = (row j, row j + 1); pk() of two equal scalars
+// costs nothing (the SASS forms take a broadcast 32-bit operand, negation folded in).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void upk_bits(f2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 add2_rm(f2 a, f2 b) {
+    f2 d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 dup2(float v) { return pk(v, v); }
+
 // geometry of the block an item covers
 struct BlockGeom {
     int x_lo, y_lo, x_hi, y_hi;  // [x_lo, x_hi) x [y_lo, y_hi), multiples of 4
@@ -221,6 +260,20 @@ __device__ __forceinline__ void project_col(const Hmat& m, const ColProj& cp, fl
     v = fmaf(fmaf(-q, w, ny), r, q);
     rw = r;
 }
+// the same for rows (y, y + 1) of a column, bit for bit: -w is carried instead of w so that every step is a plain FFMA2
+__device__ __forceinline__ void project_col2(const Hmat& m, const ColProj& cp, f2 y2, f2& u2, f2& v2, f2& r2) {
+    const f2 mw = fma2(dup2(-m.h[7]), y2, dup2(-cp.aw));
+    const f2 nx = fma2(dup2(m.h[1]), y2, dup2(cp.ax)), ny = fma2(dup2(m.h[4]), y2, dup2(cp.ay));
+    float m0, m1, r0, r1;
+    upk(mw, m0, m1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-m0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-m1));
+    r2 = pk(r0, r1);
+    f2 q = mul2(nx, r2);
+    u2 = fma2(fma2(q, mw, nx), r2, q);
+    q = mul2(ny, r2);
+    v2 = fma2(fma2(q, mw, ny), r2, q);
+}
 
 // Where the taps of an item live: the framed shared window, or the whole plane in global memory.
 struct Window {
@@ -267,6 +320,58 @@ __device__ __forceinline__ void zero_x_taps(Cell4& c, int Ws) {
     c.sw = l ? c.sw : 0.0f;
     c.ne = r ? c.ne : 0.0f;
     c.se = r ? c.se : 0.0f;
+}
+// Two cells at once (rows j, j + 1 of a lane) out of a shared window; kPitch > 0: compile-time window pitch.
+// xpred: dense window, see zero_x_taps.
+struct Cell8 {
+    f2 fx, fy, nw, ne, sw, se;
+};
+template <int kPitch>
+__device__ __forceinline__ Cell8 cell_at2(f2 u2, f2 v2, const Window& wd, bool xpred, int Ws) {
+    Cell8 c;
+    const f2 tx = add2_rm(u2, dup2(kMagic)), ty = add2_rm(v2, dup2(kMagic));
+    c.fx = sub2(u2, add2(tx, dup2(-kMagic)));
+    c.fy = sub2(v2, add2(ty, dup2(-kMagic)));
+    uint32_t tx0, tx1, ty0, ty1;
+    upk_bits(tx, tx0, tx1);
+    upk_bits(ty, ty0, ty1);
+    const uint32_t pitch = kPitch > 0 ? static_cast<uint32_t>(kPitch) : static_cast<uint32_t>(wd.pitch);
+    const uint32_t a0 = wd.base_s32 + (ty0 * pitch + tx0) * 4u, a1 = wd.base_s32 + (ty1 * pitch + tx1) * 4u;
+    float n0, e0, s0, t0, n1, e1, s1, t1;   // nw, ne, sw, se of row j / row j + 1
+    if (kPitch > 0) {
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(n0) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(e0) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(s0) : "r"(a0), "n"(kPitch * 4));
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(t0) : "r"(a0), "n"(kPitch * 4 + 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(n1) : "r"(a1));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(e1) : "r"(a1));
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(s1) : "r"(a1), "n"(kPitch * 4));
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(t1) : "r"(a1), "n"(kPitch * 4 + 4));
+    } else {
+        const uint32_t b0 = a0 + pitch * 4u, b1 = a1 + pitch * 4u;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(n0) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(e0) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s0) : "r"(b0));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(t0) : "r"(b0));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(n1) : "r"(a1));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(e1) : "r"(a1));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s1) : "r"(b1));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(t1) : "r"(b1));
+    }
+    if (xpred) {
+        const int i0 = static_cast<int>(tx0) - kMagicBits, i1 = static_cast<int>(tx1) - kMagicBits;
+        const bool l0 = static_cast<unsigned>(i0) < static_cast<unsigned>(Ws), r0 = static_cast<unsigned>(i0 + 1) < static_cast<unsigned>(Ws);
+        const bool l1 = static_cast<unsigned>(i1) < static_cast<unsigned>(Ws), r1 = static_cast<unsigned>(i1 + 1) < static_cast<unsigned>(Ws);
+        n0 = l0 ? n0 : 0.0f; s0 = l0 ? s0 : 0.0f; e0 = r0 ? e0 : 0.0f; t0 = r0 ? t0 : 0.0f;
+        n1 = l1 ? n1 : 0.0f; s1 = l1 ? s1 : 0.0f; e1 = r1 ? e1 : 0.0f; t1 = r1 ? t1 : 0.0f;
+    }
+    c.nw = pk(n0, n1); c.ne = pk(e0, e1); c.sw = pk(s0, s1); c.se = pk(t0, t1);
+    return c;
+}
+// bilinear blend of two cells: the scalar sequence of fwd_group, two rows per instruction
+__device__ __forceinline__ f2 lerp2(const Cell8& c) {
+    const f2 top = fma2(c.fx, sub2(c.ne, c.nw), c.nw), bot = fma2(c.fx, sub2(c.se, c.sw), c.sw);
+    return fma2(c.fy, sub2(bot, top), top);
 }
 // predicated taps for the global-memory fallback (no frame there)
 __device__ __forceinline__ Taps make_taps_fast(float u, float v, int Ws, int Hs) {
@@ -467,8 +572,9 @@ __device__ __forceinline__ ItemView ring_view(const ItemHeader* hd, const float*
     return v;
 }
 
-// one 32x4 group of the forward pass.  kWo > 0: compile-time output pitch (immediate store offsets)
-template <bool kMask, bool kShared, int kWo>
+// one 32x4 group of the forward pass.  kWo > 0: compile-time output pitch (immediate store offsets); kPitch > 0:
+// compile-time window pitch.  Shared windows go through the packed two-rows-per-instruction sequence.
+template <bool kMask, bool kShared, int kWo, int kPitch>
 __device__ __forceinline__ void fwd_group(const ItemView& iv, const ColProj& cp, int cls, float yg, float* __restrict__ og,
                                           float* __restrict__ mcell, int Hs, int Ws, int Wo_rt) {
     const int Wo = kWo > 0 ? kWo : Wo_rt;
@@ -476,13 +582,22 @@ __device__ __forceinline__ void fwd_group(const ItemView& iv, const ColProj& cp,
     if (cls == kInside) {
         if (iv.xin) {
             float o4[4];
+            if (kShared) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float u, v, rw;
-                project_col(iv.hm, cp, yg + static_cast<float>(j), u, v, rw);
-                const Cell4 c = cell_at<kShared>(u, v, iv.wd);
-                const float top = fmaf(c.fx, c.ne - c.nw, c.nw), bot = fmaf(c.fx, c.se - c.sw, c.sw);
-                o4[j] = fmaf(c.fy, bot - top, top);
+                for (int p = 0; p < 2; ++p) {
+                    f2 u2, v2, r2;
+                    project_col2(iv.hm, cp, add2(dup2(yg), pk(2.0f * p, 2.0f * p + 1.0f)), u2, v2, r2);
+                    upk(lerp2(cell_at2<kPitch>(u2, v2, iv.wd, false, Ws)), o4[2 * p], o4[2 * p + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float u, v, rw;
+                    project_col(iv.hm, cp, yg + static_cast<float>(j), u, v, rw);
+                    const Cell4 c = cell_at<false>(u, v, iv.wd);
+                    const float top = fmaf(c.fx, c.ne - c.nw, c.nw), bot = fmaf(c.fx, c.se - c.sw, c.sw);
+                    o4[j] = fmaf(c.fy, bot - top, top);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) st_stream1(og + j * Wo, o4[j]);
@@ -492,21 +607,28 @@ __device__ __forceinline__ void fwd_group(const ItemView& iv, const ColProj& cp,
         float msum = 0.0f;
         if (iv.xin) {  // lanes right of the output would sample outside the staged box
             float o4[4];
+            if (kShared) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float u, v, rw;
-                project_col(iv.hm, cp, yg + static_cast<float>(j), u, v, rw);
-                if (kShared) {
+                for (int p = 0; p < 2; ++p) {
+                    f2 u2, v2, r2;
+                    project_col2(iv.hm, cp, add2(dup2(yg), pk(2.0f * p, 2.0f * p + 1.0f)), u2, v2, r2);
                     // zero frame: clamp, then the unpredicated interior sequence (fmaxf / fminf also absorb NaN)
-                    u = fminf(fmaxf(u, -1.0f), Wsf);
-                    v = fminf(fmaxf(v, -1.0f), Hsf);
-                    Cell4 c = cell_at<true>(u, v, iv.wd);
-                    if (iv.wd.xpred) zero_x_taps(c, Ws);
-                    const float top = fmaf(c.fx, c.ne - c.nw, c.nw), bot = fmaf(c.fx, c.se - c.sw, c.sw);
-                    o4[j] = fmaf(c.fy, bot - top, top);
-                    if (kMask) msum = fmaf(cover1(u, Wsf), cover1(v, Hsf), msum);
-                } else {
-                    float nw, ne, sw, se;
+                    float u0, u1, v0, v1;
+                    upk(u2, u0, u1);
+                    upk(v2, v0, v1);
+                    u0 = fminf(fmaxf(u0, -1.0f), Wsf); u1 = fminf(fmaxf(u1, -1.0f), Wsf);
+                    v0 = fminf(fmaxf(v0, -1.0f), Hsf); v1 = fminf(fmaxf(v1, -1.0f), Hsf);
+                    upk(lerp2(cell_at2<kPitch>(pk(u0, u1), pk(v0, v1), iv.wd, iv.wd.xpred, Ws)), o4[2 * p], o4[2 * p + 1]);
+                    if (kMask) {
+                        msum = fmaf(cover1(u0, Wsf), cover1(v0, Hsf), msum);
+                        msum = fmaf(cover1(u1, Wsf), cover1(v1, Hsf), msum);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float u, v, rw, nw, ne, sw, se;
+                    project_col(iv.hm, cp, yg + static_cast<float>(j), u, v, rw);
                     const Taps t = make_taps_fast(u, v, Ws, Hs);
                     global_taps(t, iv.wd.taps, iv.wd.pitch, nw, ne, sw, se);
                     o4[j] = blend(t, nw, ne, sw, se);
@@ -530,7 +652,7 @@ __device__ __forceinline__ void fwd_group(const ItemView& iv, const ColProj& cp,
     }
 }
 
-template <bool kMask, bool kShared, int kWo>
+template <bool kMask, bool kShared, int kWo, int kPitch>
 __device__ __forceinline__ void fwd_item(const ItemView& iv, float* __restrict__ out, float* __restrict__ mask_pooled, int Hs, int Ws,
                                          int Ho, int Wo_rt) {
     const int Wo = kWo > 0 ? kWo : Wo_rt;
@@ -544,12 +666,14 @@ __device__ __forceinline__ void fwd_item(const ItemView& iv, float* __restrict__
 #pragma unroll 1
     for (int gq = 0; gq < 4; ++gq) {
         const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
-        fwd_group<kMask, kShared, kWo>(iv, cp, cls, y0f + static_cast<float>(4 * gq), og + gq * 4 * Wo,
-                                       mcell ? mcell + gq * (Wo >> 2) : nullptr, Hs, Ws, Wo_rt);
+        fwd_group<kMask, kShared, kWo, kPitch>(iv, cp, cls, y0f + static_cast<float>(4 * gq), og + gq * 4 * Wo,
+                                               mcell ? mcell + gq * (Wo >> 2) : nullptr, Hs, Ws, Wo_rt);
     }
 }
 
-// kMask: also emit the 4x4-pooled coverage mask (written by the items of channel 0)
+// kMask: also emit the 4x4-pooled coverage mask (written by the items of channel 0).
+// kWo = 128: the north-star shape, Wo == 128 and (whole-plane items) Ws == 128 as well -- output and window pitches are
+// immediates; kWo = 0: run-time sizes.
 template <int kBlk, bool kMask, int kWo>
 __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasPerSm)
     warp_fwd_ring_kernel(const float* __restrict__ src, const float* __restrict__ H, float* __restrict__ out,
@@ -586,8 +710,9 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
 #pragma unroll 1
             for (int q = 0; q < Cfg::kStripsPerWarp; ++q) {
                 ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
-                if (iv.wd.shared) fwd_item<kMask, true, kWo>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
-                else fwd_item<kMask, false, kWo>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
+                constexpr int kPitch = (kBlk == 128 && kWo == 128) ? 128 : 0;
+                if (iv.wd.shared) fwd_item<kMask, true, kWo, kPitch>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
+                else fwd_item<kMask, false, kWo, 0>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
             }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
@@ -597,74 +722,103 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
 
 // ---- backward ------------------------------------------------------------------------------------------------
 // dH sums of one strip.  A lane keeps its column fixed, so the x factor of the nine sums is applied once at the end:
-// per pixel only  sum a, sum a*y, sum b, sum b*y, sum c, sum c*y  are advanced.
-struct StripSums {
-    float sa, say, sb, sby, sc, scy;
+// per pixel only  sum a, sum a*y, sum b, sum b*y, sum c, sum c*y  are advanced -- packed, rows (j, j + 1) in the two
+// halves of a register pair (added at the end of the strip); c is accumulated with its sign flipped.
+struct StripSums2 {
+    f2 sa, say, sb, sby, sc, scy;
 };
-__device__ __forceinline__ void sums_add(StripSums& t, float gu, float gv, float u, float v, float rw, float y) {
-    const float a = gu * rw, b = gv * rw, c = -fmaf(gu, u, gv * v) * rw;
-    t.sa += a; t.say = fmaf(a, y, t.say);
-    t.sb += b; t.sby = fmaf(b, y, t.sby);
-    t.sc += c; t.scy = fmaf(c, y, t.scy);
+__device__ __forceinline__ void sums_add2(StripSums2& t, f2 gu, f2 gv, f2 u, f2 v, f2 rw, f2 y) {
+    const f2 a = mul2(gu, rw), b = mul2(gv, rw), c = mul2(fma2(gu, u, mul2(gv, v)), rw);
+    t.sa = add2(t.sa, a); t.say = fma2(a, y, t.say);
+    t.sb = add2(t.sb, b); t.sby = fma2(b, y, t.sby);
+    t.sc = add2(t.sc, c); t.scy = fma2(c, y, t.scy);
+}
+// d out / du, d out / dv of two cells for unit upstream
+__device__ __forceinline__ void cell_grad2(const Cell8& c, f2& du, f2& dv) {
+    const f2 dt = sub2(c.ne, c.nw), db = sub2(c.se, c.sw), dl = sub2(c.sw, c.nw), dr = sub2(c.se, c.ne);
+    du = fma2(c.fy, sub2(db, dt), dt);
+    dv = fma2(c.fx, sub2(dr, dl), dl);
 }
 
-template <bool kImage, bool kMask, bool kShared>
+template <bool kImage, bool kMask, bool kShared, int kPitch>
 __device__ __forceinline__ void bwd_group(const ItemView& iv, const ColProj& cp, int cls, float yg, const float (&g4)[4], float gm,
-                                          StripSums& t, int Hs, int Ws) {
+                                          StripSums2& t, int Hs, int Ws) {
     const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
     if (!iv.xin) return;
     if (cls == kInside) {
         if (kImage) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float y = yg + static_cast<float>(j);
-                float u, v, rw;
-                project_col(iv.hm, cp, y, u, v, rw);
-                const Cell4 c = cell_at<kShared>(u, v, iv.wd);
-                const float dt = c.ne - c.nw, db = c.se - c.sw, dl = c.sw - c.nw, dr = c.se - c.ne;
-                const float du = fmaf(c.fy, db - dt, dt), dv = fmaf(c.fx, dr - dl, dl);
-                sums_add(t, g4[j] * du, g4[j] * dv, u, v, rw, y);
+            for (int p = 0; p < 2; ++p) {
+                const f2 y2 = add2(dup2(yg), pk(2.0f * p, 2.0f * p + 1.0f)), g2 = pk(g4[2 * p], g4[2 * p + 1]);
+                f2 u2, v2, r2, du, dv;
+                project_col2(iv.hm, cp, y2, u2, v2, r2);
+                if (kShared) {
+                    cell_grad2(cell_at2<kPitch>(u2, v2, iv.wd, false, Ws), du, dv);
+                } else {
+                    float u0, u1, v0, v1;
+                    upk(u2, u0, u1);
+                    upk(v2, v0, v1);
+                    const Cell4 c0 = cell_at<false>(u0, v0, iv.wd), c1 = cell_at<false>(u1, v1, iv.wd);
+                    Cell8 c;
+                    c.fx = pk(c0.fx, c1.fx); c.fy = pk(c0.fy, c1.fy);
+                    c.nw = pk(c0.nw, c1.nw); c.ne = pk(c0.ne, c1.ne); c.sw = pk(c0.sw, c1.sw); c.se = pk(c0.se, c1.se);
+                    cell_grad2(c, du, dv);
+                }
+                sums_add2(t, mul2(g2, du), mul2(g2, dv), u2, v2, r2, y2);
             }
         }
     } else if (cls == kBorder) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float y = yg + static_cast<float>(j);
-            float u, v, rw;
-            project_col(iv.hm, cp, y, u, v, rw);
-            float gu = 0.0f, gv = 0.0f;
+        for (int p = 0; p < 2; ++p) {
+            const f2 y2 = add2(dup2(yg), pk(2.0f * p, 2.0f * p + 1.0f)), g2 = pk(g4[2 * p], g4[2 * p + 1]);
+            f2 u2, v2, r2;
+            project_col2(iv.hm, cp, y2, u2, v2, r2);
+            float u0, u1, v0, v1, r0, r1;
+            upk(u2, u0, u1);
+            upk(v2, v0, v1);
+            upk(r2, r0, r1);
+            f2 gu = dup2(0.0f), gv = dup2(0.0f);
             if (kShared) {
-                const float uc = fminf(fmaxf(u, -1.0f), Wsf), vc = fminf(fmaxf(v, -1.0f), Hsf);
+                // zero frame: clamp (fmaxf / fminf also absorb NaN), sample like an interior pixel
+                const float uc0 = fminf(fmaxf(u0, -1.0f), Wsf), uc1 = fminf(fmaxf(u1, -1.0f), Wsf);
+                const float vc0 = fminf(fmaxf(v0, -1.0f), Hsf), vc1 = fminf(fmaxf(v1, -1.0f), Hsf);
+                const f2 uc = pk(uc0, uc1), vc = pk(vc0, vc1);
                 if (kImage) {
-                    Cell4 c = cell_at<true>(uc, vc, iv.wd);
-                    if (iv.wd.xpred) zero_x_taps(c, Ws);
-                    const float dt = c.ne - c.nw, db = c.se - c.sw, dl = c.sw - c.nw, dr = c.se - c.ne;
-                    gu = g4[j] * fmaf(c.fy, db - dt, dt);
-                    gv = g4[j] * fmaf(c.fx, dr - dl, dl);
+                    f2 du, dv;
+                    cell_grad2(cell_at2<kPitch>(uc, vc, iv.wd, iv.wd.xpred, Ws), du, dv);
+                    gu = mul2(g2, du);
+                    gv = mul2(g2, dv);
                 }
                 if (kMask) {
-                    gu = fmaf(gm, cover1(vc, Hsf) * cover1_grad(uc, Wsf), gu);
-                    gv = fmaf(gm, cover1(uc, Wsf) * cover1_grad(vc, Hsf), gv);
+                    gu = fma2(dup2(gm), pk(cover1(vc0, Hsf) * cover1_grad(uc0, Wsf), cover1(vc1, Hsf) * cover1_grad(uc1, Wsf)), gu);
+                    gv = fma2(dup2(gm), pk(cover1(uc0, Wsf) * cover1_grad(vc0, Hsf), cover1(uc1, Wsf) * cover1_grad(vc1, Hsf)), gv);
                 }
-                // a clamped coordinate does not move with H (also true for NaN: the comparison fails)
-                if (!(uc == u && vc == v)) { gu = 0.0f; gv = 0.0f; u = 0.0f; v = 0.0f; rw = 0.0f; }
+                // a clamped coordinate does not move with H (also true for NaN: the comparison fails): no contribution
+                const bool k0 = (uc0 == u0) && (vc0 == v0), k1 = (uc1 == u1) && (vc1 == v1);
+                const f2 keep = pk(k0 ? 1.0f : 0.0f, k1 ? 1.0f : 0.0f);
+                sums_add2(t, mul2(gu, keep), mul2(gv, keep), uc, vc, pk(k0 ? r0 : 0.0f, k1 ? r1 : 0.0f), y2);
             } else {
-                const Taps tp = make_taps_fast(u, v, Ws, Hs);
-                if (kImage) {
-                    float nw, ne, sw, se, du, dv;
-                    global_taps(tp, iv.wd.taps, iv.wd.pitch, nw, ne, sw, se);
-                    blend_grad(tp, nw, ne, sw, se, du, dv);
-                    gu = g4[j] * du;
-                    gv = g4[j] * dv;
+                float gus[2] = {0.0f, 0.0f}, gvs[2] = {0.0f, 0.0f};
+                const float us[2] = {u0, u1}, vs[2] = {v0, v1};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const Taps tp = make_taps_fast(us[e], vs[e], Ws, Hs);
+                    if (kImage) {
+                        float nw, ne, sw, se, du, dv;
+                        global_taps(tp, iv.wd.taps, iv.wd.pitch, nw, ne, sw, se);
+                        blend_grad(tp, nw, ne, sw, se, du, dv);
+                        gus[e] = g4[2 * p + e] * du;
+                        gvs[e] = g4[2 * p + e] * dv;
+                    }
+                    if (kMask) {
+                        float du, dv;
+                        cover_grad(tp, du, dv);
+                        gus[e] = fmaf(gm, du, gus[e]);
+                        gvs[e] = fmaf(gm, dv, gvs[e]);
+                    }
                 }
-                if (kMask) {
-                    float du, dv;
-                    cover_grad(tp, du, dv);
-                    gu = fmaf(gm, du, gu);
-                    gv = fmaf(gm, dv, gv);
-                }
+                sums_add2(t, pk(gus[0], gus[1]), pk(gvs[0], gvs[1]), u2, v2, r2, y2);
             }
-            sums_add(t, gu, gv, u, v, rw, y);
         }
     }
 }
@@ -694,51 +848,60 @@ __device__ __forceinline__ void warp_reduce9(const float (&v)[9], float& r, floa
     r8 = warp_sum(v[8]);
 }
 
-template <bool kImage, bool kMask, bool kShared>
+template <bool kImage, bool kMask, bool kShared, int kWo, int kPitch>
 __device__ __forceinline__ void bwd_item(const ItemView& iv, const float* __restrict__ gOut, const float* __restrict__ gMaskPooled,
-                                         float (&acc)[9], int Hs, int Ws, int Ho, int Wo) {
+                                         float (&acc)[9], int Hs, int Ws, int Ho, int Wo_rt) {
+    const int Wo = kWo > 0 ? kWo : Wo_rt;
     const float xf = static_cast<float>(iv.x);
     const ColProj cp = col_proj(iv.hm, xf);
-    const float* gcol = nullptr;
-    if (kImage) gcol = gOut + static_cast<size_t>(iv.plane) * Ho * Wo + iv.y0 * Wo + iv.x;
+    const float* gp = nullptr;   // upstream gradient of this lane's column, first row of the group being fetched
+    if (kImage) gp = gOut + static_cast<size_t>(iv.plane) * Ho * Wo + iv.y0 * Wo + iv.x;
     const float* mcell = nullptr;
     if (kMask && iv.c == 0) mcell = gMaskPooled + static_cast<size_t>(iv.b) * (Ho >> 2) * (Wo >> 2) + (iv.y0 >> 2) * (Wo >> 2) + (iv.x >> 2);
     const float y0f = static_cast<float>(iv.y0);
-    StripSums t = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    StripSums2 t;
+    t.sa = t.say = t.sb = t.sby = t.sc = t.scy = dup2(0.0f);
     // the upstream gradients of group gq + 1 are requested before group gq is sampled: their latency hides behind it.
     // (loops deliberately not unrolled: the body is large and the instruction cache is the scarcer resource)
     float gcur[4], gnext[4];
     {
-        const int cls = iv.cls4 & 0xf;
-        const bool need = kImage && iv.xin && (cls == kInside || cls == kBorder);
+        const bool need = kImage && iv.xin && (iv.cls4 & 0xf) <= kBorder;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gcur[j] = need ? ld_stream1(gcol + j * Wo) : 0.0f;
+        for (int j = 0; j < 4; ++j) gcur[j] = need ? ld_stream1(gp + j * Wo) : 0.0f;
     }
 #pragma unroll 1
     for (int gq = 0; gq < 4; ++gq) {
         const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
         {
-            const int cn = (iv.cls4 >> (4 * (gq + 1))) & 0xf;   // gq == 3: bits 16.. are zero or the next strip's class; unused
-            const bool need = kImage && iv.xin && gq < 3 && (cn == kInside || cn == kBorder);
+            const int cn = (iv.cls4 >> (4 * (gq + 1))) & 0xf;   // gq == 3: no next group in this strip
+            const bool need = kImage && iv.xin && gq < 3 && cn <= kBorder;
+            if (kImage) gp += 4 * Wo;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gnext[j] = need ? ld_stream1(gcol + ((gq + 1) * 4 + j) * Wo) : 0.0f;
+            for (int j = 0; j < 4; ++j) gnext[j] = need ? ld_stream1(gp + j * Wo) : 0.0f;
         }
         float gm = 0.0f;
         if (kMask && mcell != nullptr && cls == kBorder && iv.xin) gm = __ldg(mcell + gq * (Wo >> 2)) * 0.0625f;
-        bwd_group<kImage, kMask, kShared>(iv, cp, cls, y0f + static_cast<float>(4 * gq), gcur, gm, t, Hs, Ws);
+        bwd_group<kImage, kMask, kShared, kPitch>(iv, cp, cls, y0f + static_cast<float>(4 * gq), gcur, gm, t, Hs, Ws);
 #pragma unroll
         for (int j = 0; j < 4; ++j) gcur[j] = gnext[j];
     }
-    acc[0] = t.sa * xf; acc[1] = t.say; acc[2] = t.sa;
-    acc[3] = t.sb * xf; acc[4] = t.sby; acc[5] = t.sb;
-    acc[6] = t.sc * xf; acc[7] = t.scy; acc[8] = t.sc;
+    float sa, say, sb, sby, sc, scy, hi;
+    upk(t.sa, sa, hi); sa += hi;
+    upk(t.say, say, hi); say += hi;
+    upk(t.sb, sb, hi); sb += hi;
+    upk(t.sby, sby, hi); sby += hi;
+    upk(t.sc, sc, hi); sc += hi;
+    upk(t.scy, scy, hi); scy += hi;
+    acc[0] = sa * xf; acc[1] = say; acc[2] = sa;
+    acc[3] = sb * xf; acc[4] = sby; acc[5] = sb;
+    acc[6] = -(sc * xf); acc[7] = -scy; acc[8] = -sc;
 }
 
 // Every consumer warp writes the nine sums of each of its strips to partials[plane][block][strip][9] (no CTA-wide
 // barrier), warp_bwd_finish_kernel adds them in a fixed order (bit reproducible, no atomics).
 // kImage: gOut given (source staged); false = mask gradient only.  kMask: the pooled-mask upstream (pool == 4) is folded
 // into the same pass (channel 0).
-template <int kBlk, bool kImage, bool kMask>
+template <int kBlk, bool kImage, bool kMask, int kWo>
 __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasPerSm)
     warp_bwd_ring_kernel(const float* __restrict__ src, const float* __restrict__ H, const float* __restrict__ gOut,
                          const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C, int Hs, int Ws, int Ho,
@@ -776,8 +939,9 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
             for (int q = 0; q < Cfg::kStripsPerWarp; ++q) {
                 ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
                 float acc[9];
-                if (iv.wd.shared) bwd_item<kImage, kMask, true>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
-                else bwd_item<kImage, kMask, false>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
+                constexpr int kPitch = (kBlk == 128 && kWo == 128) ? 128 : 0;
+                if (iv.wd.shared) bwd_item<kImage, kMask, true, kWo, kPitch>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
+                else bwd_item<kImage, kMask, false, kWo, 0>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
                 if (q == Cfg::kStripsPerWarp - 1) {
                     __syncwarp();
                     if (lane == 0u) mbar_arrive(&empty[s]);   // the window is free while the last sums are reduced
@@ -1018,7 +1182,7 @@ inline int launch_fwd_ring(const float* src, const float* H, float* out, float* 
     const int blocks_x = blocks_of(Wo, kBlk), n_blocks = blocks_x * blocks_of(Ho, kBlk);
     const long long n_items = static_cast<long long>(B) * C * n_blocks;
     void (*kern)(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int);
-    if (Wo == 128) kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 128> : warp_fwd_ring_kernel<kBlk, false, 128>;
+    if (Wo == 128 && (kBlk != 128 || Ws == 128)) kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 128> : warp_fwd_ring_kernel<kBlk, false, 128>;
     else kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 0> : warp_fwd_ring_kernel<kBlk, false, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -1039,9 +1203,10 @@ inline int launch_bwd_ring(const float* src, const float* H, const float* gOut, 
     const int blocks_x = blocks_of(Wo, kBlk), n_blocks = blocks_x * blocks_of(Ho, kBlk);
     const long long n_items = static_cast<long long>(B) * Cw * n_blocks;
     void (*kern)(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int);
-    if (gOut && gMaskPooled) kern = warp_bwd_ring_kernel<kBlk, true, true>;
-    else if (gOut) kern = warp_bwd_ring_kernel<kBlk, true, false>;
-    else kern = warp_bwd_ring_kernel<kBlk, false, true>;
+    const bool fixed = Wo == 128 && (kBlk != 128 || Ws == 128);   // immediate pitches, see warp_fwd_ring_kernel
+    if (gOut && gMaskPooled) kern = fixed ? warp_bwd_ring_kernel<kBlk, true, true, 128> : warp_bwd_ring_kernel<kBlk, true, true, 0>;
+    else if (gOut) kern = fixed ? warp_bwd_ring_kernel<kBlk, true, false, 128> : warp_bwd_ring_kernel<kBlk, true, false, 0>;
+    else kern = fixed ? warp_bwd_ring_kernel<kBlk, false, true, 128> : warp_bwd_ring_kernel<kBlk, false, true, 0>;
     const int smem = gOut ? Cfg::kSmem : 0;
     if (smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
