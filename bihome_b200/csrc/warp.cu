@@ -88,11 +88,14 @@ __device__ __forceinline__ void store9(const float (&acc)[9], float* dst) {
 constexpr int kStripRows = 16;    // rows walked by one consumer warp per strip (32 columns x 16 rows)
 constexpr int kPadL = 4, kPadT = 1, kPadB = 2;   // the 4 floats in front of a window row are also the right pad of the row above
 // Two item sizes.  kBlk = 128: the source plane (<= 128x128) always fits one stage, so a whole plane is staged once and
-// its 32 strips are sampled by 16 consumer warps, 1 CTA per SM; the copies of the next plane have a full plane-time to
-// land.  kBlk = 64: larger sources, 8 consumer warps, 3 stages, 2 CTAs per SM.
+// its 32 strips are sampled by 16 consumer warps, 1 CTA per SM, 3 stages (216 KB): the copies run two planes ahead.
+// kBlk = 64: larger sources, 8 consumer warps, 3 stages, 2 CTAs per SM.
+// (Measured dead ends, kept out of the code: folding the producer into the last consumer warp to finish -- 16 warps, 128
+// registers -- is 7 % slower; fetching a whole strip of upstream gradients one strip ahead spills at the 96 registers a
+// 17-warp CTA leaves per thread and is 40 % slower.)
 template <int kBlk>
 struct RingCfg {
-    static constexpr int kStages = kBlk == 128 ? 2 : 3;
+    static constexpr int kStages = 3;
     static constexpr int kStageBytes = kBlk == 128 ? 72 * 1024 : 36 * 1024;
     static constexpr int kConsumers = kBlk == 128 ? 512 : 256;
     static constexpr int kThreads = kConsumers + 32;
@@ -652,6 +655,29 @@ __device__ __forceinline__ void fwd_group(const ItemView& iv, const ColProj& cp,
     }
 }
 
+// two vertically adjacent interior groups of a shared window at once (32 x 8 pixels): four independent row pairs in
+// flight per lane -- the consumer warps are few (the staging windows take the shared memory), so the latency of the
+// reciprocal -> floor -> LDS -> blend chain has to be covered by instruction-level parallelism
+template <int kWo, int kPitch>
+__device__ __forceinline__ void fwd_inside8(const ItemView& iv, const ColProj& cp, float yg, float* __restrict__ og, int Ws, int Wo_rt) {
+    const int Wo = kWo > 0 ? kWo : Wo_rt;
+    f2 u2[4], v2[4], o2[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        f2 r2;
+        project_col2(iv.hm, cp, add2(dup2(yg), pk(2.0f * p, 2.0f * p + 1.0f)), u2[p], v2[p], r2);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) o2[p] = lerp2(cell_at2<kPitch>(u2[p], v2[p], iv.wd, false, Ws));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float a, b;
+        upk(o2[p], a, b);
+        st_stream1(og + (2 * p) * Wo, a);
+        st_stream1(og + (2 * p + 1) * Wo, b);
+    }
+}
+
 template <bool kMask, bool kShared, int kWo, int kPitch>
 __device__ __forceinline__ void fwd_item(const ItemView& iv, float* __restrict__ out, float* __restrict__ mask_pooled, int Hs, int Ws,
                                          int Ho, int Wo_rt) {
@@ -664,10 +690,20 @@ __device__ __forceinline__ void fwd_item(const ItemView& iv, float* __restrict__
         mcell = mask_pooled + static_cast<size_t>(iv.b) * (Ho >> 2) * (Wo >> 2) + (iv.y0 >> 2) * (Wo >> 2) + (iv.x >> 2);
     const float y0f = static_cast<float>(iv.y0);
 #pragma unroll 1
-    for (int gq = 0; gq < 4; ++gq) {
-        const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
-        fwd_group<kMask, kShared, kWo, kPitch>(iv, cp, cls, y0f + static_cast<float>(4 * gq), og + gq * 4 * Wo,
-                                               mcell ? mcell + gq * (Wo >> 2) : nullptr, Hs, Ws, Wo_rt);
+    for (int gh = 0; gh < 2; ++gh) {
+        const int cls_a = (iv.cls4 >> (8 * gh)) & 0xf, cls_b = (iv.cls4 >> (8 * gh + 4)) & 0xf;
+        const float yg = y0f + static_cast<float>(8 * gh);
+        float* ogg = og + gh * 8 * Wo;
+        float* mc = mcell ? mcell + gh * 2 * (Wo >> 2) : nullptr;
+        if (kShared && cls_a == kInside && cls_b == kInside) {
+            if (iv.xin) {
+                fwd_inside8<kWo, kPitch>(iv, cp, yg, ogg, Ws, Wo_rt);
+                if (kMask && mc != nullptr) { mc[0] = 1.0f; mc[Wo >> 2] = 1.0f; }
+            }
+        } else {
+            fwd_group<kMask, kShared, kWo, kPitch>(iv, cp, cls_a, yg, ogg, mc, Hs, Ws, Wo_rt);
+            fwd_group<kMask, kShared, kWo, kPitch>(iv, cp, cls_b, yg + 4.0f, ogg + 4 * Wo, mc ? mc + (Wo >> 2) : nullptr, Hs, Ws, Wo_rt);
+        }
     }
 }
 
