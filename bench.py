@@ -226,7 +226,7 @@ def run_ours(args):
     loss_ms = kt.get('bh_bihome_fwd_bwd', [])
     avg = sum(loss_ms) / max(len(loss_ms), 1)
     achieved = LOSS_BYTES_PER_PAIR * B / (avg * 1e-3) / 1e9 if avg > 0 else None
-    roofline = {'bound': 'hbm', 'kernel': 'bihome_kernel<4,false> (bh_bihome_fwd_bwd)', 'achieved': achieved, 'peak': peak,
+    roofline = {'bound': 'hbm', 'kernel': 'bihome_nhwc_tma_kernel<false,1> (bh_bihome_fwd_bwd, channels-last C=64)', 'achieved': achieved, 'peak': peak,
                 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
                 'traffic': args.loss_traffic, 'launch_ms': avg,
                 'algorithmic_bytes_per_launch': LOSS_BYTES_PER_PAIR * B}
@@ -257,6 +257,10 @@ def run_ours(args):
 
 
 def main():
+    # ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr for the rest of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w', buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -14,6 +14,7 @@
 // through distributed shared memory.  Each feature element is read once and each gradient element written
 // once: 4*C*h*w*4 B in, 2*C*h*w*4 B out per sample -- the compulsory traffic.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "bh_common.cuh"
 
@@ -73,6 +74,35 @@ __device__ __forceinline__ void feat_elem(float p1w, float p2, float p2w, float 
         gc = -gb - s3;  // d/df1
         gd = -ga + s3;  // d/df2
     }
+}
+
+// loss, TensorBoard parts and the H12 / H21 gradients of one sample (one thread)
+__device__ __forceinline__ void sample_tail(const LossArgs& a, int b, float N1, float N2, float S1, float S2, float inv1, float inv2) {
+    float h1[9], h2[9], E[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { h1[i] = __ldg(a.H12 + b * 9 + i); h2[i] = __ldg(a.H21 + b * 9 + i); }
+    float ln3 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float e = h1[i * 3] * h2[j] + h1[i * 3 + 1] * h2[3 + j] + h1[i * 3 + 2] * h2[6 + j] - (i == j ? 1.0f : 0.0f);
+            E[i * 3 + j] = e;
+            ln3 = fmaf(e, e, ln3);
+        }
+    const float ln1 = N1 * inv1, ln2 = N2 * inv2;
+    a.loss[b] = ln1 + ln2 + a.mu * ln3;
+    a.parts[b * 5 + 0] = ln1; a.parts[b * 5 + 1] = ln2; a.parts[b * 5 + 2] = S1; a.parts[b * 5 + 3] = S2;
+    a.parts[b * 5 + 4] = ln3;
+    const float k = 2.0f * a.mu;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // (E H21^T)[i][j] = sum_k E[i][k] H21[j][k] ; (H12^T E)[i][j] = sum_k H12[k][i] E[k][j]
+            a.gH12[b * 9 + i * 3 + j] = k * (E[i * 3] * h2[j * 3] + E[i * 3 + 1] * h2[j * 3 + 1] + E[i * 3 + 2] * h2[j * 3 + 2]);
+            a.gH21[b * 9 + i * 3 + j] = k * (h1[i] * E[j] + h1[3 + i] * E[3 + j] + h1[6 + i] * E[6 + j]);
+        }
 }
 
 // V = pixels per thread-vector for the mask passes and the NCHW feature pass (4: hw % 4 == 0; 1: any strides).
@@ -250,33 +280,7 @@ __global__ void __launch_bounds__(kLossThreads) bihome_kernel(const LossArgs a) 
         N1 += remote[0];
         N2 += remote[1];
     }
-    if (rank == 0 && tid == 0) {
-        float h1[9], h2[9], E[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { h1[i] = __ldg(a.H12 + b * 9 + i); h2[i] = __ldg(a.H21 + b * 9 + i); }
-        float ln3 = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                float e = h1[i * 3] * h2[j] + h1[i * 3 + 1] * h2[3 + j] + h1[i * 3 + 2] * h2[6 + j] - (i == j ? 1.0f : 0.0f);
-                E[i * 3 + j] = e;
-                ln3 = fmaf(e, e, ln3);
-            }
-        const float ln1 = N1 * inv1, ln2 = N2 * inv2;
-        a.loss[b] = ln1 + ln2 + a.mu * ln3;
-        a.parts[b * 5 + 0] = ln1; a.parts[b * 5 + 1] = ln2; a.parts[b * 5 + 2] = S1; a.parts[b * 5 + 3] = S2;
-        a.parts[b * 5 + 4] = ln3;
-        const float k = 2.0f * a.mu;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                // (E H21^T)[i][j] = sum_k E[i][k] H21[j][k] ; (H12^T E)[i][j] = sum_k H12[k][i] E[k][j]
-                a.gH12[b * 9 + i * 3 + j] = k * (E[i * 3] * h2[j * 3] + E[i * 3 + 1] * h2[j * 3 + 1] + E[i * 3 + 2] * h2[j * 3 + 2]);
-                a.gH21[b * 9 + i * 3 + j] = k * (h1[i] * E[j] + h1[3 + i] * E[3 + j] + h1[6 + i] * E[6 + j]);
-            }
-    }
+    if (rank == 0 && tid == 0) sample_tail(a, b, N1, N2, S1, S2, inv1, inv2);
 
     // ---- phase 3: mask gradients, in place over the parked D ------------------------------------------
     const float c1 = (S1 > 1.0f) ? N1 * inv1 * inv1 : 0.0f, c2 = (S2 > 1.0f) ? N2 * inv2 * inv2 : 0.0f;
@@ -295,6 +299,353 @@ __global__ void __launch_bounds__(kLossThreads) bihome_kernel(const LossArgs a) 
         }
     }
     cluster.sync();  // keep this CTA's shared memory alive until every peer has read it
+}
+
+// ---- channels-last, TMA-staged variant ---------------------------------------------------------------------------
+// The register file caps what the kernel above can keep in flight (every outstanding float4 holds four registers of a
+// 63-register thread: ~64 KB per SM).  Here the four feature streams of a CTA's pixel range -- contiguous in NHWC -- are
+// pulled into a shared-memory ring by 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) issued by one thread, kLossStages
+// tiles ahead, starting BEFORE the mask sums of phase 0 so that the first tiles land while the denominators are being
+// exchanged.  A tile is one float4 per thread and tensor (kPerLane = 1) or two (kPerLane = 2, C = 256).
+constexpr int kLossStages = 4;
+template <bool kInputGrads, int kPerLane>
+__global__ void __launch_bounds__(kLossThreads) bihome_nhwc_tma_kernel(const LossArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = static_cast<int>(cluster.num_blocks());
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int b = blockIdx.x / CL;
+    const int tid = threadIdx.x;
+
+    extern __shared__ __align__(128) float tiles[];   // [stage][tensor: f1w, f2, f2w, f1][tile_floats]
+    __shared__ uint64_t full[kLossStages];
+    __shared__ float xchg_den[2];
+    __shared__ float xchg_num[2];
+    __shared__ float red[2 * (kLossThreads / 32)];
+
+    const int nvec = a.hw / 4;
+    const int v0 = static_cast<int>(static_cast<long long>(rank) * nvec / CL);
+    const int v1 = static_cast<int>(static_cast<long long>(rank + 1) * nvec / CL);
+    const long long mbase = static_cast<long long>(b) * a.hw;
+    const long long fbase = static_cast<long long>(b) * a.C * a.hw;
+
+    const int quads = a.C >> 2;
+    const int tpp = quads / kPerLane;                 // lanes per pixel (power of two, <= 32)
+    const int gl = tid & (tpp - 1), pg = tid / tpp, gpp = kLossThreads / tpp;   // pixels per tile
+    const int tile_floats = gpp * a.C;
+    const int p0 = v0 * 4, p1e = v1 * 4;
+    const int n_tiles = (p1e - p0 + gpp - 1) / gpp;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kLossStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int i) {   // one thread: tile i -> stage i % kLossStages
+        const int s = i % kLossStages;
+        const int px0 = p0 + i * gpp;
+        const int npx = min(gpp, p1e - px0);
+        const uint32_t bytes = static_cast<uint32_t>(npx) * a.C * 4u;
+        mbar_expect_tx(&full[s], 4u * bytes);
+        float* dst = tiles + static_cast<size_t>(s) * 4 * tile_floats;
+        const long long off = fbase + static_cast<long long>(px0) * a.C;
+        bulk_g2s(dst, a.f1w + off, bytes, &full[s]);
+        bulk_g2s(dst + tile_floats, a.f2 + off, bytes, &full[s]);
+        bulk_g2s(dst + 2 * tile_floats, a.f2w + off, bytes, &full[s]);
+        bulk_g2s(dst + 3 * tile_floats, a.f1 + off, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int i = 0; i < kLossStages && i < n_tiles; ++i) issue(i);
+
+    // ---- phase 0: mask sums of the whole sample (den1, den2) via DSMEM; the first tiles are already on their way ----
+    float s2[2] = {0.0f, 0.0f};
+    for (int pv = v0 + tid; pv < v1; pv += kLossThreads) {
+        float x1[4], x2[4], y1[4], y2[4];
+        ldv_cached<4>(a.m1w + mbase + pv * 4, x1);
+        ldv_cached<4>(a.m2w + mbase + pv * 4, x2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y1[i] = y2[i] = 1.0f;
+        if (a.m1) ldv_cached<4>(a.m1 + mbase + pv * 4, y1);
+        if (a.m2) ldv_cached<4>(a.m2 + mbase + pv * 4, y2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s2[0] = fmaf(x1[i], y2[i], s2[0]);
+            s2[1] = fmaf(x2[i], y1[i], s2[1]);
+        }
+    }
+    block_sum<2>(s2, red);
+    if (tid == 0) { xchg_den[0] = s2[0]; xchg_den[1] = s2[1]; }
+    cluster.sync();
+    float S1 = 0.0f, S2 = 0.0f;
+    for (int r = 0; r < CL; ++r) {
+        const float* remote = cluster.map_shared_rank(xchg_den, r);
+        S1 += remote[0];
+        S2 += remote[1];
+    }
+    const float inv1 = 1.0f / fmaxf(S1, 1.0f), inv2 = 1.0f / fmaxf(S2, 1.0f);
+
+    // ---- phase 1: the streaming pass over the ring -------------------------------------------------------------
+    float num[2] = {0.0f, 0.0f};
+    for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kLossStages;
+        const int p = p0 + i * gpp + pg;
+        const bool live = p < p1e;
+        float W1 = 0.0f, W2 = 0.0f;
+        if (live) {   // the pixel's mask weights: issued before the wait so that their latency overlaps it
+            const float x1 = __ldg(a.m1w + mbase + p), x2 = __ldg(a.m2w + mbase + p);
+            const float y1 = a.m1 ? __ldg(a.m1 + mbase + p) : 1.0f, y2 = a.m2 ? __ldg(a.m2 + mbase + p) : 1.0f;
+            W1 = x1 * y2;
+            W2 = x2 * y1;
+        }
+        mbar_wait(&full[s], static_cast<uint32_t>(i / kLossStages) & 1u);
+        const float* st = tiles + static_cast<size_t>(s) * 4 * tile_floats + pg * a.C + gl * 4;
+        float4 q1w[kPerLane], q2[kPerLane], q2w[kPerLane], q1[kPerLane];
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const float* e = st + k * tpp * 4;
+            q1w[k] = *reinterpret_cast<const float4*>(e);
+            q2[k] = *reinterpret_cast<const float4*>(e + tile_floats);
+            q2w[k] = *reinterpret_cast<const float4*>(e + 2 * tile_floats);
+            q1[k] = *reinterpret_cast<const float4*>(e + 3 * tile_floats);
+        }
+        __syncthreads();   // every thread holds its part of the tile in registers: the stage can be refilled
+        if (tid == 0 && i + kLossStages < n_tiles) {
+            fence_proxy_async();
+            issue(i + kLossStages);
+        }
+        float d1 = 0.0f, d2 = 0.0f;
+        if (live) {
+            const float k1 = W1 * inv1, k2 = W2 * inv2;
+            const long long poff = fbase + static_cast<long long>(p) * a.C;
+#pragma unroll
+            for (int k = 0; k < kPerLane; ++k) {
+                const long long o = poff + (gl + k * tpp) * 4;
+                const float p1w[4] = {q1w[k].x, q1w[k].y, q1w[k].z, q1w[k].w}, p2[4] = {q2[k].x, q2[k].y, q2[k].z, q2[k].w};
+                const float p2w[4] = {q2w[k].x, q2w[k].y, q2w[k].z, q2w[k].w}, p1[4] = {q1[k].x, q1[k].y, q1[k].z, q1[k].w};
+                float ga[4], gb[4], gc[4], gd[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    feat_elem<kInputGrads>(p1w[e], p2[e], p2w[e], p1[e], k1, k2, d1, d2, ga[e], gb[e], gc[e], gd[e]);
+                stv<4>(a.g_f1w + o, ga);
+                stv<4>(a.g_f2w + o, gb);
+                if (kInputGrads) {
+                    stv<4>(a.g_f1 + o, gc);
+                    stv<4>(a.g_f2 + o, gd);
+                }
+            }
+        }
+        for (int o = tpp >> 1; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        if (live && gl == 0) {
+            num[0] = fmaf(W1, d1, num[0]);
+            num[1] = fmaf(W2, d2, num[1]);
+            a.g_m1w[mbase + p] = d1;  // parked D, see phase 3
+            a.g_m2w[mbase + p] = d2;
+        }
+    }
+
+    // ---- phase 2: numerators of the whole sample via DSMEM, loss, dH ----------------------------------------------
+    block_sum<2>(num, red);
+    if (tid == 0) { xchg_num[0] = num[0]; xchg_num[1] = num[1]; }
+    cluster.sync();
+    float N1 = 0.0f, N2 = 0.0f;
+    for (int r = 0; r < CL; ++r) {
+        const float* remote = cluster.map_shared_rank(xchg_num, r);
+        N1 += remote[0];
+        N2 += remote[1];
+    }
+    if (rank == 0 && tid == 0) sample_tail(a, b, N1, N2, S1, S2, inv1, inv2);
+
+    // ---- phase 3: mask gradients, in place over the parked D --------------------------------------------------------
+    const float c1 = (S1 > 1.0f) ? N1 * inv1 * inv1 : 0.0f, c2 = (S2 > 1.0f) ? N2 * inv2 * inv2 : 0.0f;
+    for (int pv = v0 + tid; pv < v1; pv += kLossThreads) {
+        float y1[4], y2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y1[i] = y2[i] = 1.0f;
+        if (a.m1) ldv_cached<4>(a.m1 + mbase + pv * 4, y1);
+        if (a.m2) ldv_cached<4>(a.m2 + mbase + pv * 4, y2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* q1p = a.g_m1w + mbase + pv * 4 + i;
+            float* q2p = a.g_m2w + mbase + pv * 4 + i;
+            *q1p = y2[i] * (*q1p * inv1 - c1);
+            *q2p = y1[i] * (*q2p * inv2 - c2);
+        }
+    }
+    cluster.sync();  // keep this CTA's shared memory alive until every peer has read it
+}
+
+// ---- channels-last, persistent TMA-staged variant ("stream") ------------------------------------------------------
+// No clusters: 3 CTAs per SM walk a CONTIGUOUS range of (sample, pixel-tile) work items each (balanced to one tile, one
+// wave, no tail), the ring of bulk copies runs across tile and sample boundaries, and the only per-sample state a CTA
+// needs up front -- the two mask sums -- it computes itself when it enters a sample (8 KB of L2 hits).  The numerators,
+// the loss, dH and the mask gradients are left to bihome_finish_kernel (one CTA per sample, a fixed-order reduction over
+// the D values this kernel parks in the mask-gradient buffers): nothing crosses CTAs here.
+template <bool kInputGrads, int kPerLane>
+__global__ void __launch_bounds__(kLossThreads) bihome_stream_kernel(const LossArgs a, int tiles_per_sample, long long n_tiles_total) {
+    const int tid = threadIdx.x;
+    extern __shared__ __align__(128) float tiles[];   // [stage][tensor: f1w, f2, f2w, f1][tile_floats]
+    __shared__ uint64_t full[kLossStages];
+    __shared__ float red[2 * (kLossThreads / 32)];
+
+    const int quads = a.C >> 2;
+    const int tpp = quads / kPerLane;                 // lanes per pixel (power of two, <= 32)
+    const int gl = tid & (tpp - 1), pg = tid / tpp, gpp = kLossThreads / tpp;   // gpp = pixels per tile
+    const int tile_floats = gpp * a.C;
+    const long long t0 = n_tiles_total * blockIdx.x / gridDim.x, t1 = n_tiles_total * (blockIdx.x + 1) / gridDim.x;
+    const int n_tiles = static_cast<int>(t1 - t0);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kLossStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int i) {   // one thread: local tile i -> stage i % kLossStages
+        const int s = i % kLossStages;
+        const long long t = t0 + i;
+        const int b = static_cast<int>(t / tiles_per_sample);
+        const int px0 = static_cast<int>(t - static_cast<long long>(b) * tiles_per_sample) * gpp;
+        const int npx = min(gpp, a.hw - px0);
+        const uint32_t bytes = static_cast<uint32_t>(npx) * a.C * 4u;
+        mbar_expect_tx(&full[s], 4u * bytes);
+        float* dst = tiles + static_cast<size_t>(s) * 4 * tile_floats;
+        const long long off = (static_cast<long long>(b) * a.hw + px0) * a.C;
+        bulk_g2s(dst, a.f1w + off, bytes, &full[s]);
+        bulk_g2s(dst + tile_floats, a.f2 + off, bytes, &full[s]);
+        bulk_g2s(dst + 2 * tile_floats, a.f2w + off, bytes, &full[s]);
+        bulk_g2s(dst + 3 * tile_floats, a.f1 + off, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int i = 0; i < kLossStages && i < n_tiles; ++i) issue(i);
+
+    int cur_b = -1;
+    float inv1 = 0.0f, inv2 = 0.0f;
+    for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kLossStages;
+        const long long t = t0 + i;
+        const int b = static_cast<int>(t / tiles_per_sample);
+        const long long mbase = static_cast<long long>(b) * a.hw;
+        if (b != cur_b) {   // entering a sample (uniform across the CTA): its two mask sums
+            cur_b = b;
+            float s2[2] = {0.0f, 0.0f};
+            for (int pv = tid; pv < a.hw / 4; pv += kLossThreads) {
+                float x1[4], x2[4], y1[4], y2[4];
+                ldv_cached<4>(a.m1w + mbase + pv * 4, x1);
+                ldv_cached<4>(a.m2w + mbase + pv * 4, x2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y1[e] = y2[e] = 1.0f;
+                if (a.m1) ldv_cached<4>(a.m1 + mbase + pv * 4, y1);
+                if (a.m2) ldv_cached<4>(a.m2 + mbase + pv * 4, y2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    s2[0] = fmaf(x1[e], y2[e], s2[0]);
+                    s2[1] = fmaf(x2[e], y1[e], s2[1]);
+                }
+            }
+            block_sum<2>(s2, red);
+            inv1 = 1.0f / fmaxf(s2[0], 1.0f);
+            inv2 = 1.0f / fmaxf(s2[1], 1.0f);
+        }
+        const int p = static_cast<int>(t - static_cast<long long>(b) * tiles_per_sample) * gpp + pg;
+        const bool live = p < a.hw;
+        float W1 = 0.0f, W2 = 0.0f;
+        if (live) {   // the pixel's mask weights: requested before the wait so that their latency overlaps it
+            const float x1 = __ldg(a.m1w + mbase + p), x2 = __ldg(a.m2w + mbase + p);
+            const float y1 = a.m1 ? __ldg(a.m1 + mbase + p) : 1.0f, y2 = a.m2 ? __ldg(a.m2 + mbase + p) : 1.0f;
+            W1 = x1 * y2;
+            W2 = x2 * y1;
+        }
+        mbar_wait(&full[s], static_cast<uint32_t>(i / kLossStages) & 1u);
+        const float* st = tiles + static_cast<size_t>(s) * 4 * tile_floats + pg * a.C + gl * 4;
+        float4 q1w[kPerLane], q2[kPerLane], q2w[kPerLane], q1[kPerLane];
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const float* e = st + k * tpp * 4;
+            q1w[k] = *reinterpret_cast<const float4*>(e);
+            q2[k] = *reinterpret_cast<const float4*>(e + tile_floats);
+            q2w[k] = *reinterpret_cast<const float4*>(e + 2 * tile_floats);
+            q1[k] = *reinterpret_cast<const float4*>(e + 3 * tile_floats);
+        }
+        __syncthreads();   // every thread holds its part of the tile in registers: the stage can be refilled
+        if (tid == 0 && i + kLossStages < n_tiles) {
+            fence_proxy_async();
+            issue(i + kLossStages);
+        }
+        float d1 = 0.0f, d2 = 0.0f;
+        if (live) {
+            const float k1 = W1 * inv1, k2 = W2 * inv2;
+            const long long poff = (mbase + p) * a.C;
+#pragma unroll
+            for (int k = 0; k < kPerLane; ++k) {
+                const long long o = poff + (gl + k * tpp) * 4;
+                const float p1w[4] = {q1w[k].x, q1w[k].y, q1w[k].z, q1w[k].w}, p2[4] = {q2[k].x, q2[k].y, q2[k].z, q2[k].w};
+                const float p2w[4] = {q2w[k].x, q2w[k].y, q2w[k].z, q2w[k].w}, p1[4] = {q1[k].x, q1[k].y, q1[k].z, q1[k].w};
+                float ga[4], gb[4], gc[4], gd[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    feat_elem<kInputGrads>(p1w[e], p2[e], p2w[e], p1[e], k1, k2, d1, d2, ga[e], gb[e], gc[e], gd[e]);
+                stv<4>(a.g_f1w + o, ga);
+                stv<4>(a.g_f2w + o, gb);
+                if (kInputGrads) {
+                    stv<4>(a.g_f1 + o, gc);
+                    stv<4>(a.g_f2 + o, gd);
+                }
+            }
+        }
+        for (int o = tpp >> 1; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        if (live && gl == 0) {   // parked D: bihome_finish_kernel turns it into the mask gradient in place
+            a.g_m1w[mbase + p] = d1;
+            a.g_m2w[mbase + p] = d2;
+        }
+    }
+}
+
+// One CTA per sample, after bihome_stream_kernel: mask sums and numerators in a fixed order, loss / parts / dH, and the
+// mask gradients in place over the parked D.
+__global__ void __launch_bounds__(kLossThreads) bihome_finish_kernel(const LossArgs a) {
+    __shared__ float red[2 * (kLossThreads / 32)];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const long long mbase = static_cast<long long>(b) * a.hw;
+    // the mask sums exactly as bihome_stream_kernel forms them (same order): loss and gradients see the same denominators
+    float s2[2] = {0.0f, 0.0f};
+    for (int pv = tid; pv < a.hw / 4; pv += kLossThreads) {
+        float x1[4], x2[4], y1[4], y2[4];
+        ldv_cached<4>(a.m1w + mbase + pv * 4, x1);
+        ldv_cached<4>(a.m2w + mbase + pv * 4, x2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y1[e] = y2[e] = 1.0f;
+        if (a.m1) ldv_cached<4>(a.m1 + mbase + pv * 4, y1);
+        if (a.m2) ldv_cached<4>(a.m2 + mbase + pv * 4, y2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            s2[0] = fmaf(x1[e], y2[e], s2[0]);
+            s2[1] = fmaf(x2[e], y1[e], s2[1]);
+        }
+    }
+    block_sum<2>(s2, red);
+    float n2[2] = {0.0f, 0.0f};
+    for (int p = tid; p < a.hw; p += kLossThreads) {
+        const float x1 = __ldg(a.m1w + mbase + p), x2 = __ldg(a.m2w + mbase + p);
+        const float y1 = a.m1 ? __ldg(a.m1 + mbase + p) : 1.0f, y2 = a.m2 ? __ldg(a.m2 + mbase + p) : 1.0f;
+        n2[0] = fmaf(x1 * y2, a.g_m1w[mbase + p], n2[0]);
+        n2[1] = fmaf(x2 * y1, a.g_m2w[mbase + p], n2[1]);
+    }
+    block_sum<2>(n2, red);
+    const float S1 = s2[0], S2 = s2[1], N1 = n2[0], N2 = n2[1];
+    const float inv1 = 1.0f / fmaxf(S1, 1.0f), inv2 = 1.0f / fmaxf(S2, 1.0f);
+    if (tid == 0) sample_tail(a, b, N1, N2, S1, S2, inv1, inv2);
+    const float c1 = (S1 > 1.0f) ? N1 * inv1 * inv1 : 0.0f, c2 = (S2 > 1.0f) ? N2 * inv2 * inv2 : 0.0f;
+    for (int p = tid; p < a.hw; p += kLossThreads) {
+        const float y1 = a.m1 ? __ldg(a.m1 + mbase + p) : 1.0f, y2 = a.m2 ? __ldg(a.m2 + mbase + p) : 1.0f;
+        a.g_m1w[mbase + p] = y2 * (a.g_m1w[mbase + p] * inv1 - c1);
+        a.g_m2w[mbase + p] = y1 * (a.g_m2w[mbase + p] * inv2 - c2);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -336,6 +687,54 @@ int launch_bihome(const LossArgs& a, int CL, cudaStream_t stream) {
     return e == cudaSuccess ? BH_OK : static_cast<int>(e);
 }
 
+template <bool G, int kPerLane>
+int launch_bihome_tma(const LossArgs& a, int CL, size_t smem, cudaStream_t stream) {
+    cudaError_t e;
+    static size_t granted = 0;   // per instantiation; the attribute only ever grows (racing callers set the same value)
+    if (smem > granted) {
+        e = cudaFuncSetAttribute(bihome_nhwc_tma_kernel<G, kPerLane>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        granted = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.B) * CL);
+    cfg.blockDim = dim3(kLossThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, bihome_nhwc_tma_kernel<G, kPerLane>, a);
+    ++g_launch_count;
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? BH_OK : static_cast<int>(e);
+}
+
+template <bool G, int kPerLane>
+int launch_bihome_stream(const LossArgs& a, size_t smem, int gpp, cudaStream_t stream) {
+    cudaError_t e;
+    static size_t granted = 0;   // per instantiation; the attribute only ever grows (racing callers set the same value)
+    if (smem > granted) {
+        e = cudaFuncSetAttribute(bihome_stream_kernel<G, kPerLane>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        granted = smem;
+    }
+    const int tiles_per_sample = (a.hw + gpp - 1) / gpp;
+    const long long n_tiles = static_cast<long long>(a.B) * tiles_per_sample;
+    const long long resident = static_cast<long long>(kNumSMs) * (smem <= 72 * 1024 ? 3 : 1);
+    const unsigned grid = static_cast<unsigned>(n_tiles < resident ? n_tiles : resident);
+    bihome_stream_kernel<G, kPerLane><<<grid, kLossThreads, smem, stream>>>(a, tiles_per_sample, n_tiles);
+    int rc = launch_status();
+    if (rc != BH_OK) return rc;
+    bihome_finish_kernel<<<a.B, kLossThreads, 0, stream>>>(a);
+    return launch_status();
+}
+
 }  // namespace bh
 
 extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* f1w, const float* f2w, const float* m1,
@@ -363,10 +762,35 @@ extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* 
     const int nvec = vec ? a.hw / 4 : a.hw;
     int CL = (B >= 2 * kNumSMs) ? 2 : (B >= kNumSMs ? 4 : 8);
     while (CL > 1 && nvec / CL < kLanes) CL >>= 1;
+    if (const char* e = getenv("BH_LOSS_CL")) {   // tuning knob (tools/microbench.py --loss-cl): cluster size 1, 2, 4 or 8
+        const int f = atoi(e);
+        if (f == 1 || f == 2 || f == 4 || f == 8) CL = f;
+    }
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (channels_last) {
         const int quads = C / 4;
         const bool pow2 = (C % 4) == 0 && quads > 0 && (quads & (quads - 1)) == 0 && quads <= 256;
+        // Measured on B200 (tools/microbench.py --loss-cl, C = 64, h = w = 32): the persistent stream wins while the whole
+        // job is a few dozen tiles per CTA (B = 256: 84 % of the HBM peak against 72 % for the cluster kernels, which run
+        // 2.3 waves there); from B = 1024 on the clustered TMA kernel does (94 - 100 % against 86 - 90 %).
+        const char* force = getenv("BH_LOSS_VARIANT");   // tuning knob: "ldg", "cluster", "stream"
+        const bool want_stream = force ? force[0] == 's' : B < 512;
+        const bool want_tma = force ? force[0] != 'l' : true;
+        if (vec && pow2 && quads <= 64 && want_stream) {
+            // persistent TMA-staged stream + per-sample finish
+            const int per_lane = quads > 32 ? 2 : 1;
+            const int gpp = kLossThreads / (quads / per_lane);
+            const size_t smem = static_cast<size_t>(kLossStages) * 4 * gpp * C * sizeof(float);
+            if (per_lane == 1) return g_f1 ? launch_bihome_stream<true, 1>(a, smem, gpp, stream) : launch_bihome_stream<false, 1>(a, smem, gpp, stream);
+            return g_f1 ? launch_bihome_stream<true, 2>(a, smem, gpp, stream) : launch_bihome_stream<false, 2>(a, smem, gpp, stream);
+        }
+        if (vec && pow2 && quads <= 64 && want_tma) {
+            // TMA-staged ring: one float4 per thread and tensor per tile (two for C = 256)
+            const int per_lane = quads > 32 ? 2 : 1;
+            const size_t smem = static_cast<size_t>(kLossStages) * 4 * (kLossThreads / (quads / per_lane)) * C * sizeof(float);
+            if (per_lane == 1) return g_f1 ? launch_bihome_tma<true, 1>(a, CL, smem, stream) : launch_bihome_tma<false, 1>(a, CL, smem, stream);
+            return g_f1 ? launch_bihome_tma<true, 2>(a, CL, smem, stream) : launch_bihome_tma<false, 2>(a, CL, smem, stream);
+        }
         if (vec && pow2) return g_f1 ? launch_bihome<4, true, true>(a, CL, stream) : launch_bihome<4, false, true>(a, CL, stream);
         return g_f1 ? launch_bihome<1, true, false>(a, CL, stream) : launch_bihome<1, false, false>(a, CL, stream);
     }

@@ -4,7 +4,7 @@
     python tools/microbench.py --sweep         # the full sweep (shapes over ~60 GB footprint are skipped)
     python tools/microbench.py --once          # one launch of every kernel at B=256, P=128 (the command ncu profiles)
 
-Every timing: CUDA events on the launching stream, >= 3 warm-up launches, the L2 flushed (256 MB memset) before each
+Every timing: CUDA events on the launching stream, >= 3 warm-up launches, the L2 flushed (256 MB written, then 256 MB read) before each
 timed launch, mean of `--iters` launches.  Algorithmic bytes are those of SURVEY.md 8(d) / DESIGN.md section 4.
 """
 import argparse
@@ -37,9 +37,15 @@ except Exception:  # noqa: BLE001
 
 
 class Timer:
-    def __init__(self, iters, flush=True):
+    """L2 flush before every timed launch: a 256 MB buffer is WRITTEN (evicts everything the kernel under test could hit),
+    then a second 256 MB buffer is READ so that the L2 is left full of clean lines.  Without the read the kernel inherits
+    ~126 MB of dirty lines from the memset and pays their write-back (~20 us at HBM speed) inside its own timed region --
+    measured as a constant 18-30 us offset on every kernel of this file, whatever its size."""
+    def __init__(self, iters, flush=True, dirty=False):
         self.iters = iters
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda') if flush else None
+        self.clean = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device='cuda') if flush and not dirty else None
+        self.sink = None
 
     def __call__(self, fn, warm=3):
         for _ in range(warm):
@@ -48,6 +54,8 @@ class Timer:
         for _ in range(self.iters):
             if self.flush is not None:
                 self.flush.zero_()
+                if self.clean is not None:
+                    self.sink = self.clean.sum()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -142,6 +150,8 @@ def main():
     ap.add_argument('--once', action='store_true')
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--warp-only', action='store_true', help='time only the 1-channel image warp (forward + backward)')
+    ap.add_argument('--dirty', action='store_true', help='flush by memset only (leaves the L2 full of dirty lines: adds their write-back to every timing)')
+    ap.add_argument('--loss-cl', action='store_true', help='time the fused loss for every cluster size (BH_LOSS_CL knob)')
     a = ap.parse_args()
     torch.manual_seed(0)
     if a.once:
@@ -152,12 +162,27 @@ def main():
         bench_feature_warp(64, 128, 64, t)
         bench_small(256, 128, t)
         return
-    t = Timer(a.iters)
+    t = Timer(a.iters, dirty=a.dirty)
+    if a.loss_cl:
+        for cl in (1, 2, 4, 8):
+            os.environ['BH_LOSS_CL'] = str(cl)
+            print(json.dumps({'BH_LOSS_CL': cl}))
+            for B in (256, 1024):
+                bench_loss(B, 128, 64, t, True)
+                bench_loss(B, 128, 64, t, False)
+        os.environ.pop('BH_LOSS_CL')
+        for var in ('ldg', 'cluster', 'stream'):
+            os.environ['BH_LOSS_VARIANT'] = var
+            print(json.dumps({'BH_LOSS_VARIANT': var}))
+            for B in (256, 1024, 4096):
+                bench_loss(B, 128, 64, t, True)
+        os.environ.pop('BH_LOSS_VARIANT')
+        return
     if a.warp_only:
         for B, P in ((256, 128), (1024, 128), (4096, 128), (256, 256), (64, 512)):
             bench_image_warp(B, P, t)
         return
-    print(json.dumps({'peak_GBps_measured': PEAK, 'timing': 'cuda events, L2 flushed before every launch, mean of %d' % a.iters}))
+    print(json.dumps({'peak_GBps_measured': PEAK, 'timing': 'cuda events, L2 flushed (256 MB written, then 256 MB read: clean lines) before every launch, mean of %d' % a.iters}))
     shapes = [(256, 128, 64)]
     if a.sweep:
         shapes = [(B, P, C) for B in (64, 256, 1024, 4096) for P in (128, 256, 512) for C in (64, 128, 256)]
