@@ -226,7 +226,7 @@ def run_ours(args):
     loss_ms = kt.get('bh_bihome_fwd_bwd', [])
     avg = sum(loss_ms) / max(len(loss_ms), 1)
     achieved = LOSS_BYTES_PER_PAIR * B / (avg * 1e-3) / 1e9 if avg > 0 else None
-    roofline = {'bound': 'hbm', 'kernel': 'bihome_nhwc_tma_kernel<false,1> (bh_bihome_fwd_bwd, channels-last C=64)', 'achieved': achieved, 'peak': peak,
+    roofline = {'bound': 'hbm', 'kernel': 'bihome_stream_kernel<false,1> + bihome_finish_kernel (bh_bihome_fwd_bwd, channels-last C=64, B<512)', 'achieved': achieved, 'peak': peak,
                 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
                 'traffic': args.loss_traffic, 'launch_ms': avg,
                 'algorithmic_bytes_per_launch': LOSS_BYTES_PER_PAIR * B}

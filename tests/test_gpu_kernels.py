@@ -295,6 +295,37 @@ def test_bihome_loss_vs_oracle(F, B, C, h, w, nhwc, user_masks, in_grads):
         assert rel_l2(gi.cpu().numpy(), g64[i].numpy()) < TOL, 'gradient %d' % i
 
 
+@pytest.mark.parametrize('variant', ['ldg', 'cluster', 'stream'])
+@pytest.mark.parametrize('B,C,h,w,user_masks,in_grads', [
+    (5, 64, 32, 32, False, False),     # north-star shape: 16 lanes per pixel, 64 tiles per sample
+    (3, 256, 8, 8, False, True),       # two float4 per thread and tensor (128 KB ring), gradients w.r.t. f1/f2 too
+    (7, 16, 6, 6, True, False),        # 36 pixels per sample: one PARTIAL tile of 64 pixels, user masks
+    (9, 4, 20, 20, False, False),      # one lane per pixel, 400 pixels = 1 full + 1 partial tile of 256
+    (600, 8, 8, 8, False, False),      # more samples than resident CTAs (the batch size that selects 'cluster' by default)
+])
+def test_bihome_loss_channels_last_variants(F, monkeypatch, variant, B, C, h, w, user_masks, in_grads):
+    """the three channels-last kernels (cluster + LDG, cluster + TMA ring, persistent TMA stream + finish) against the
+    float64 oracle on the same inputs; BH_LOSS_VARIANT is the library's tuning knob (read at every call)"""
+    monkeypatch.setenv('BH_LOSS_VARIANT', variant)
+    test_bihome_loss_vs_oracle(F, B, C, h, w, True, user_masks, in_grads)
+
+
+def test_bihome_loss_variants_agree_on_gradients(F, monkeypatch):
+    """feature gradients are sign * W / den; the variants differ only in the order the mask sums are added (per-CTA
+    partial sums in the cluster kernels, one pass in the stream kernel): agreement to a few ulp"""
+    f, m1w, m2w, _, _, H12, H21 = _loss_inputs(6, 64, 32, 32, seed=11)
+    cl = lambda t: t.float().cuda().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for variant in ('ldg', 'cluster', 'stream'):
+        monkeypatch.setenv('BH_LOSS_VARIANT', variant)
+        a = [cl(f[2]).requires_grad_(True), cl(f[3]).requires_grad_(True)]
+        loss_b, _ = F.bihome_loss(cl(f[0]), cl(f[1]), a[0], a[1], m1w.float().cuda(), m2w.float().cuda(), H12.float().cuda(),
+                                  H21.float().cuda(), 0.01)
+        outs.append(torch.autograd.grad(loss_b.sum(), a))
+    for other in outs[1:]:
+        assert torch.allclose(outs[0][0], other[0], rtol=2e-6, atol=0) and torch.allclose(outs[0][1], other[1], rtol=2e-6, atol=0)
+
+
 def test_bihome_loss_upstream_scale(F):
     """backward with a non-unit upstream gradient goes through bh_bihome_rescale"""
     f, m1w, m2w, _, _, H12, H21 = _loss_inputs(3, 8, 8, 8, seed=1)
