@@ -897,29 +897,34 @@ __device__ __forceinline__ void bwd_item(const ItemView& iv, const float* __rest
     const float y0f = static_cast<float>(iv.y0);
     StripSums2 t;
     t.sa = t.say = t.sb = t.sby = t.sc = t.scy = dup2(0.0f);
-    // the upstream gradients of group gq + 1 are requested before group gq is sampled: their latency hides behind it.
+    // the upstream gradients of group gq + 2 are requested before group gq is sampled: an L2 hit takes about as long as
+    // one group does, so one group of look-ahead leaves part of it exposed.
     // (loops deliberately not unrolled: the body is large and the instruction cache is the scarcer resource)
-    float gcur[4], gnext[4];
+    float gcur[4], gn1[4], gn2[4];
     {
-        const bool need = kImage && iv.xin && (iv.cls4 & 0xf) <= kBorder;
+        const bool need0 = kImage && iv.xin && (iv.cls4 & 0xf) <= kBorder;
+        const bool need1 = kImage && iv.xin && ((iv.cls4 >> 4) & 0xf) <= kBorder;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gcur[j] = need ? ld_stream1(gp + j * Wo) : 0.0f;
+        for (int j = 0; j < 4; ++j) gcur[j] = need0 ? ld_stream1(gp + j * Wo) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gn1[j] = need1 ? ld_stream1(gp + (4 + j) * Wo) : 0.0f;
+        if (kImage) gp += 4 * Wo;
     }
 #pragma unroll 1
     for (int gq = 0; gq < 4; ++gq) {
         const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
         {
-            const int cn = (iv.cls4 >> (4 * (gq + 1))) & 0xf;   // gq == 3: no next group in this strip
-            const bool need = kImage && iv.xin && gq < 3 && cn <= kBorder;
+            const int cn = (iv.cls4 >> (4 * (gq + 2))) & 0xf;   // gq >= 2: no such group in this strip
+            const bool need = kImage && iv.xin && gq < 2 && cn <= kBorder;
             if (kImage) gp += 4 * Wo;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gnext[j] = need ? ld_stream1(gp + j * Wo) : 0.0f;
+            for (int j = 0; j < 4; ++j) gn2[j] = need ? ld_stream1(gp + j * Wo) : 0.0f;
         }
         float gm = 0.0f;
         if (kMask && mcell != nullptr && cls == kBorder && iv.xin) gm = __ldg(mcell + gq * (Wo >> 2)) * 0.0625f;
         bwd_group<kImage, kMask, kShared, kPitch>(iv, cp, cls, y0f + static_cast<float>(4 * gq), gcur, gm, t, Hs, Ws);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gcur[j] = gnext[j];
+        for (int j = 0; j < 4; ++j) { gcur[j] = gn1[j]; gn1[j] = gn2[j]; }
     }
     float sa, say, sb, sby, sc, scy, hi;
     upk(t.sa, sa, hi); sa += hi;
