@@ -714,7 +714,7 @@ template <int kBlk, bool kMask, int kWo>
 __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasPerSm)
     warp_fwd_ring_kernel(const float* __restrict__ src, const float* __restrict__ H, float* __restrict__ out,
                          float* __restrict__ mask_pooled, int C, int Hs, int Ws, int Ho, int Wo, int blocks_x, int n_blocks,
-                         int n_items) {
+                         int n_items, int n_full) {
     using Cfg = RingCfg<kBlk>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[Cfg::kStages], empty[Cfg::kStages];
@@ -735,16 +735,21 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
         const int s = k % Cfg::kStages;
         const uint32_t round = static_cast<uint32_t>(k / Cfg::kStages);
         float* stage = reinterpret_cast<float*>(smem_raw + s * Cfg::kStageBytes);
+        // launch items [0, n_full) are whole items; the rest are HALVES of the remaining items (see ring_split)
+        const bool half = it >= n_full;
+        const int item = half ? n_full + ((it - n_full) >> 1) : it;
+        const int q_lo = half ? ((it - n_full) & 1) * (Cfg::kStripsPerWarp / 2) : 0;
+        const int q_hi = half ? q_lo + Cfg::kStripsPerWarp / 2 : Cfg::kStripsPerWarp;
         if (producer) {
             if (k >= Cfg::kStages) mbar_wait_sleep(&empty[s], (round - 1u) & 1u);  // consumers released the stage
-            ring_produce<kBlk, true>(src, H, it, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
+            ring_produce<kBlk, true>(src, H, item, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
                                      nullptr);
         } else {
             mbar_wait_hint(&full[s], round & 1u);
             ItemView iv = ring_view(&header[s], src, stage, Hs, Ws);
             const unsigned classes = ring_classify<kBlk, false>(&header[s], iv.hm, warp, Hs, Ws);
 #pragma unroll 1
-            for (int q = 0; q < Cfg::kStripsPerWarp; ++q) {
+            for (int q = q_lo; q < q_hi; ++q) {
                 ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
                 constexpr int kPitch = (kBlk == 128 && kWo == 128) ? 128 : 0;
                 if (iv.wd.shared) fwd_item<kMask, true, kWo, kPitch>(iv, out, mask_pooled, Hs, Ws, Ho, Wo);
@@ -946,7 +951,7 @@ template <int kBlk, bool kImage, bool kMask, int kWo>
 __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasPerSm)
     warp_bwd_ring_kernel(const float* __restrict__ src, const float* __restrict__ H, const float* __restrict__ gOut,
                          const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C, int Hs, int Ws, int Ho,
-                         int Wo, int blocks_x, int n_blocks, int n_items) {
+                         int Wo, int blocks_x, int n_blocks, int n_items, int n_full) {
     using Cfg = RingCfg<kBlk>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[Cfg::kStages], empty[Cfg::kStages];
@@ -967,9 +972,13 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
         const int s = k % Cfg::kStages;
         const uint32_t round = static_cast<uint32_t>(k / Cfg::kStages);
         float* stage = reinterpret_cast<float*>(smem_raw + s * Cfg::kStageBytes);
+        const bool half = it >= n_full;
+        const int item = half ? n_full + ((it - n_full) >> 1) : it;
+        const int q_lo = half ? ((it - n_full) & 1) * (Cfg::kStripsPerWarp / 2) : 0;
+        const int q_hi = half ? q_lo + Cfg::kStripsPerWarp / 2 : Cfg::kStripsPerWarp;
         if (producer) {
             if (k >= Cfg::kStages) mbar_wait_sleep(&empty[s], (round - 1u) & 1u);
-            ring_produce<kBlk, kImage>(src, H, it, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
+            ring_produce<kBlk, kImage>(src, H, item, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
                                        kImage ? gOut : nullptr);
         } else {
             mbar_wait_hint(&full[s], round & 1u);
@@ -977,13 +986,13 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
             const unsigned classes = ring_classify<kBlk, !kImage>(&header[s], iv.hm, warp, Hs, Ws);
             const unsigned lane = threadIdx.x & 31u;
 #pragma unroll 1
-            for (int q = 0; q < Cfg::kStripsPerWarp; ++q) {
+            for (int q = q_lo; q < q_hi; ++q) {
                 ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
                 float acc[9];
                 constexpr int kPitch = (kBlk == 128 && kWo == 128) ? 128 : 0;
                 if (iv.wd.shared) bwd_item<kImage, kMask, true, kWo, kPitch>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
                 else bwd_item<kImage, kMask, false, kWo, 0>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
-                if (q == Cfg::kStripsPerWarp - 1) {
+                if (q == q_hi - 1) {
                     __syncwarp();
                     if (lane == 0u) mbar_arrive(&empty[s]);   // the window is free while the last sums are reduced
                 }
@@ -1210,6 +1219,19 @@ inline int ring_grid(long long n_items) {
     const long long cap = static_cast<long long>(kNumSMs) * RingCfg<kBlk>::kCtasPerSm;
     return static_cast<int>(n_items < cap ? n_items : cap);
 }
+// Tail balance.  Items are dealt round-robin to `cap` persistent CTAs, so n_items = r * cap + R costs r + 1 rounds.  When
+// R <= cap / 2 (B = 256 pairs: 512 planes on 148 SMs, R = 68) the last R items are launched as 2 R half-items -- the two
+// halves of an item stage the same window and take half of each warp's strips -- and the last round takes half the time.
+// Returns the number of launch items; n_full = how many of them are whole.
+template <int kBlk>
+inline long long ring_split(long long n_items, int& n_full) {
+    const long long cap = static_cast<long long>(kNumSMs) * RingCfg<kBlk>::kCtasPerSm;
+    const long long R = n_items % cap;
+    n_full = static_cast<int>(n_items);
+    if (RingCfg<kBlk>::kStripsPerWarp < 2 || R == 0 || 2 * R > cap) return n_items;
+    n_full = static_cast<int>(n_items - R);
+    return n_items + R;
+}
 inline int grid_for(long long n, int threads) {
     long long g = (n + threads - 1) / threads;
     const long long cap = static_cast<long long>(kNumSMs) * 16;
@@ -1222,13 +1244,15 @@ inline int launch_fwd_ring(const float* src, const float* H, float* out, float* 
     using Cfg = RingCfg<kBlk>;
     const int blocks_x = blocks_of(Wo, kBlk), n_blocks = blocks_x * blocks_of(Ho, kBlk);
     const long long n_items = static_cast<long long>(B) * C * n_blocks;
-    void (*kern)(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int);
+    void (*kern)(const float*, const float*, float*, float*, int, int, int, int, int, int, int, int, int);
     if (Wo == 128 && (kBlk != 128 || Ws == 128)) kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 128> : warp_fwd_ring_kernel<kBlk, false, 128>;
     else kern = fuse_mask ? warp_fwd_ring_kernel<kBlk, true, 0> : warp_fwd_ring_kernel<kBlk, false, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    kern<<<ring_grid<kBlk>(n_items), Cfg::kThreads, Cfg::kSmem, stream>>>(src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo, blocks_x, n_blocks,
-                                                                          static_cast<int>(n_items));
+    int n_full;
+    const long long n_launch = ring_split<kBlk>(n_items, n_full);
+    kern<<<ring_grid<kBlk>(n_launch), Cfg::kThreads, Cfg::kSmem, stream>>>(src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo, blocks_x, n_blocks,
+                                                                           static_cast<int>(n_launch), n_full);
     return launch_status();
 }
 
@@ -1243,7 +1267,7 @@ inline int launch_bwd_ring(const float* src, const float* H, const float* gOut, 
     using Cfg = RingCfg<kBlk>;
     const int blocks_x = blocks_of(Wo, kBlk), n_blocks = blocks_x * blocks_of(Ho, kBlk);
     const long long n_items = static_cast<long long>(B) * Cw * n_blocks;
-    void (*kern)(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int);
+    void (*kern)(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int);
     const bool fixed = Wo == 128 && (kBlk != 128 || Ws == 128);   // immediate pitches, see warp_fwd_ring_kernel
     if (gOut && gMaskPooled) kern = fixed ? warp_bwd_ring_kernel<kBlk, true, true, 128> : warp_bwd_ring_kernel<kBlk, true, true, 0>;
     else if (gOut) kern = fixed ? warp_bwd_ring_kernel<kBlk, true, false, 128> : warp_bwd_ring_kernel<kBlk, true, false, 0>;
@@ -1253,8 +1277,10 @@ inline int launch_bwd_ring(const float* src, const float* H, const float* gOut, 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
-    kern<<<ring_grid<kBlk>(n_items), Cfg::kThreads, smem, stream>>>(src, H, gOut, gMaskPooled, partials, Cw, Hs, Ws, Ho, Wo, blocks_x, n_blocks,
-                                                                    static_cast<int>(n_items));
+    int n_full;
+    const long long n_launch = ring_split<kBlk>(n_items, n_full);
+    kern<<<ring_grid<kBlk>(n_launch), Cfg::kThreads, smem, stream>>>(src, H, gOut, gMaskPooled, partials, Cw, Hs, Ws, Ho, Wo, blocks_x, n_blocks,
+                                                                     static_cast<int>(n_launch), n_full);
     return launch_status();
 }
 
@@ -1274,7 +1300,7 @@ extern "C" int bh_warp_fwd(const float* src, const float* H, float* out, float* 
     bool mask_done = (mask_pooled == nullptr);
     if (src) {
         const long long n_items64 = static_cast<long long>(B) * C * blocks_of(Wo, 64) * blocks_of(Ho, 64);
-        if (ring_ok(Hs, Ws, Ho, Wo, channels_last) && n_items64 < (1ll << 31)) {
+        if (ring_ok(Hs, Ws, Ho, Wo, channels_last) && n_items64 < (1ll << 31) - 1024) {
             const bool fuse_mask = mask_pooled && pool == 4;
             rc = ring_blk(Hs, Ws) == 128 ? launch_fwd_ring<128>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream)
                                          : launch_fwd_ring<64>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream);
@@ -1326,7 +1352,7 @@ extern "C" int bh_warp_bwd(const float* src, const float* H, const float* gOut, 
     const bool mask4 = gMaskPooled == nullptr || pool == 4;
     const int Cw = gOut ? C : 1;   // coverage-only work has one "plane" per sample
     const long long n_items64 = static_cast<long long>(B) * Cw * blocks_of(Wo, 64) * blocks_of(Ho, 64);
-    if (!gSrc && mask4 && ring_ok(Hs, Ws, Ho, Wo, gOut ? channels_last : 0) && n_items64 < (1ll << 31)) {
+    if (!gSrc && mask4 && ring_ok(Hs, Ws, Ho, Wo, gOut ? channels_last : 0) && n_items64 < (1ll << 31) - 1024) {
         const bool planes = ring_blk(Hs, Ws) == 128;
         const int chunks = planes ? ring_bwd_chunks<128>(Cw, Ho, Wo) : ring_bwd_chunks<64>(Cw, Ho, Wo);
         const size_t need = static_cast<size_t>(B) * chunks * 9 * sizeof(float);
