@@ -29,6 +29,16 @@ UNIT = 'image-pairs/s'
 LOSS_BYTES_PER_PAIR = (4 + 2) * 64 * 32 * 32 * 4 + 4 * 32 * 32 * 4
 
 
+def loss_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the loss launch(es) at B=256, from the committed ncu capture
+    (profiles/loss_traffic.json, written by tools/summarize_profiles.py); None when the capture is absent"""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'loss_traffic.json')) as f:
+            return float(json.load(f)['dram_bytes_per_launch'])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -228,7 +238,7 @@ def run_ours(args):
     achieved = LOSS_BYTES_PER_PAIR * B / (avg * 1e-3) / 1e9 if avg > 0 else None
     roofline = {'bound': 'hbm', 'kernel': 'bihome_stream_kernel<false,1> + bihome_finish_kernel (bh_bihome_fwd_bwd, channels-last C=64, B<512)', 'achieved': achieved, 'peak': peak,
                 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None,
-                'traffic': args.loss_traffic, 'launch_ms': avg,
+                'traffic': args.loss_traffic if args.loss_traffic is not None else loss_traffic(), 'launch_ms': avg,
                 'algorithmic_bytes_per_launch': LOSS_BYTES_PER_PAIR * B}
     kernels = {k: {'launches': len(v), 'avg_ms': sum(v) / len(v)} for k, v in sorted(kt.items())}
 

@@ -159,6 +159,7 @@ def main():
         bench_image_warp(256, 128, t)
         bench_loss(256, 128, 64, t, True)
         bench_loss(256, 128, 64, t, False)
+        bench_loss(1024, 128, 64, t, True)      # B >= 512: the clustered TMA-ring kernel
         bench_feature_warp(64, 128, 64, t)
         bench_small(256, 128, t)
         return

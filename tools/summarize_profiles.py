@@ -63,6 +63,20 @@ if os.path.isfile(rep):
         for r in rows[2:]:
             w.writerow([re.sub(r'\(.*', '', r[i]) if hdr[i] == 'Kernel Name' else r[i] for i in idx])
     print('wrote ncu kernel summary')
+    # dram traffic of the loss launch at B=256 (stream + finish kernels), for bench.py's roofline.traffic
+    ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    per = {}
+    for r in rows[2:]:
+        for key in ('bihome_stream_kernel', 'bihome_finish_kernel'):
+            if key in r[ik]:
+                per.setdefault(key, []).append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+    if 'bihome_stream_kernel' in per:
+        total = sum(sum(v) / len(v) for v in per.values())
+        with open(os.path.join(P, 'loss_traffic.json'), 'w') as f:
+            json.dump({'dram_bytes_per_launch': total, 'kernels': {k: sum(v) / len(v) for k, v in per.items()},
+                       'source': 'ncu --set full, %s, tools/microbench.py --once (B=256, C=64, h=w=32, channels-last)' % os.path.basename(rep)}, f, indent=1)
+        print('wrote loss_traffic.json', total)
 
 mb = os.path.join(G, 'microbench_%s.jsonl' % tag)
 if os.path.isfile(mb):
