@@ -86,6 +86,7 @@ __device__ __forceinline__ void store9(const float (&acc)[9], float* dst) {
 // cache with predicated taps inside the same kernel.
 // =================================================================================================
 constexpr int kStripRows = 16;    // rows walked by one consumer warp per strip (32 columns x 16 rows)
+constexpr int kGBufBytes = (kStripRows + 4) * 32 * 4;   // one strip of upstream gradients + its 4 pooled-mask cells, per lane
 constexpr int kPadL = 4, kPadT = 1, kPadB = 2;   // the 4 floats in front of a window row are also the right pad of the row above
 // Two item sizes.  kBlk = 128: the source plane (<= 128x128) always fits one stage, so a whole plane is staged once and
 // its 32 strips are sampled by 16 consumer warps, 1 CTA per SM, 3 stages (216 KB): the copies run two planes ahead.
@@ -103,6 +104,10 @@ struct RingCfg {
     static constexpr int kStripsX = kBlk / 32, kStripsY = kBlk / kStripRows, kStrips = kStripsX * kStripsY;
     static constexpr int kStripsPerWarp = kStrips / (kConsumers / 32);
     static constexpr int kSmem = kStages * kStageBytes;
+    // backward with an upstream image gradient: two window stages + a double-buffered per-warp landing zone for the
+    // gradient stream (see strip_prefetch)
+    static constexpr int kBwdStages = 2;
+    static constexpr int kBwdSmem = kBwdStages * kStageBytes + (kConsumers / 32) * 2 * kGBufBytes;
 };
 constexpr float kMagic = 12582912.0f;            // 1.5 * 2^23: ulp == 1, add.rm.f32 leaves floor(t) in the mantissa
 constexpr int kMagicBits = 0x4B400000;
@@ -889,47 +894,82 @@ __device__ __forceinline__ void warp_reduce9(const float (&v)[9], float& r, floa
     r8 = warp_sum(v[8]);
 }
 
+// The upstream-gradient stream of the backward pass.  Lane l of a warp needs, for its strip, the 16 values of its own
+// output column and (channel 0) the 4 pooled-mask gradients above it -- addresses that depend on the item index only, not
+// on the staged window or on H.  Every lane therefore copies ITS values for the NEXT strip (of this item, or the first
+// one of the next item) into a per-warp shared-memory buffer with 4-byte cp.async (LDGSTS: no registers held while in
+// flight, unlike a register prefetch, which at the 96 registers of this CTA shape either spills or is too shallow to
+// cover an L2 hit), double-buffered, and reads them back with LDS one strip later.  A lane only ever reads what it
+// wrote: cp.async.wait_group is all the synchronisation there is.
+__device__ __forceinline__ void cp_async4(uint32_t dst_s32, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_s32), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+template <int kBlk, bool kMask, int kWo>
+__device__ __forceinline__ void strip_prefetch(const float* __restrict__ gOut, const float* __restrict__ gMaskPooled, int item, int q, int warp,
+                                               int n_planes_items, int n_blocks, int blocks_x, int C, int Ho, int Wo_rt, uint32_t buf_s32) {
+    using Cfg = RingCfg<kBlk>;
+    const int Wo = kWo > 0 ? kWo : Wo_rt;
+    if (item < n_planes_items) {
+        const int plane = item / n_blocks, blk = item - plane * n_blocks;
+        const int by = blk / blocks_x, bxi = blk - by * blocks_x;
+        const int sidx = warp + q * (Cfg::kConsumers / 32);
+        const int x = bxi * kBlk + (sidx % Cfg::kStripsX) * 32 + static_cast<int>(threadIdx.x & 31u);
+        const int y0 = by * kBlk + (sidx / Cfg::kStripsX) * kStripRows;
+        if (x < Wo) {
+            const float* gp = gOut + static_cast<size_t>(plane) * Ho * Wo + static_cast<size_t>(y0) * Wo + x;
+#pragma unroll
+            for (int r = 0; r < kStripRows; ++r)
+                if (y0 + r < Ho) cp_async4(buf_s32 + r * 128, gp + r * Wo);
+            if (kMask) {
+                const int b = plane / C;
+                if (plane - b * C == 0) {
+                    const float* mp = gMaskPooled + static_cast<size_t>(b) * (Ho >> 2) * (Wo >> 2) + (y0 >> 2) * (Wo >> 2) + (x >> 2);
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq)
+                        if (y0 + 4 * gq < Ho) cp_async4(buf_s32 + (kStripRows + gq) * 128, mp + gq * (Wo >> 2));
+                }
+            }
+        }
+    }
+    cp_async_commit();   // always: the group count must advance uniformly
+}
+
+// gbuf_s32 (kImage): shared address of this lane's slot in the landing buffer of the current strip (row r at + r * 128 B,
+// pooled-mask cell of group gq at + (16 + gq) * 128 B); kImage = false: mask gradients come straight from global memory.
 template <bool kImage, bool kMask, bool kShared, int kWo, int kPitch>
-__device__ __forceinline__ void bwd_item(const ItemView& iv, const float* __restrict__ gOut, const float* __restrict__ gMaskPooled,
+__device__ __forceinline__ void bwd_item(const ItemView& iv, uint32_t gbuf_s32, const float* __restrict__ gMaskPooled,
                                          float (&acc)[9], int Hs, int Ws, int Ho, int Wo_rt) {
     const int Wo = kWo > 0 ? kWo : Wo_rt;
     const float xf = static_cast<float>(iv.x);
     const ColProj cp = col_proj(iv.hm, xf);
-    const float* gp = nullptr;   // upstream gradient of this lane's column, first row of the group being fetched
-    if (kImage) gp = gOut + static_cast<size_t>(iv.plane) * Ho * Wo + iv.y0 * Wo + iv.x;
     const float* mcell = nullptr;
-    if (kMask && iv.c == 0) mcell = gMaskPooled + static_cast<size_t>(iv.b) * (Ho >> 2) * (Wo >> 2) + (iv.y0 >> 2) * (Wo >> 2) + (iv.x >> 2);
+    if (!kImage && kMask && iv.c == 0)
+        mcell = gMaskPooled + static_cast<size_t>(iv.b) * (Ho >> 2) * (Wo >> 2) + (iv.y0 >> 2) * (Wo >> 2) + (iv.x >> 2);
     const float y0f = static_cast<float>(iv.y0);
     StripSums2 t;
     t.sa = t.say = t.sb = t.sby = t.sc = t.scy = dup2(0.0f);
-    // the upstream gradients of group gq + 2 are requested before group gq is sampled: an L2 hit takes about as long as
-    // one group does, so one group of look-ahead leaves part of it exposed.
-    // (loops deliberately not unrolled: the body is large and the instruction cache is the scarcer resource)
-    float gcur[4], gn1[4], gn2[4];
-    {
-        const bool need0 = kImage && iv.xin && (iv.cls4 & 0xf) <= kBorder;
-        const bool need1 = kImage && iv.xin && ((iv.cls4 >> 4) & 0xf) <= kBorder;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gcur[j] = need0 ? ld_stream1(gp + j * Wo) : 0.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gn1[j] = need1 ? ld_stream1(gp + (4 + j) * Wo) : 0.0f;
-        if (kImage) gp += 4 * Wo;
-    }
+    // (loop deliberately not unrolled: the body is large and the instruction cache is the scarcer resource)
 #pragma unroll 1
     for (int gq = 0; gq < 4; ++gq) {
         const int cls = (iv.cls4 >> (4 * gq)) & 0xf;
-        {
-            const int cn = (iv.cls4 >> (4 * (gq + 2))) & 0xf;   // gq >= 2: no such group in this strip
-            const bool need = kImage && iv.xin && gq < 2 && cn <= kBorder;
-            if (kImage) gp += 4 * Wo;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gn2[j] = need ? ld_stream1(gp + j * Wo) : 0.0f;
-        }
+        float g4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         float gm = 0.0f;
-        if (kMask && mcell != nullptr && cls == kBorder && iv.xin) gm = __ldg(mcell + gq * (Wo >> 2)) * 0.0625f;
-        bwd_group<kImage, kMask, kShared, kPitch>(iv, cp, cls, y0f + static_cast<float>(4 * gq), gcur, gm, t, Hs, Ws);
+        if (iv.xin && cls <= kBorder) {
+            if (kImage) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { gcur[j] = gn1[j]; gn1[j] = gn2[j]; }
+                for (int j = 0; j < 4; ++j) g4[j] = lds_f32(gbuf_s32 + (4 * gq + j) * 128);
+            }
+            if (kMask && cls == kBorder && iv.c == 0)
+                gm = (kImage ? lds_f32(gbuf_s32 + (kStripRows + gq) * 128) : __ldg(mcell + gq * (Wo >> 2))) * 0.0625f;
+        }
+        bwd_group<kImage, kMask, kShared, kPitch>(iv, cp, cls, y0f + static_cast<float>(4 * gq), g4, gm, t, Hs, Ws);
     }
     float sa, say, sb, sby, sc, scy, hi;
     upk(t.sa, sa, hi); sa += hi;
@@ -953,12 +993,13 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
                          const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C, int Hs, int Ws, int Ho,
                          int Wo, int blocks_x, int n_blocks, int n_items, int n_full) {
     using Cfg = RingCfg<kBlk>;
+    constexpr int kS = Cfg::kBwdStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full[Cfg::kStages], empty[Cfg::kStages];
-    __shared__ ItemHeader header[Cfg::kStages];
+    __shared__ uint64_t full[kS], empty[kS];
+    __shared__ ItemHeader header[kS];
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < Cfg::kStages; ++s) {
+        for (int s = 0; s < kS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], Cfg::kConsumers / 32);
         }
@@ -966,33 +1007,58 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31u;
     const bool producer = warp == Cfg::kConsumers / 32;
+    // launch items [0, n_full) are whole items; the rest are HALVES of the remaining items (see ring_split)
+    const int n_planes_items = n_full + ((n_items - n_full) >> 1);
+    auto decode = [&](int it, int& item, int& q_lo, int& q_hi) {
+        const bool half = it >= n_full;
+        item = half ? n_full + ((it - n_full) >> 1) : it;
+        q_lo = half ? ((it - n_full) & 1) * (Cfg::kStripsPerWarp / 2) : 0;
+        q_hi = half ? q_lo + Cfg::kStripsPerWarp / 2 : Cfg::kStripsPerWarp;
+    };
+    // this lane's slots in the two landing buffers of its warp
+    const uint32_t gbuf0 = smem_u32(smem_raw + kS * Cfg::kStageBytes) + static_cast<uint32_t>(producer ? 0 : warp) * 2u * kGBufBytes + lane * 4u;
+    uint32_t flip = 0u;
+    if (kImage && !producer) {   // the first strip of this CTA
+        int item, q_lo, q_hi;
+        decode(blockIdx.x, item, q_lo, q_hi);
+        strip_prefetch<kBlk, kMask, kWo>(gOut, gMaskPooled, blockIdx.x < n_items ? item : n_planes_items, q_lo, warp, n_planes_items, n_blocks,
+                                         blocks_x, C, Ho, Wo, gbuf0);
+    }
     int k = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k) {
-        const int s = k % Cfg::kStages;
-        const uint32_t round = static_cast<uint32_t>(k / Cfg::kStages);
+        const int s = k % kS;
+        const uint32_t round = static_cast<uint32_t>(k / kS);
         float* stage = reinterpret_cast<float*>(smem_raw + s * Cfg::kStageBytes);
-        const bool half = it >= n_full;
-        const int item = half ? n_full + ((it - n_full) >> 1) : it;
-        const int q_lo = half ? ((it - n_full) & 1) * (Cfg::kStripsPerWarp / 2) : 0;
-        const int q_hi = half ? q_lo + Cfg::kStripsPerWarp / 2 : Cfg::kStripsPerWarp;
+        int item, q_lo, q_hi;
+        decode(it, item, q_lo, q_hi);
         if (producer) {
-            if (k >= Cfg::kStages) mbar_wait_sleep(&empty[s], (round - 1u) & 1u);
-            ring_produce<kBlk, kImage>(src, H, item, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= Cfg::kStages,
+            if (k >= kS) mbar_wait_sleep(&empty[s], (round - 1u) & 1u);
+            ring_produce<kBlk, kImage>(src, H, item, n_blocks, blocks_x, C, &header[s], stage, &full[s], Hs, Ws, Ho, Wo, k >= kS,
                                        kImage ? gOut : nullptr);
         } else {
+            // the strip after the last one of this item: the first strip of this CTA's next launch item
+            int nitem = n_planes_items, nq_lo = 0, nq_hi = 0;
+            if (it + static_cast<int>(gridDim.x) < n_items) decode(it + static_cast<int>(gridDim.x), nitem, nq_lo, nq_hi);
             mbar_wait_hint(&full[s], round & 1u);
             ItemView iv = ring_view(&header[s], src, stage, Hs, Ws);
             const unsigned classes = ring_classify<kBlk, !kImage>(&header[s], iv.hm, warp, Hs, Ws);
-            const unsigned lane = threadIdx.x & 31u;
 #pragma unroll 1
             for (int q = q_lo; q < q_hi; ++q) {
+                const bool last = q == q_hi - 1;
+                if (kImage) {
+                    strip_prefetch<kBlk, kMask, kWo>(gOut, gMaskPooled, last ? nitem : item, last ? nq_lo : q + 1, warp, n_planes_items, n_blocks,
+                                                     blocks_x, C, Ho, Wo, gbuf0 + (flip ^ 1u) * kGBufBytes);
+                    cp_async_wait_1();   // everything but the group just committed has landed: this strip's values
+                }
                 ring_view_strip<kBlk>(iv, &header[s], warp, q, classes, Wo);
                 float acc[9];
                 constexpr int kPitch = (kBlk == 128 && kWo == 128) ? 128 : 0;
-                if (iv.wd.shared) bwd_item<kImage, kMask, true, kWo, kPitch>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
-                else bwd_item<kImage, kMask, false, kWo, 0>(iv, gOut, gMaskPooled, acc, Hs, Ws, Ho, Wo);
-                if (q == q_hi - 1) {
+                if (iv.wd.shared) bwd_item<kImage, kMask, true, kWo, kPitch>(iv, gbuf0 + flip * kGBufBytes, gMaskPooled, acc, Hs, Ws, Ho, Wo);
+                else bwd_item<kImage, kMask, false, kWo, 0>(iv, gbuf0 + flip * kGBufBytes, gMaskPooled, acc, Hs, Ws, Ho, Wo);
+                flip ^= 1u;
+                if (last) {
                     __syncwarp();
                     if (lane == 0u) mbar_arrive(&empty[s]);   // the window is free while the last sums are reduced
                 }
@@ -1272,7 +1338,7 @@ inline int launch_bwd_ring(const float* src, const float* H, const float* gOut, 
     if (gOut && gMaskPooled) kern = fixed ? warp_bwd_ring_kernel<kBlk, true, true, 128> : warp_bwd_ring_kernel<kBlk, true, true, 0>;
     else if (gOut) kern = fixed ? warp_bwd_ring_kernel<kBlk, true, false, 128> : warp_bwd_ring_kernel<kBlk, true, false, 0>;
     else kern = fixed ? warp_bwd_ring_kernel<kBlk, false, true, 128> : warp_bwd_ring_kernel<kBlk, false, true, 0>;
-    const int smem = gOut ? Cfg::kSmem : 0;
+    const int smem = gOut ? Cfg::kBwdSmem : 0;
     if (smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return static_cast<int>(e);
