@@ -98,6 +98,10 @@ int bh_warp_bwd(const float* src, const float* H, const float* gOut, const float
  *          g_f1,g_f2: optional (NULL when the extractor inputs need no gradient, the shipped configs).
  * bh_bihome_rescale multiplies every gradient of sample b by gscale[b] (device vector) and is a no-op
  * launch when gscale[b] == 1 -- the autograd backward calls it with the upstream gradient.
+ * One or two stream-ordered launches depending on layout and batch (cluster kernel; TMA-ring cluster kernel; persistent
+ * TMA stream + per-sample finish -- DESIGN.md section 4); g_m1w / g_m2w double as scratch between them, every output is
+ * final when the call's last launch completes.  Tuning knobs read from the environment at call time, for the
+ * microbenchmark only: BH_LOSS_VARIANT = ldg | cluster | stream, BH_LOSS_CL = 1 | 2 | 4 | 8.
  * ------------------------------------------------------------------------------------------- */
 int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* f1w, const float* f2w, const float* m1,
                       const float* m2, const float* m1w, const float* m2w, const float* H12, const float* H21,
