@@ -68,22 +68,28 @@ __device__ __forceinline__ void store9(const float (&acc)[9], float* dst) {
 // =================================================================================================
 // ring path (NCHW, the default): persistent, warp-specialised, TMA-pipelined.
 //
-//   work item  = (plane, 64x64 block of output pixels); grid = 3 CTAs per SM walking the items round-robin.
-//   warp 8     = PRODUCER.  For the item after the one being sampled it loads H, computes the source box the block can
-//                touch (bounding box of its four projected corners), classifies the 8 x 4 groups of 32x4 output pixels
-//                (one group per lane, convexity argument on the group's corners), writes the ZERO FRAME of the staging
-//                window, publishes all of it as an item header in shared memory and issues one bulk TMA copy per source
-//                row of the box (cp.async.bulk -> UBLKCP) into the free stage, completing on full[stage].
-//   warps 0..7 = CONSUMERS.  Wait full[stage], read the header (~20 LDS instead of hundreds of set-up instructions per
-//                thread), sample, arrive on empty[stage].  The lanes of a warp sit on 32 CONSECUTIVE output columns and
-//                walk down 16 rows in groups of 4: with a window pitch that is a multiple of 32 floats the four tap
-//                loads of a warp are conflict-free LDS, output stores / upstream-gradient loads are 128-byte rows.
+//   work item  = a whole source plane with its 128x128 (or smaller) output (kBlk = 128), or one 64x64 block of output
+//                pixels (kBlk = 64); one (two) persistent CTA(s) per SM walk the items round-robin; the last round is
+//                split into half-items when that evens out the tail (ring_split).
+//   last warp  = PRODUCER.  For the items after the one being sampled it loads H, computes the source box the block can
+//                touch (kBlk = 64: bounding box of its four projected corners; kBlk = 128: the plane), writes the ZERO
+//                FRAME of the staging window, publishes the geometry as an item header in shared memory and issues the
+//                bulk TMA copies (cp.async.bulk -> UBLKCP: 4 x 16 KB for a plane, one per source row for a box) into
+//                the free stage, completing on full[stage].
+//   the others = CONSUMERS.  Wait full[stage], read the header, classify their 32x4 groups (inside / border / outside,
+//                convexity argument on the projected group corners), sample, arrive on empty[stage].  The lanes of a
+//                warp sit on 32 CONSECUTIVE output columns and walk down 16 rows in groups of 4 (8 on the interior
+//                fast path): with a window pitch that is a multiple of 32 floats the four tap loads of a warp are
+//                conflict-free LDS, output stores are 128-byte rows.
 //   zero frame = 1 row above, 2 below, 4 columns left and right of the staged box: grid_sample's "zeros" padding is a
 //                clamp of (u, v) to [-1, W] x [-1, H] followed by the same four unpredicated LDS an interior pixel does.
 //   floor      = add.rm.f32 with 1.5 * 2^23: cell index and fraction come out of the FMA pipe (no FRND / F2I).
-// The copies of item k+1 are in flight while item k is sampled, so no warp waits on the DRAM latency of its own box.
-// Blocks whose box exceeds the stage (local scale > ~1.4, strong down-sampling) read the plane through the read-only
-// cache with predicated taps inside the same kernel.
+//   arithmetic = packed fp32x2 (FFMA2 / FADD2 / FMUL2): rows (j, j + 1) of a lane's column share an instruction.
+//   backward   = the upstream gradients of the NEXT strip travel by 4-byte cp.async into per-warp landing buffers while
+//                the current strip is sampled (strip_prefetch); six packed partial sums per lane, fixed-order finish.
+// The copies run two items (backward: one item) ahead of the consumers, so no warp waits on the DRAM latency of its own
+// window.  Blocks whose box exceeds the stage (local scale > ~1.4, strong down-sampling) read the plane through the
+// read-only cache with predicated taps inside the same kernel.
 // =================================================================================================
 constexpr int kStripRows = 16;    // rows walked by one consumer warp per strip (32 columns x 16 rows)
 constexpr int kGBufBytes = (kStripRows + 4) * 32 * 4;   // one strip of upstream gradients + its 4 pooled-mask cells, per lane
@@ -92,8 +98,9 @@ constexpr int kPadL = 4, kPadT = 1, kPadB = 2;   // the 4 floats in front of a w
 // its 32 strips are sampled by 16 consumer warps, 1 CTA per SM, 3 stages (216 KB): the copies run two planes ahead.
 // kBlk = 64: larger sources, 8 consumer warps, 3 stages, 2 CTAs per SM.
 // (Measured dead ends, kept out of the code: folding the producer into the last consumer warp to finish -- 16 warps, 128
-// registers -- is 7 % slower; fetching a whole strip of upstream gradients one strip ahead spills at the 96 registers a
-// 17-warp CTA leaves per thread and is 40 % slower.)
+// registers -- is 7 % slower; fetching a whole strip of upstream gradients one strip ahead IN REGISTERS spills at the
+// 96 registers a 17-warp CTA leaves per thread and is 40 % slower -- hence the cp.async landing buffers; issuing the
+// copies before the header's H load (two arrivals on full[]) changes nothing measurable.)
 template <int kBlk>
 struct RingCfg {
     static constexpr int kStages = 3;

@@ -162,6 +162,9 @@ def main():
         bench_loss(1024, 128, 64, t, True)      # B >= 512: the clustered TMA-ring kernel
         bench_feature_warp(64, 128, 64, t)
         bench_small(256, 128, t)
+        F.mace(torch.randn(256, 4, 2, device='cuda'), torch.randn(256, 4, 2, device='cuda'))
+        F.coverage_mask(rand_h(256, 128)[0].detach(), (128, 128), (128, 128), pool=8)      # the stand-alone analytic mask kernel
+        torch.cuda.synchronize()
         return
     t = Timer(a.iters, dirty=a.dirty)
     if a.loss_cl:
