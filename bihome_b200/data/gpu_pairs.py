@@ -4,7 +4,9 @@
 A pool of uint8 RGB images lives in HBM; every batch is drawn and rendered by the K5 kernels
 (``bh_pairgen_draw`` + ``bh_pairgen_apply``): no worker processes, no pickling, no host->device copy of
 240x320x3 float images the model never reads.  The batch dict has the reference's keys
-that the model consumes: patch_1, patch_2 [B,1,P,P], delta [B,4,2] (ground truth for MACE).
+that the model consumes: patch_1, patch_2 [B,1,P,P], delta [B,4,2] (ground truth for MACE), corners [B,4,2]
+(image-frame patch corners) and target -- delta again for target_gen '4_points', the dense perspective field
+[B,2,P,P] for 'all_points' (the supervised zeng-orig configs).
 """
 import os
 
@@ -16,15 +18,16 @@ from .. import functional as F
 
 def transform_args(transforms, name='HomographyNetPrep'):
     """pull [rho, patch_size, distort_keys, max_delta, target_gen] and the standardisation out of a DATA.TRANSFORMS list"""
-    out = {'rho': 32, 'patch_size': 128, 'max_delta': 32, 'mean': 0.443, 'std': 0.129}
+    out = {'rho': 32, 'patch_size': 128, 'max_delta': 32, 'mean': 0.443, 'std': 0.129, 'target_gen': '4_points'}
     for t in transforms:
         (k, v), = t.items()
         if k == name:
             out['rho'], out['patch_size'] = int(v[0]), int(v[1])
             if len(v) > 3:
                 out['max_delta'] = float(v[3])
-            if len(v) > 4 and v[4] != '4_points':
-                raise NotImplementedError("GPU pair generation implements target_gen '4_points' only")
+            if len(v) > 4:
+                assert v[4] in ('4_points', 'all_points'), 'I do not know this, it should be either \'4_points\' ar \'all_points\''
+                out['target_gen'] = v[4]
         elif k == 'DictStandardize':
             m, s = v[0], v[1]
             out['mean'] = float(m[0] if isinstance(m, (list, tuple)) else m)
@@ -80,6 +83,41 @@ def load_pool(directory, device='cuda', limit=None, size=(320, 240)):
     return torch.from_numpy(np.stack(arrs)).to(device)
 
 
+def patch_corners(pos_xy, patch_size):
+    """centre positions [B,2] -> image-frame corners [B,4,2], clockwise from the top left (transforms.py:527-531)"""
+    s = patch_size // 2
+    off = torch.tensor([[-s, -s], [s, -s], [s, s], [-s, s]], device=pos_xy.device, dtype=pos_xy.dtype)
+    return pos_xy.unsqueeze(1) + off
+
+
+def perspective_field_target(corners, delta, patch_size):
+    """HomographyNetPrep's 'all_points' target (reference src/data/transforms.py:634-687): the displacement
+    proj(H, p) - p of every patch pixel p under the image-frame homography corners -> corners + delta, [B,2,P,P].
+
+    Arithmetic as the reference's: the 8x8 system of cv2.getPerspectiveTransform and the projection in float64, the
+    projected point rounded to float32 (cv2.perspectiveTransform's output type), the difference to the integer pixel
+    coordinate taken exactly, the result cast to float32 (train.py:308-309).  Plain torch ops on the pool's device:
+    33 MB of writes per 256 pairs, off the north-star path (only the supervised *-orig configs ask for it)."""
+    B = corners.shape[0]
+    src = corners.to(torch.float64)
+    dst = src + delta.to(torch.float64)
+    x, y, u, v = src[..., 0], src[..., 1], dst[..., 0], dst[..., 1]
+    zero, one = torch.zeros_like(x), torch.ones_like(x)
+    rows_u = torch.stack([x, y, one, zero, zero, zero, -x * u, -y * u], dim=-1)
+    rows_v = torch.stack([zero, zero, zero, x, y, one, -x * v, -y * v], dim=-1)
+    A = torch.cat([rows_u, rows_v], dim=1)                                   # [B,8,8]
+    h = torch.linalg.solve(A, torch.cat([u, v], dim=1).unsqueeze(-1)).squeeze(-1)
+    P = int(patch_size)
+    r = torch.arange(P, device=src.device, dtype=torch.float64)
+    px = (src[:, 0, 0].view(B, 1, 1) + r.view(1, 1, P)).expand(B, P, P)
+    py = (src[:, 0, 1].view(B, 1, 1) + r.view(1, P, 1)).expand(B, P, P)
+    g = lambda i: h[:, i].view(B, 1, 1)
+    w = g(6) * px + g(7) * py + 1.0
+    qx = ((g(0) * px + g(1) * py + g(2)) / w).float().double() - px
+    qy = ((g(3) * px + g(4) * py + g(5)) / w).float().double() - py
+    return torch.stack([qx, qy], dim=1).float()
+
+
 def rank_seed(seed, rank):
     """rank-seeded generator key: ranks of a data-parallel job draw disjoint streams"""
     return (int(seed) * 1000003 + int(rank)) & (2 ** 63 - 1)
@@ -89,12 +127,13 @@ class GpuPairLoader:
     """Iterable of batch dicts; ``len`` = steps per epoch (reference DatasetSampler.__len__)."""
 
     def __init__(self, pool, batch_size, samples_per_epoch, rho=32, patch_size=128, max_delta=32.0, mean=0.443, std=0.129,
-                 seed=42, rank=0):
+                 seed=42, rank=0, target_gen='4_points'):
         assert pool.is_cuda and pool.dtype == torch.uint8 and pool.dim() == 4
         self.pool = pool
         self.batch_size = int(batch_size)
         self.steps = int(samples_per_epoch) // self.batch_size
         self.cfg = dict(rho=int(rho), patch_size=int(patch_size), max_delta=float(max_delta), mean=float(mean), std=float(std))
+        self.target_gen = target_gen
         self.seed = rank_seed(seed, rank)
         self.step = 0
 
@@ -108,7 +147,9 @@ class GpuPairLoader:
                                        self.step, self.pool.device)
         p1, p2, delta = F.pairgen_apply(self.pool, index, params, c['patch_size'], c['mean'], c['std'])
         self.step += 1
-        return {'patch_1': p1, 'patch_2': p2, 'delta': delta}
+        corners = patch_corners(params[:, 22:24], c['patch_size'])           # pos_x, pos_y of the params table
+        target = delta if self.target_gen == '4_points' else perspective_field_target(corners, delta, c['patch_size'])
+        return {'patch_1': p1, 'patch_2': p2, 'delta': delta, 'corners': corners.float(), 'target': target}
 
     def __iter__(self):
         for _ in range(self.steps):

@@ -52,6 +52,8 @@ def evaluate(model, batches, log_filepath=None, seed=None):
             e0.record()
             delta_hat, _ = model.predict_homography(data)
             e1.record()
+            if not torch.is_tensor(delta_hat):      # NoOpHead 'all_points': cv2 RANSAC post-processing returns numpy
+                delta_hat = torch.as_tensor(np.asarray(delta_hat), device=data['delta'].device)
             mace = F.mace(data['delta'].float(), delta_hat.float())
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -65,10 +67,10 @@ def evaluate(model, batches, log_filepath=None, seed=None):
 
 def fixed_batches(path, batch_size, device):
     z = np.load(path)
-    p1, p2, d = (torch.from_numpy(z[k]).float() for k in ('patch_1', 'patch_2', 'delta'))
-    for i in range(0, p1.shape[0], batch_size):
-        yield {'patch_1': p1[i:i + batch_size].to(device), 'patch_2': p2[i:i + batch_size].to(device),
-               'delta': d[i:i + batch_size].to(device)}
+    keys = ['patch_1', 'patch_2', 'delta'] + [k for k in ('corners', 'target') if k in z.files]
+    arrays = {k: torch.from_numpy(z[k]).float() for k in keys}
+    for i in range(0, arrays['patch_1'].shape[0], batch_size):
+        yield {k: v[i:i + batch_size].to(device) for k, v in arrays.items()}
 
 
 def main(config_file_path, ckpt_file_path=None, batch_size=None, visualize=False, log_filepath=None, samples=None,

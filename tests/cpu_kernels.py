@@ -1,0 +1,60 @@
+"""Oracle-backed stand-ins for the CUDA ops of ``bihome_b200.functional`` -- for the CPU tests of the HOST LOGIC only.
+
+The product has no CPU path (every op raises on a non-CUDA tensor).  To check on a machine without a GPU that the
+Python mirrors of the reference's heads wire the ops together the way the reference does, the tests patch the
+entry points the mirrors call with the oracle's closed forms (float64 capable, autograd through plain torch ops).
+Nothing outside tests/ imports this module.
+"""
+import torch
+
+from oracle import ref_path as R
+
+
+def dlt4(delta, corners=None, size=None):
+    if corners is None:
+        w, h = size
+        corners = torch.tensor([[0, 0], [w, 0], [w, h], [0, h]], dtype=delta.dtype).repeat(delta.shape[0], 1, 1)
+    return R.four_point_to_homography(corners.to(delta.dtype), delta)
+
+
+def coverage_mask(H, src_hw, out_hw, pool=1):
+    m = R.analytic_mask(H, src_hw[0], src_hw[1], out_hw[0], out_hw[1])
+    return torch.nn.functional.avg_pool2d(m, pool).squeeze(1)
+
+
+def warp(src, H, out_h, out_w, pool=None):
+    if tuple(src.shape[-2:]) == (out_h, out_w):
+        # like for like with the golden vectors: the kornia route of the reference, whose sampling grid is born in
+        # float32 even in a float64 evaluation (1e-8 px of coordinate noise, enough to flip bilinear cells)
+        out = R.warp_image(src, H, out_h, out_w)
+    else:
+        out = R.warp_direct(src, H, out_h, out_w)
+    if pool:
+        return out, coverage_mask(H, src.shape[-2:], (out_h, out_w), pool)
+    return out
+
+
+def bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu, m1=None, m2=None):
+    ones = torch.ones_like(m1w)
+    u = lambda t: (ones if t is None else t).unsqueeze(1)
+    _, p = R.bihome_double_line(f1, f2, f1w, f2w, u(m1), u(m2), u(m1w), u(m2w), H12, H21, mu)
+    loss_b = p['ln1'] + p['ln2'] + mu * p['ln3']
+    parts = torch.stack([p['ln1'], p['ln2'], p['den1'], p['den2'], p['ln3']], dim=1).detach()
+    return loss_b, parts
+
+
+def dltn_field(field, choice, four_points):
+    delta, H, _ = R.zeng_delta_hat(field, choice.shape[1], 1, choice.reshape(-1))
+    return H.reshape(-1, 3, 3), delta.reshape(-1, 4, 2)
+
+
+def mace(delta_gt, delta_hat):
+    return (delta_gt.reshape(-1, 2) - delta_hat.reshape(-1, 2)).norm(dim=-1).mean()
+
+
+def install(monkeypatch):
+    import bihome_b200.functional as F
+    for name, fn in (('dlt4', dlt4), ('warp', warp), ('coverage_mask', coverage_mask), ('bihome_loss', bihome_loss),
+                     ('dltn_field', dltn_field), ('mace', mace)):
+        monkeypatch.setattr(F, name, fn)
+    return F

@@ -1,0 +1,89 @@
+"""GPU parity of the remaining heads (TripletHead, PhotometricHead, NoOpHead) and of the PerceptualHead variants that
+run their loss algebra in torch ops on the K1 / K2 kernels, against golden vectors of the unmodified reference modules
+(oracle/make_golden_heads.py).  float32 on the device against the reference's float64 evaluation; the reference's own
+float32 run differs from it by up to 4e-5 on these gradients (hinge and bilinear-cell discontinuities), hence 1e-3.
+
+Named to sort after the kernel / north-star head tests.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from test_head_mirrors import PERCEPTUAL_CASES, TRIPLET_CASES, perceptual_kwargs, triplet_forward
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL, GRAD_TOL = 2e-5, 1e-3
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _exact_convs():
+    assert torch.cuda.is_available()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def cu(a):
+    return torch.as_tensor(np.asarray(a)).float().cuda()
+
+
+@pytest.mark.parametrize('name', sorted(PERCEPTUAL_CASES))
+def test_perceptual_variants_golden(golden, name):
+    from bihome_b200.heads import PerceptualHead as PH
+    from oracle.make_golden import TinyExtractor
+    g = golden('perceptual_variants_P64.npz')
+    model = PH.Model(backbone=torch.nn.Identity(), **perceptual_kwargs(64, **PERCEPTUAL_CASES[name])).cuda()
+    model.auxiliary_resnet = TinyExtractor().cuda()
+    a, b = cu(g['delta_12']).requires_grad_(True), cu(g['delta_21']).requires_grad_(True)
+    data = {'patch_1': cu(g['patch_1']), 'patch_2': cu(g['patch_2']), 'delta_hat_12': a, 'delta_hat_21': b,
+            'mask_1': cu(g['mask_1']), 'mask_2': cu(g['mask_2'])}
+    loss, _, _ = model(data)
+    ref = float(g[name + '_loss64'])
+    assert abs(loss.item() - ref) < LOSS_TOL * abs(ref)
+    double = 'double' in name
+    grads = torch.autograd.grad(loss, (a, b) if double else (a,))
+    tol = 2 * GRAD_TOL if 'cos' in name else GRAD_TOL
+    assert rel_l2(grads[0].cpu().numpy(), g[name + '_g12_64']) < tol
+    if double:
+        assert rel_l2(grads[1].cpu().numpy(), g[name + '_g21_64']) < tol
+
+
+@pytest.mark.parametrize('name', sorted(TRIPLET_CASES))
+def test_triplet_head_golden(golden, name):
+    g = golden('triplet_head_P32.npz')
+    loss, g12, g21, gnorm, conv1 = triplet_forward(g, name, torch.float32, 'cuda')
+    ref = float(g[name + '_loss64'])
+    assert abs(loss.item() - ref) < LOSS_TOL * abs(ref)
+    assert rel_l2(g12.cpu().numpy(), g[name + '_g12_64']) < GRAD_TOL
+    if g21 is not None:
+        assert rel_l2(g21.cpu().numpy(), g[name + '_g21_64']) < GRAD_TOL
+    assert abs(gnorm - float(g[name + '_gparam_norm64'])) < GRAD_TOL * float(g[name + '_gparam_norm64'])
+    assert rel_l2(conv1.cpu().numpy(), g[name + '_gfe_conv1_64']) < GRAD_TOL
+
+
+def test_photometric_head_golden(golden):
+    from bihome_b200.heads import PhotometricHead as PHO
+    g = golden('photometric_noop_P32.npz')
+    head = PHO.Model(None, LEARNING_KEYS=['patch_2', 'image_1', 'delta', 'delta_hat_12'])
+    d = cu(g['delta_hat']).requires_grad_(True)
+    data = {'patch_2': cu(g['patch_gt']), 'image_1': cu(g['image']), 'delta': cu(g['delta_gt']), 'delta_hat_12': d,
+            'corners': cu(g['corners'])}
+    gt, hat, dg, dh = head(data)
+    assert gt is data['patch_2'] and dg is data['delta'] and dh is d
+    assert rel_l2(hat.detach().cpu().numpy(), g['photo_patch_hat64']) < 1e-5
+    gd, = torch.autograd.grad((hat * cu(g['g_out'])).sum(), d)
+    assert rel_l2(gd.cpu().numpy(), g['photo_gdelta64']) < GRAD_TOL
+    _, hom = head.predict_homography(data)
+    assert rel_l2(hom.detach().cpu().numpy(), g['photo_H64']) < 1e-5
+
+
+def test_noop_head_on_device(golden):
+    from bihome_b200.heads import NoOpHead as NO
+    g = golden('photometric_noop_P32.npz')
+    head = NO.Model(None, TARGET_GEN='all_points', LEARNING_KEYS=['target', 'pf_hat_12', 'delta', 'pf_hat_12'])
+    ret = head({'target': cu(g['noop_target']), 'pf_hat_12': cu(g['noop_field']), 'delta': cu(g['delta_gt'])})
+    assert np.array_equal(ret[3].cpu().numpy(), g['noop_delta_hat'])
+    head4 = NO.Model(None, TARGET_GEN='4_points', LEARNING_KEYS=['delta', 'delta_hat_12', 'delta', 'delta_hat_12'])
+    _, hom = head4.predict_homography({'delta_hat_12': cu(g['delta_hat']), 'corners': cu(g['corners'])})
+    assert rel_l2(hom.cpu().numpy(), g['noop_H64']) < 1e-5

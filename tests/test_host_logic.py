@@ -69,9 +69,24 @@ def test_hot_path_refuses_cpu_tensors():
 def test_transform_args_from_yaml():
     from bihome_b200.data import gpu_pairs
     t = gpu_pairs.transform_args(cfg('pds-coco/zeng-bihome-lr-1e-3.yaml')['DATA']['TRANSFORMS'])
-    assert t == {'rho': 32, 'patch_size': 128, 'max_delta': 32.0, 'mean': 0.443, 'std': 0.129}
+    assert t == {'rho': 32, 'patch_size': 128, 'max_delta': 32.0, 'mean': 0.443, 'std': 0.129, 'target_gen': '4_points'}
     t = gpu_pairs.transform_args(cfg('s-coco/detone-bihome-lr-5e-3.yaml')['DATA']['TRANSFORMS'])
     assert t['max_delta'] == 0.0
+    zeng_orig = [{'HomographyNetPrep': [32, 128, ['image_1', 'image_2'], 32, 'all_points']},
+                 {'DictStandardize': [[0.443], [0.129], ['patch_1', 'patch_2']]}]
+    assert gpu_pairs.transform_args(zeng_orig)['target_gen'] == 'all_points'
+
+
+def test_all_points_target_is_bit_exact(golden):
+    """the dense perspective-field target of the zeng-orig configs against HomographyNetPrep(target_gen='all_points')
+    of the unmodified reference (oracle/make_golden_heads.py): every one of the 2 x 2 x 128 x 128 floats equal"""
+    from bihome_b200.data import gpu_pairs
+    g = golden('all_points_target.npz')
+    corners, delta = torch.as_tensor(g['corners']), torch.as_tensor(g['delta'])
+    target = gpu_pairs.perspective_field_target(corners, delta, 128)
+    assert target.dtype == torch.float32 and np.array_equal(target.numpy(), g['target'])
+    centre = (corners[:, 0] + 64).double()
+    assert torch.equal(gpu_pairs.patch_corners(centre, 128), corners.double())
 
 
 def test_dsac_scores_single_hypothesis_are_ones():
