@@ -55,6 +55,10 @@ class Model(nn.Module):
         hs, deltas = [], []
         for i in range(b):
             hom = cv2.findHomography(np.float32(coords), np.float32(moved[i]), cv2.RANSAC, 10)[0]
+            if hom is None:     # no consensus (an untrained network's field): the reference would raise here
+                hom = cv2.findHomography(np.float32(coords), np.float32(moved[i]), 0)[0]
+            if hom is None:
+                hom = np.eye(3)
             deltas.append(cv2.perspectiveTransform(np.asarray([four], dtype=np.float32), hom).squeeze() - four)
             hs.append(hom)
         return np.array(deltas), np.array(hs)
