@@ -14,6 +14,16 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_sessionstart(session):
+    """the built library is git-ignored: a fresh checkout builds it once (nvcc cross-compiles sm_100a without a GPU)"""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, 'bihome_b200', 'libbihome_b200.so')
+    if not os.path.isfile(lib) and shutil.which('nvcc') and shutil.which('make'):
+        subprocess.run(['make', '-C', os.path.join(ROOT, 'bihome_b200', 'csrc'), '-j8'], check=False,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
 @pytest.fixture(scope='session')
 def golden():
     import numpy as np
