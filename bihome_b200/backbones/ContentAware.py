@@ -8,11 +8,10 @@ Dense convolutions: cuDNN through PyTorch (BASELINE.json north_star).  Each patc
 own call, and the trunk runs once per direction, because every BatchNorm here normalises with the statistics of the
 call it sits in -- batching the two patches would change the numbers the reference produces.
 """
-import warnings
-
 import torch
 import torch.nn as nn
-import torchvision.models as models
+
+from .blocks import offset_regressor
 
 
 def _stage(cin, cout, last=None):
@@ -85,15 +84,7 @@ class Model(nn.Module):
         pretrained = kwargs['PRETRAINED_RESNET']
         if pretrained:
             self.init()                 # reference order (:104-117): small nets first, then the pretrained trunk
-        net = None
-        if pretrained:
-            try:
-                net = models.resnet34(weights='DEFAULT', progress=True)
-            except Exception as e:  # noqa: BLE001 -- no network / no cached checkpoint
-                warnings.warn('bihome_b200: pretrained resnet34 weights unavailable (%s); using random init' % e)
-        self.resnet34 = net if net is not None else models.resnet34(weights=None)
-        self.resnet34.conv1 = nn.Conv2d(2, 64, kernel_size=(7, 7), stride=(2, 2), padding=(3, 3), bias=False)
-        self.resnet34.fc = nn.Linear(512, 8, bias=True)
+        self.resnet34 = offset_regressor(pretrained)
         if not pretrained:
             self.init()
 

@@ -1,10 +1,9 @@
 """DeTone-style regression backbone (reference ``src/backbones/ResNet34.py``): torchvision ResNet-34 with a
 2-channel stem and an 8-way head, emitting the 4-point offsets directly.  Same kwargs / dict protocol / names."""
-import warnings
-
 import torch
 import torch.nn as nn
-import torchvision.models as models
+
+from .blocks import offset_regressor
 
 
 class Model(nn.Module):
@@ -13,27 +12,21 @@ class Model(nn.Module):
         super().__init__()
         self.patch_keys = kwargs['PATCH_KEYS']
         self.target_keys = kwargs['TARGET_KEYS']
-        net = None
-        if kwargs['PRETRAINED_RESNET']:
-            try:
-                net = models.resnet34(weights='DEFAULT', progress=True)
-            except Exception as e:  # noqa: BLE001
-                warnings.warn('bihome_b200: pretrained resnet34 weights unavailable (%s); using random init' % e)
-        self.resnet34 = net if net is not None else models.resnet34(weights=None)
-        self.resnet34.conv1 = nn.Conv2d(2, 64, kernel_size=(7, 7), stride=(2, 2), padding=(3, 3), bias=False)
-        self.resnet34.fc = nn.Linear(512, 8, bias=True)
-        self.variant = str.lower(kwargs['VARIANT']) if 'VARIANT' in kwargs else 'oneline'
-        assert 'oneline' in self.variant or 'doubleline' in self.variant, 'Only OneLine or DoubleLine variant is supported'
+        self.resnet34 = offset_regressor(kwargs['PRETRAINED_RESNET'])
+        self.variant = kwargs.get('VARIANT', 'oneline').lower()
+        if not ('oneline' in self.variant or 'doubleline' in self.variant):
+            raise AssertionError('Only OneLine or DoubleLine variant is supported')
 
     def single_forward(self, x):
         return self.resnet34(x).reshape(-1, 4, 2)
 
     def forward(self, data):
-        e1, e2 = self.patch_keys
-        p1, p2 = data[e1], data[e2]
-        data[self.target_keys[0]] = self.single_forward(torch.cat([p1, p2], dim=1))
-        if self.variant == 'doubleline':
-            data[self.target_keys[1]] = self.single_forward(torch.cat([p2, p1], dim=1))
+        """adds TARGET_KEYS[0] (patch 1 -> 2) and, for DoubleLine, TARGET_KEYS[1] (patch 2 -> 1) to the batch dict; the
+        two directions are separate passes because BatchNorm normalises with the statistics of each call"""
+        pair = [data[k] for k in self.patch_keys]
+        directions = (pair, pair[::-1]) if self.variant == 'doubleline' else (pair,)
+        for key, (a, b) in zip(self.target_keys, directions):
+            data[key] = self.single_forward(torch.cat([a, b], dim=1))
         return data
 
     def predict_homography(self, data):

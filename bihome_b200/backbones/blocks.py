@@ -4,7 +4,10 @@ Same layer graph and the same parameter names (``upper_branch.<i>`` / ``lower_br
 ``src/backbones/utils.py`` so that reference checkpoints load unchanged; the dense convolutions stay on cuDNN
 (tensor-core work is out of scope for the custom kernels, BASELINE.json north_star).
 """
+import warnings
+
 import torch.nn as nn
+import torchvision.models as models
 
 
 def _conv(cin, cout, k, stride=1, bias=False):
@@ -77,3 +80,20 @@ class ResNet50DeconvBlock(_Residual):
         upper = _seq(('t', c, c, True), ('c', c, c, 3, 1), 'r', ('c', c, c // 2, 1, 1))
         lower = _seq(('t', c, c // 2, False), ('b', c // 2))
         super().__init__(upper, lower)
+
+
+def offset_regressor(pretrained):
+    """torchvision ResNet-34 turned into the 4-point regressor both the DeTone-style and the content-aware backbone use:
+    a 2-channel 7x7 stem (the two patches, or the two masked feature maps) and an 8-way linear head.  ``pretrained``
+    asks for the ImageNet trunk; without network access (no cached checkpoint) it degrades to random init with a warning."""
+    trunk = None
+    if pretrained:
+        try:
+            trunk = models.resnet34(weights='DEFAULT', progress=True)
+        except Exception as e:  # noqa: BLE001 -- URLError / missing cache
+            warnings.warn('bihome_b200: pretrained resnet34 weights unavailable (%s); using random init' % e)
+    if trunk is None:
+        trunk = models.resnet34(weights=None)
+    trunk.conv1 = nn.Conv2d(2, 64, kernel_size=7, stride=2, padding=3, bias=False)
+    trunk.fc = nn.Linear(512, 8, bias=True)
+    return trunk
