@@ -29,6 +29,16 @@ def test_build_model_from_yaml(rel):
     assert opt.defaults['lr'] == c['SOLVER']['LR'] and sched.milestones
 
 
+@pytest.mark.parametrize('rel', ['pds-coco/zeng-bihome-lr-1e-3.yaml', 's-coco/detone-bihome-lr-5e-3.yaml'])
+def test_committed_configs_equal_the_reference_files(rel):
+    """config/ holds normalised YAML: every key and value must equal the reference's file of the same name"""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip('reference tree not present')
+    from bihome_b200 import engine
+    assert cfg(rel) == engine.load_config(os.path.join(ref_import.REFERENCE_ROOT, 'config', rel))
+
+
 def test_reference_state_dict_compatibility():
     from oracle import ref_import
     if not ref_import.available():
