@@ -261,6 +261,7 @@ def run_ours(args):
                                    'loss, ResNet-34 stem extractor), 128x128 patches, B=%d per GPU, fp32 (cuDNN TF32 convs = torch default), '
                                    'random-init weights, synthetic uint8 image pool (%d x 240x320) resident in HBM' % (B, args.pool),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world, 'channels_last': bool(args.channels_last),
+                       'field_head': 'fused (K6)' if F.field_head_enabled() else 'aten',
                        'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
@@ -285,11 +286,16 @@ def main():
     ap.add_argument('--pool', type=int, default=256, help='synthetic uint8 images resident on each GPU')
     ap.add_argument('--nchw', dest='channels_last', action='store_false',
                     help='keep the conv stack in NCHW (default: channels-last, 2.5x faster cuDNN path on B200)')
+    ap.add_argument('--field-head', default=None, choices=['aten', 'fused'],
+                    help="Zeng backbone's last stage: 'aten' = the four torch modules (default), 'fused' = K6 (csrc/fieldhead.cu); "
+                         'unset = whatever BH_FIELD_HEAD says')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer phase (profiling runs)')
     ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.field_head is not None:
+        os.environ['BH_FIELD_HEAD'] = args.field_head
     if args.impl == 'reference':
         run_reference(args)
     else:

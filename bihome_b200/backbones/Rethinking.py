@@ -6,6 +6,7 @@ import warnings
 import torch
 import torch.nn as nn
 
+from .. import functional as F
 from .blocks import (ResNet34ConvBlock, ResNet34IdentityBlock, ResNet50ConvBlock, ResNet50DeconvBlock,
                      ResNet50IdentityBlock)
 
@@ -83,9 +84,13 @@ class Model(nn.Module):
         self.load_state_dict(picked, strict=False)
 
     def _forward(self, x):
-        for i in range(1, 9):
+        for i in range(1, 8):
             x = getattr(self, 'layer%d' % i)(x)
-        return x
+        # layer8 (1x1 conv -> BatchNorm -> ReLU -> 1x1 conv at full resolution) is 21 passes over a [B,128,P,P] tensor
+        # through ATen; K6 computes it per pixel from the 16-channel input (opt-in, see functional.field_head_enabled)
+        if F.field_head_enabled() and F.field_head_supported(self.layer8, x):
+            return F.field_head(self.layer8, x)
+        return self.layer8(x)
 
     def forward(self, data):
         e1, e2 = self.patch_keys

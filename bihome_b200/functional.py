@@ -10,8 +10,10 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   dltn(p1, p2, choice) / dltn_field(field, choice, four)   K4   find_homography_dlt        (ransac_utils.py:58-72, PerceptualHead.py:164-178)
   pairgen_draw(...) / pairgen_apply(...)                   K5   HomographyNetPrep pipeline (src/data/transforms.py:456-576)
   mace(delta_gt, delta_hat)                                     train.py:401-404
+  field_head(stage, x)                                     K6   Zeng backbone layer8       (src/backbones/Rethinking.py:144-147)
 """
 import ctypes
+import os
 
 import torch
 
@@ -391,3 +393,160 @@ def mace(delta_gt, delta_hat):
     with torch.cuda.device(a.device), _timed('bh_mace'):
         cabi.check(cabi.lib().bh_mace(_ptr(a), _ptr(b), _ptr(out), a.numel() // 8, _stream()), 'bh_mace')
     return out[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# K6: perspective-field head (Conv2d(16,128,1) -> BatchNorm2d -> ReLU -> Conv2d(128,2,1)) as a per-pixel kernel
+# ------------------------------------------------------------------------------------------------
+def _fh_moments(x):
+    """x [B,C,H,W] channels-last -> (sum_p x_i [C], sum_p x_i x_k [C,C]) in float64"""
+    _need_cuda_f32('x', x)
+    B, C, H, W = x.shape
+    n = B * H * W
+    lib = cabi.lib()
+    grid = lib.bh_fieldhead_grid(0, n)
+    pairs = C * (C + 1) // 2
+    parts = torch.empty(grid, C + pairs, device=x.device, dtype=torch.float64)
+    with torch.cuda.device(x.device), _timed('bh_fieldhead_moments'):
+        cabi.check(lib.bh_fieldhead_moments(_ptr(x), _ptr(parts), n, C, _stream()), 'bh_fieldhead_moments')
+    s = parts.sum(0)
+    iu = torch.triu_indices(C, C, device=x.device)
+    upper = torch.zeros(C, C, device=x.device, dtype=torch.float64)
+    upper[iu[0], iu[1]] = s[C:]
+    return s[:C], upper + upper.triu(1).t()
+
+
+def _fh_fwd(x, W1, b1, W2, b2):
+    """x [B,C,H,W] channels-last, folded W1 [hid,C], b1 [hid], W2 [2,hid], b2 [2] -> field [B,2,H,W] (planar)"""
+    B, C, H, W = x.shape
+    out = torch.empty(B, 2, H, W, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed('bh_fieldhead_fwd'):
+        cabi.check(cabi.lib().bh_fieldhead_fwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(out), B, H * W, C,
+                                               W1.shape[0], _stream()), 'bh_fieldhead_fwd')
+    return out
+
+
+def _fh_bwd(x, W1, b1, W2, g_out):
+    """-> (gx like x, gW1 [hid,C], gb1 [hid], gW2 [2,hid], gb2 [2]) for the folded weights"""
+    B, C, H, W = x.shape
+    hid = W1.shape[0]
+    lib = cabi.lib()
+    grid = lib.bh_fieldhead_grid(1, B * H * W)
+    parts = torch.empty(grid, hid * C + 3 * hid + 2, device=x.device, dtype=torch.float32)
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device), _timed('bh_fieldhead_bwd'):
+        cabi.check(lib.bh_fieldhead_bwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(g_out), _ptr(gx), _ptr(parts), B, H * W, C,
+                                        hid, _stream()), 'bh_fieldhead_bwd')
+    s = parts.sum(0)
+    return (gx, s[:hid * C].view(hid, C), s[hid * C:hid * C + hid], s[hid * C + hid:hid * C + 3 * hid].view(2, hid),
+            s[hid * C + 3 * hid:])
+
+
+def _fh_affine(x, a, M, gx):
+    """gx += a + M x per pixel, in place"""
+    B, C, H, W = x.shape
+    with torch.cuda.device(x.device), _timed('bh_fieldhead_affine'):
+        cabi.check(cabi.lib().bh_fieldhead_affine(_ptr(x), _ptr(a), _ptr(M), _ptr(gx), B * H * W, C, 1, _stream()),
+                   'bh_fieldhead_affine')
+    return gx
+
+
+def _fold_batchnorm(W1, b1, gamma, beta, mean_y, var_y, eps):
+    """BatchNorm(y) with y = W1 x + b1 as a rescaled first layer: (W1', b1')"""
+    scale = gamma / torch.sqrt(var_y + eps)
+    return W1 * scale[:, None], (b1 - mean_y) * scale + beta
+
+
+def _hidden_statistics(W1, b1, s1, s2, n):
+    """mean and (biased) variance over all pixels of y = W1 x + b1, from the input's first and second moments"""
+    mean_x = s1 / n
+    cov_x = s2 / n - torch.outer(mean_x, mean_x)
+    return W1 @ mean_x + b1, ((W1 @ cov_x) * W1).sum(1)
+
+
+class _FieldHead(torch.autograd.Function):
+    """out = conv2(relu(bn(conv1(x)))) for 1x1 convolutions, without the hidden tensor (csrc/fieldhead.cu).
+    The tiny algebra (fold, statistics and their adjoints) runs in float64 torch ops."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, gamma, beta, W2, b2, running_mean, running_var, training, eps):
+        B, C, H, W = x.shape
+        n = B * H * W
+        hid = W1.shape[0]
+        d = torch.float64
+        W1d, b1d, gd, bd = W1.reshape(hid, C).to(d), b1.to(d), gamma.to(d), beta.to(d)
+        if training:
+            s1, s2 = _fh_moments(x)
+            mean_y, var_y = _hidden_statistics(W1d, b1d, s1, s2, n)
+            stats = (s1, s2)
+        else:
+            mean_y, var_y = running_mean.to(d), running_var.to(d)
+            stats = (mean_y, var_y)
+        W1f, b1f = _fold_batchnorm(W1d, b1d, gd, bd, mean_y, var_y, eps)
+        out = _fh_fwd(x, W1f.to(x.dtype).contiguous(), b1f.to(x.dtype).contiguous(), W2.reshape(2, hid).contiguous(), b2.contiguous())
+        ctx.save_for_backward(x, W1, b1, gamma, beta, W2, *stats)
+        ctx.cfg = (training, eps, n)
+        ctx.mark_non_differentiable(mean_y, var_y)
+        return out, mean_y, var_y
+
+    @staticmethod
+    def backward(ctx, g_out, _g_mean, _g_var):
+        x, W1, b1, gamma, beta, W2, st0, st1 = ctx.saved_tensors
+        training, eps, n = ctx.cfg
+        B, C, H, W = x.shape
+        hid = W1.shape[0]
+        d = torch.float64
+        with torch.enable_grad():
+            leaves = [t.detach().to(d).requires_grad_(True) for t in (W1.reshape(hid, C), b1, gamma, beta)]
+            if training:
+                s1, s2 = st0.detach().requires_grad_(True), st1.detach().requires_grad_(True)
+                mean_y, var_y = _hidden_statistics(leaves[0], leaves[1], s1, s2, n)
+                leaves += [s1, s2]
+            else:
+                mean_y, var_y = st0, st1
+            W1f, b1f = _fold_batchnorm(leaves[0], leaves[1], leaves[2], leaves[3], mean_y, var_y, eps)
+        gx, gW1f, gb1f, gW2, gb2 = _fh_bwd(x, W1f.detach().to(x.dtype).contiguous(), b1f.detach().to(x.dtype).contiguous(),
+                                           W2.reshape(2, hid).contiguous(), g_out.contiguous())
+        grads = torch.autograd.grad([W1f, b1f], leaves, [gW1f.to(d), gb1f.to(d)])
+        if training:
+            g1, g2 = grads[4], grads[5]
+            gx = _fh_affine(x, g1.to(x.dtype).contiguous(), (g2 + g2.t()).to(x.dtype).contiguous(), gx)
+        return (gx, grads[0].to(W1.dtype).reshape(W1.shape), grads[1].to(b1.dtype), grads[2].to(gamma.dtype),
+                grads[3].to(beta.dtype), gW2.to(W2.dtype).reshape(W2.shape), gb2.to(W2.dtype), None, None, None, None)
+
+
+def field_head_enabled():
+    """BH_FIELD_HEAD=fused routes the Zeng backbone's last stage through K6; anything else keeps the ATen modules
+    (the default until the kernel's GPU parity tests have run on a B200 -- DESIGN.md section 9)"""
+    return os.environ.get('BH_FIELD_HEAD', 'aten') == 'fused'
+
+
+def field_head_supported(stage, x):
+    """stage = nn.Sequential(Conv2d 1x1, BatchNorm2d, ReLU, Conv2d 1x1 -> 2): is this the geometry K6 is compiled for?"""
+    if len(stage) != 4 or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+        return False
+    c1, bn, act, c2 = stage[0], stage[1], stage[2], stage[3]
+    ok = (isinstance(c1, torch.nn.Conv2d) and isinstance(c2, torch.nn.Conv2d) and isinstance(bn, torch.nn.BatchNorm2d)
+          and isinstance(act, torch.nn.ReLU) and c1.kernel_size == (1, 1) and c2.kernel_size == (1, 1)
+          and c1.stride == (1, 1) and c2.stride == (1, 1) and c1.bias is not None and c2.bias is not None
+          and c2.out_channels == 2 and bn.affine and bn.momentum is not None
+          and (bn.training or bn.running_mean is not None))
+    return bool(ok and cabi.lib().bh_fieldhead_supported(c1.in_channels, c1.out_channels))
+
+
+def field_head(stage, x):
+    """the four modules of ``stage`` applied to x [B,16,H,W] -> field [B,2,H,W] (planar), same parameters, same
+    running-statistics update as nn.BatchNorm2d, no [B,128,H,W] tensor"""
+    c1, bn, c2 = stage[0], stage[1], stage[3]
+    x = x.contiguous(memory_format=torch.channels_last)
+    training = bn.training or bn.running_mean is None
+    out, mean_y, var_y = _FieldHead.apply(x, c1.weight, c1.bias, bn.weight, bn.bias, c2.weight, c2.bias, bn.running_mean,
+                                          bn.running_var, training, float(bn.eps))
+    if bn.training and bn.track_running_stats and bn.running_mean is not None:
+        n = x.shape[0] * x.shape[2] * x.shape[3]
+        with torch.no_grad():       # nn.BatchNorm2d's update: biased variance normalises, unbiased variance is tracked
+            bn.num_batches_tracked.add_(1)
+            m = float(bn.momentum)
+            bn.running_mean.mul_(1 - m).add_(mean_y.to(bn.running_mean.dtype), alpha=m)
+            bn.running_var.mul_(1 - m).add_((var_y * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=m)
+    return out

@@ -156,6 +156,35 @@ int bh_pairgen_apply(const uint8_t* images, const int32_t* index, const double* 
                      bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K6  perspective-field head of the Zeng backbone (per-pixel 16 -> 128 -> 2 network with folded BatchNorm)
+ *
+ * replaces: src/backbones/Rethinking.py:144-147,293  layer8 = Conv2d(16,128,1) -> BatchNorm2d(128) -> ReLU ->
+ *           Conv2d(128,2,1): ~21 ATen/cuDNN passes over a [B,128,P,P] tensor per backbone pass.
+ *
+ * x [n_pix, cin] is the channels-last input (n_pix = B*HW pixels, cin = 16); the field `out` and its gradient `gOut`
+ * are planar [B,2,HW] (what K4 reads).  W1 [hid,cin], b1 [hid] are the FOLDED first layer (BatchNorm's batch or
+ * running statistics applied by the caller: bihome_b200/functional.py), W2 [2,hid], b2 [2].
+ *   bh_fieldhead_supported   1 for the compiled geometry (cin = 16, hid = 128), else 0 -> the caller keeps ATen.
+ *   bh_fieldhead_grid        CTAs the moments (what = 0) / backward (what = 1) launch uses == rows of `partials`.
+ *   bh_fieldhead_moments     partials [grid, cin + cin(cin+1)/2] double: per-CTA sums of x_i, then of x_i x_k for
+ *                            i <= k (row-major upper triangle); the caller adds the rows (fixed order).
+ *   bh_fieldhead_fwd         out = W2 relu(W1 x + b1) + b2.
+ *   bh_fieldhead_bwd         gx [n_pix, cin] = d/dx (overwritten); partials [grid, hid*cin + hid + 2*hid + 2] float:
+ *                            per-CTA { gW1 | gb1 | gW2 | gb2 }, the caller adds the rows.
+ *   bh_fieldhead_affine      gx (+)= a + M x per pixel, a [cin], M [cin,cin]: the adjoint of the moments (how the
+ *                            batch statistics feed back into the input); accumulate = 0 overwrites gx.
+ * ------------------------------------------------------------------------------------------- */
+int bh_fieldhead_supported(int cin, int hid);
+int bh_fieldhead_grid(int what, long long n_pix);
+int bh_fieldhead_moments(const float* x, double* partials, long long n_pix, int cin, bh_stream_t stream);
+int bh_fieldhead_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* out,
+                     int B, int HW, int cin, int hid, bh_stream_t stream);
+int bh_fieldhead_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* gOut, float* gx,
+                     float* partials, int B, int HW, int cin, int hid, bh_stream_t stream);
+int bh_fieldhead_affine(const float* x, const float* a, const float* M, float* gx, long long n_pix, int cin,
+                        int accumulate, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MACE: mean over B*4 corners of ||delta_gt - delta_hat||_2  (train.py:401-404, eval.py:133-134)
  * out: 1 float (overwritten).
  * ------------------------------------------------------------------------------------------- */

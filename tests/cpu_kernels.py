@@ -52,9 +52,44 @@ def mace(delta_gt, delta_hat):
     return (delta_gt.reshape(-1, 2) - delta_hat.reshape(-1, 2)).norm(dim=-1).mean()
 
 
+# ---- K6 (field head): the four device entry points as plain torch ops on [N, C] views ---------------------------------
+def _rows(x):
+    return x.permute(0, 2, 3, 1).reshape(-1, x.shape[1])
+
+
+def fh_moments(x):
+    X = _rows(x).double()
+    return X.sum(0), X.t() @ X
+
+
+def fh_fwd(x, W1, b1, W2, b2):
+    B, C, H, W = x.shape
+    out = torch.relu(_rows(x) @ W1.t() + b1) @ W2.t() + b2
+    return out.reshape(B, H, W, 2).permute(0, 3, 1, 2).contiguous()
+
+
+def fh_bwd(x, W1, b1, W2, g_out):
+    B, C, H, W = x.shape
+    X = _rows(x)
+    pre = X @ W1.t() + b1
+    h = torch.relu(pre)
+    G = g_out.permute(0, 2, 3, 1).reshape(-1, 2)
+    gh = (G @ W2) * (pre > 0).to(X.dtype)
+    gx = torch.empty_like(x)
+    gx.copy_((gh @ W1).reshape(B, H, W, C).permute(0, 3, 1, 2))
+    return gx, gh.t() @ X, gh.sum(0), G.t() @ h, G.sum(0)
+
+
+def fh_affine(x, a, M, gx):
+    B, C, H, W = x.shape
+    gx.add_((a + _rows(x) @ M.t()).reshape(B, H, W, C).permute(0, 3, 1, 2))
+    return gx
+
+
 def install(monkeypatch):
     import bihome_b200.functional as F
     for name, fn in (('dlt4', dlt4), ('warp', warp), ('coverage_mask', coverage_mask), ('bihome_loss', bihome_loss),
-                     ('dltn_field', dltn_field), ('mace', mace)):
+                     ('dltn_field', dltn_field), ('mace', mace), ('_fh_moments', fh_moments), ('_fh_fwd', fh_fwd),
+                     ('_fh_bwd', fh_bwd), ('_fh_affine', fh_affine)):
         monkeypatch.setattr(F, name, fn)
     return F

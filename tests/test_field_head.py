@@ -1,0 +1,132 @@
+"""K6 -- the Zeng backbone's last stage (Conv2d(16,128,1) -> BatchNorm2d -> ReLU -> Conv2d(128,2,1), reference
+src/backbones/Rethinking.py:144-147) computed per pixel with BatchNorm's batch statistics derived from the moments of
+the 16-channel input.
+
+CPU part: the host algebra of ``functional._FieldHead`` (statistics from moments, fold, their adjoints, running-statistics
+update) against the four ATen modules in float64, with the device entry points replaced by torch ops
+(tests/cpu_kernels.py).  GPU part: every device entry point against those same torch ops evaluated in float64 on the
+device, and the whole stage / the whole backbone against the ATen modules.  The kernels were written after the last
+GPU minutes of round 1 were spent: they compile for sm_100a but have not run on hardware yet, the backbone uses them
+only with BH_FIELD_HEAD=fused, and the GPU tests are opt-in (BH_TEST_UNVERIFIED=1) until their first run on a B200.
+"""
+import copy
+import os
+
+import pytest
+import torch
+
+import cpu_kernels
+from conftest import rel_l2
+
+unverified = pytest.mark.skipif(os.environ.get('BH_TEST_UNVERIFIED') != '1',
+                                reason='K6 has not run on hardware yet: opt in with BH_TEST_UNVERIFIED=1')
+
+
+def make_stage(dtype, device='cpu', seed=0):
+    torch.manual_seed(seed)
+    nn = torch.nn
+    stage = nn.Sequential(nn.Conv2d(16, 128, 1), nn.BatchNorm2d(128), nn.ReLU(), nn.Conv2d(128, 2, 1))
+    with torch.no_grad():
+        stage[1].weight.uniform_(0.5, 1.5)
+        stage[1].bias.normal_()
+    return stage.to(dtype).to(device)
+
+
+def compare_stage(F, stage, dtype, device, shape, tol, modes=('train', 'train', 'eval')):
+    ref = copy.deepcopy(stage)
+    gen = torch.Generator().manual_seed(3)
+    for mode in modes:
+        getattr(stage, mode)()
+        getattr(ref, mode)()
+        x = torch.relu(torch.randn(*shape, generator=gen) + 0.3).to(dtype).to(device).contiguous(memory_format=torch.channels_last)
+        g = torch.randn(shape[0], 2, shape[2], shape[3], generator=gen).to(dtype).to(device)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        oa, ob = F.field_head(stage, xa), ref(xb)
+        assert oa.shape == ob.shape and oa.is_contiguous()
+        assert rel_l2(oa.detach().cpu().numpy(), ob.detach().cpu().numpy()) < tol, mode
+        (oa * g).sum().backward()
+        (ob * g).sum().backward()
+        assert rel_l2(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) < 10 * tol, mode
+        scale = max(float(q.grad.abs().max()) for q in ref.parameters())
+        for (name, p), (_, q) in zip(stage.named_parameters(), ref.named_parameters()):
+            # conv1's bias is removed by a batch-statistics BatchNorm: its gradient is exactly zero, compare absolutely
+            err = float((p.grad - q.grad).abs().max()) / max(float(q.grad.abs().max()), 1e-3 * scale)
+            assert err < 30 * tol, (mode, name, err)
+            p.grad = q.grad = None
+        for (name, p), (_, q) in zip(stage.named_buffers(), ref.named_buffers()):
+            assert float((p.double() - q.double()).abs().max()) < 10 * tol, (mode, name)
+
+
+def test_host_algebra_matches_the_aten_modules(monkeypatch):
+    F = cpu_kernels.install(monkeypatch)
+    compare_stage(F, make_stage(torch.float64), torch.float64, 'cpu', (3, 16, 12, 10), 1e-12)
+
+
+def test_backbone_switch_is_opt_in(monkeypatch):
+    import bihome_b200.functional as F
+    monkeypatch.delenv('BH_FIELD_HEAD', raising=False)
+    assert not F.field_head_enabled()
+    monkeypatch.setenv('BH_FIELD_HEAD', 'fused')
+    assert F.field_head_enabled()
+    assert not F.field_head_supported(make_stage(torch.float32), torch.zeros(1, 16, 4, 4))      # CPU tensor: ATen modules
+
+
+# ------------------------------------------------------------------------------------------------ GPU (opt-in)
+@pytest.mark.gpu
+@unverified
+@pytest.mark.parametrize('B,H,W', [(1, 4, 8), (3, 9, 7), (2, 128, 128), (5, 33, 65)])
+def test_device_entry_points_vs_float64(B, H, W):
+    import bihome_b200.functional as F
+    gen = torch.Generator().manual_seed(B * 100 + H)
+    x = torch.relu(torch.randn(B, 16, H, W, generator=gen) + 0.3).cuda().contiguous(memory_format=torch.channels_last)
+    W1 = (torch.randn(128, 16, generator=gen) * 0.3).cuda()
+    b1 = torch.randn(128, generator=gen).cuda()
+    W2 = (torch.randn(2, 128, generator=gen) * 0.2).cuda()
+    b2 = torch.randn(2, generator=gen).cuda()
+    g = torch.randn(B, 2, H, W, generator=gen).cuda()
+    d = lambda t: t.double()
+    s1, s2 = F._fh_moments(x)
+    r1, r2 = cpu_kernels.fh_moments(x)
+    assert rel_l2(s1.cpu().numpy(), r1.cpu().numpy()) < 1e-6 and rel_l2(s2.cpu().numpy(), r2.cpu().numpy()) < 1e-6
+    out = F._fh_fwd(x, W1, b1, W2, b2)
+    ref = cpu_kernels.fh_fwd(d(x), d(W1), d(b1), d(W2), d(b2))
+    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    got = F._fh_bwd(x, W1, b1, W2, g)
+    want = cpu_kernels.fh_bwd(d(x), d(W1), d(b1), d(W2), d(g))
+    for a, b, name in zip(got, want, ('gx', 'gW1', 'gb1', 'gW2', 'gb2')):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, name
+    a, M = torch.randn(16, generator=gen).cuda(), torch.randn(16, 16, generator=gen).cuda()
+    gx = got[0].clone()
+    F._fh_affine(x, a, M, gx)
+    want_gx = cpu_kernels.fh_affine(d(x), d(a), d(M), d(got[0]).clone())
+    assert rel_l2(gx.cpu().numpy(), want_gx.cpu().numpy()) < 1e-5
+    again = F._fh_bwd(x, W1, b1, W2, g)
+    assert all(torch.equal(p, q) for p, q in zip(got, again))           # fixed-order partial sums: bit reproducible
+
+
+@pytest.mark.gpu
+@unverified
+def test_stage_and_backbone_vs_aten(monkeypatch):
+    import bihome_b200.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    compare_stage(F, make_stage(torch.float32, 'cuda'), torch.float32, 'cuda', (4, 16, 64, 64), 2e-5)
+    from bihome_b200.backbones import Rethinking
+    kw = dict(IMAGE_SIZE=128, PATCH_KEYS=['patch_1', 'patch_2'], TARGET_KEYS=['pf_hat_12', 'pf_hat_21'], RESNET_BLOCK='ResNet34',
+              PRETRAINED_RESNET=False, VARIANT='DoubleLine')
+    torch.manual_seed(1)
+    net = Rethinking.Model(**kw).cuda().to(memory_format=torch.channels_last).train()
+    twin = copy.deepcopy(net)
+    p1, p2 = torch.rand(4, 1, 128, 128).cuda(), torch.rand(4, 1, 128, 128).cuda()
+    g = torch.randn(4, 2, 128, 128).cuda()
+    res = []
+    for model, mode in ((net, 'fused'), (twin, 'aten')):
+        monkeypatch.setenv('BH_FIELD_HEAD', mode)
+        out = model({'patch_1': p1, 'patch_2': p2})
+        loss = (out['pf_hat_12'] * g).sum() + (out['pf_hat_21'] * g.flip(0)).sum()
+        grads = torch.autograd.grad(loss, [p for p in model.parameters()], allow_unused=True)
+        res.append((out['pf_hat_12'].detach(), grads))
+    assert rel_l2(res[0][0].cpu().numpy(), res[1][0].cpu().numpy()) < 1e-4
+    num = sum(float(((a - b).double() ** 2).sum()) for a, b in zip(*[r[1] for r in res]) if a is not None)
+    den = sum(float((b.double() ** 2).sum()) for b in res[1][1] if b is not None)
+    assert (num / den) ** 0.5 < 1e-3

@@ -1,5 +1,6 @@
 # usage (through gpurun): bash tools/gpu_round.sh <tag> [stages]     outputs under gpurun_out/
-# stages: any of t(ests) b(ench) r(eference arm) m(icrobench) l(aunch list) n(cu full) s(moke); default "tsbmln"
+# stages: any of t(ests) b(ench) r(eference arm) m(icrobench) l(aunch list) n(cu full) s(moke) u(nverified: the opt-in
+# K6 tests and a bench line with the fused field head); default "tsbmln"
 # Every stage runs under its own `timeout` so a hung kernel cannot hold the box.
 TAG=${1:-r01}
 ST=${2:-tsbmln}
@@ -9,6 +10,12 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 if has t; then
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
   tail -5 gpurun_out/pytest_$TAG.log
+fi
+if has u; then
+  BH_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_field_head.py -m gpu -q > gpurun_out/pytest_unverified_$TAG.log 2>&1; echo "unverified rc=$?"
+  tail -5 gpurun_out/pytest_unverified_$TAG.log
+  timeout 600 python bench.py --field-head fused --no-cpu-baseline > gpurun_out/bench_fused_$TAG.json 2> gpurun_out/bench_fused_$TAG.err; echo "bench fused rc=$?"
+  tail -c 1500 gpurun_out/bench_fused_$TAG.json
 fi
 if has s; then
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_$TAG.log
