@@ -18,7 +18,11 @@
 //   affine_acc_kernel   gx += a + M x : the moments' adjoint (how the batch statistics feed back into the input)
 // The fold itself and its adjoint are a few 128x16 operations on the host side (bihome_b200/functional.py, torch ops).
 // x is channels-last ([N,16] pixel-major); the field and its gradient are planar [B,2,P,P] -- what K4 (dltn.cu) reads.
+#ifdef BH_HOST_EMULATION   // tests/emu/fieldhead_emu.cpp: the kernels below compiled for the host, CTA threads as pthreads
+#include "cuda_emu.h"
+#else
 #include "bh_common.cuh"
+#endif
 
 namespace bh {
 
@@ -303,13 +307,16 @@ __global__ void __launch_bounds__(256) affine_acc_kernel(const float* __restrict
     }
 }
 
+#ifndef BH_HOST_EMULATION
 inline int fh_grid(long long n_items, int per_sm) {
     const long long cap = static_cast<long long>(kNumSMs) * per_sm;
     return static_cast<int>(n_items < 1 ? 1 : (n_items < cap ? n_items : cap));
 }
 
+#endif
 }  // namespace bh
 
+#ifndef BH_HOST_EMULATION
 // Only the shipped geometry is compiled: 16 input channels, 128 hidden units, 2 outputs (Rethinking.py:145-147, ResNet34
 // blocks).  Other widths (the ResNet50 variant: 64 -> 512 -> 2) get BH_E_UNSUPPORTED and stay on the ATen modules.
 extern "C" int bh_fieldhead_supported(int cin, int hid) { return cin == 16 && hid == 128; }
@@ -368,3 +375,4 @@ extern "C" int bh_fieldhead_affine(const float* x, const float* a, const float* 
                                                                                                                accumulate);
     return launch_status();
 }
+#endif  // BH_HOST_EMULATION
