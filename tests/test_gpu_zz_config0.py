@@ -4,7 +4,6 @@ the CPU oracle model (oracle/ref_train.py, float64) with the same weights on the
 the gradient of every learnable parameter."""
 import os
 
-import numpy as np
 import pytest
 import torch
 

@@ -2,7 +2,6 @@
 corners of the sweep, by the same two means as tests/test_gpu_fullsize.py -- the float64 oracle on a few samples of the
 full-size launch, and size-independent properties (identity and integer translation exact, linearity, agreement of
 the channels-last and the planar kernels on the same data, run-to-run bit reproducibility)."""
-import numpy as np
 import pytest
 import torch
 
