@@ -90,7 +90,28 @@ class Model(nn.Module):
         # through ATen; K6 computes it per pixel from the 16-channel input (opt-in, see functional.field_head_enabled)
         if F.field_head_enabled() and F.field_head_supported(self.layer8, x):
             return F.field_head(self.layer8, x)
-        return self.layer8(x)
+        return self._layer8_aten(x)
+
+    def _layer8_aten(self, x):
+        """layer8 through the ATen modules.  In training its first convolution runs WITHOUT its bias: a per-channel
+        constant in front of a batch-statistics BatchNorm cancels exactly (output and every gradient unchanged, the
+        bias' own gradient is exactly zero), while adding it costs a broadcast pass over the [B,128,P,P] tensor
+        (2.1 GB read + written at B = 256: PyTorch adds cuDNN convolution biases in a separate strided kernel) and
+        a 2.1 GB reduction for its gradient.  Only BatchNorm's running mean sees the bias; it is added there."""
+        conv, bn, act, head = self.layer8
+        if not (bn.training and conv.bias is not None and isinstance(bn, nn.BatchNorm2d) and bn.momentum is not None
+                and 0 < bn.momentum < 1):
+            return self.layer8(x)
+        # keep the bias in the graph (DDP / optimizers see a used parameter) with its exact zero gradient
+        weight = conv.weight * (1 + 0 * conv.bias.sum())
+        y = nn.functional.conv2d(x, weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if bn.track_running_stats and bn.running_mean is not None:
+            # running_mean <- (1 - m) running_mean + m (mean(y) + bias): shift it before the module's own update.  The
+            # buffer is among the tensors every BatchNorm call saves for backward (unused there in training), so the
+            # shift goes through .data, like the op's own in-place update it does not advance the version counter.
+            m = float(bn.momentum)
+            bn.running_mean.data.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=m / (1 - m))
+        return head(act(bn(y)))
 
     def forward(self, data):
         e1, e2 = self.patch_keys

@@ -62,6 +62,44 @@ def test_host_algebra_matches_the_aten_modules(monkeypatch):
     compare_stage(F, make_stage(torch.float64), torch.float64, 'cpu', (3, 16, 12, 10), 1e-12)
 
 
+@pytest.mark.parametrize('dtype,tol,gtol', [(torch.float64, 1e-11, 1e-11), (torch.float32, 2e-5, 1e-2)])
+def test_aten_path_drops_the_cancelled_bias_exactly(dtype, tol, gtol):
+    """default path: in training layer8's first convolution runs without its bias (a constant in front of a batch-
+    statistics BatchNorm cancels) -- outputs, gradients and running statistics equal the plain nn.Sequential, the
+    bias' gradient is exactly zero instead of round-off noise, eval mode still applies the bias"""
+    from bihome_b200.backbones import Rethinking
+    kw = dict(IMAGE_SIZE=128, PATCH_KEYS=['patch_1', 'patch_2'], TARGET_KEYS=['pf_hat_12', 'pf_hat_21'], RESNET_BLOCK='ResNet34',
+              PRETRAINED_RESNET=False, VARIANT='OneLine')
+    torch.manual_seed(0)
+    net = Rethinking.Model(**kw).to(dtype).train()
+    with torch.no_grad():
+        net.layer8[0].bias.normal_()
+    ref = copy.deepcopy(net)
+    gen = torch.Generator().manual_seed(2)
+    for _ in range(2):
+        x = torch.rand(2, 16, 32, 32, generator=gen).to(dtype)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        a, b = net._layer8_aten(xa), ref.layer8(xb)
+        g = torch.randn(a.shape, generator=gen).to(dtype)
+        (a * g).sum().backward()
+        (b * g).sum().backward()
+        assert rel_l2(a.detach().numpy(), b.detach().numpy()) < tol
+        # float32: a pre-activation within round-off of zero may switch its ReLU between the two evaluations; one switch
+        # moves the gradient of one pixel by ~10 % (3e-3 of the whole map) -- the float64 case is the exactness check
+        assert rel_l2(xa.grad.numpy(), xb.grad.numpy()) < gtol
+        for (name, p), (_, q) in zip(net.layer8.named_parameters(), ref.layer8.named_parameters()):
+            if name == '0.bias':
+                assert float(p.grad.abs().max()) == 0.0
+            else:
+                assert rel_l2(p.grad.numpy(), q.grad.numpy()) < gtol, name
+            p.grad = q.grad = None
+        for (name, p), (_, q) in zip(net.layer8.named_buffers(), ref.layer8.named_buffers()):
+            assert float((p.double() - q.double()).abs().max()) < tol, name
+    net.eval()
+    ref.eval()
+    assert rel_l2(net._layer8_aten(x).detach().numpy(), ref.layer8(x).detach().numpy()) < tol
+
+
 def test_backbone_switch_is_opt_in(monkeypatch):
     import bihome_b200.functional as F
     monkeypatch.delenv('BH_FIELD_HEAD', raising=False)
