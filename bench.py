@@ -133,7 +133,7 @@ def run_reference(args):
 
 def run_ours(args):
     import torch.distributed as dist
-    from bihome_b200 import cabi, engine
+    from bihome_b200 import autotune, cabi, engine
     from bihome_b200 import functional as F
     from bihome_b200.data import gpu_pairs
 
@@ -261,12 +261,12 @@ def run_ours(args):
                                    'loss, ResNet-34 stem extractor), 128x128 patches, B=%d per GPU, fp32 (cuDNN TF32 convs = torch default), '
                                    'random-init weights, synthetic uint8 image pool (%d x 240x320) resident in HBM' % (B, args.pool),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world, 'channels_last': bool(args.channels_last),
-                       'field_head': 'fused (K6)' if F.field_head_enabled() else 'aten',
+                       'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten',
                        'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clk,
-            'kernels': kernels, 'final_loss': final_loss}
+            'kernels': kernels, 'final_loss': final_loss, 'field_head_self_test': autotune.last_verdict(dev)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -288,7 +288,7 @@ def main():
                     help='keep the conv stack in NCHW (default: channels-last, 2.5x faster cuDNN path on B200)')
     ap.add_argument('--field-head', default=None, choices=['aten', 'fused'],
                     help="Zeng backbone's last stage: 'aten' = the four torch modules (default), 'fused' = K6 (csrc/fieldhead.cu); "
-                         'unset = whatever BH_FIELD_HEAD says')
+                         "unset = BH_FIELD_HEAD, else the device's self-test decides (bihome_b200/autotune.py)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer phase (profiling runs)')
     ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')

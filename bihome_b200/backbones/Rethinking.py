@@ -87,8 +87,9 @@ class Model(nn.Module):
         for i in range(1, 8):
             x = getattr(self, 'layer%d' % i)(x)
         # layer8 (1x1 conv -> BatchNorm -> ReLU -> 1x1 conv at full resolution) is 21 passes over a [B,128,P,P] tensor
-        # through ATen; K6 computes it per pixel from the 16-channel input (opt-in, see functional.field_head_enabled)
-        if F.field_head_enabled() and F.field_head_supported(self.layer8, x):
+        # through ATen; K6 computes it per pixel from the 16-channel input when the device's self-test picked it
+        # (functional.field_head_enabled -> bihome_b200/autotune.py)
+        if x.is_cuda and F.field_head_supported(self.layer8, x) and F.field_head_enabled(x.device):
             return F.field_head(self.layer8, x)
         return self._layer8_aten(x)
 

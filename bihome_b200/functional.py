@@ -515,10 +515,16 @@ class _FieldHead(torch.autograd.Function):
                 grads[3].to(beta.dtype), gW2.to(W2.dtype).reshape(W2.shape), gb2.to(W2.dtype), None, None, None, None)
 
 
-def field_head_enabled():
-    """BH_FIELD_HEAD=fused routes the Zeng backbone's last stage through K6; anything else keeps the ATen modules
-    (the default until the kernel's GPU parity tests have run on a B200 -- DESIGN.md section 9)"""
-    return os.environ.get('BH_FIELD_HEAD', 'aten') == 'fused'
+def field_head_enabled(device=None):
+    """does the Zeng backbone's last stage run on K6 on this device?  BH_FIELD_HEAD=fused / aten force it; otherwise a
+    one-off self-test in a child process decides (bihome_b200/autotune.py: parity with the ATen modules, then speed)"""
+    forced = os.environ.get('BH_FIELD_HEAD', 'auto')
+    if forced in ('fused', 'aten'):
+        return forced == 'fused'
+    if device is None or torch.device(device).type != 'cuda':
+        return False
+    from . import autotune
+    return autotune.field_head_choice(torch.device(device)) == 'fused'
 
 
 def field_head_supported(stage, x):

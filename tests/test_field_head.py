@@ -6,8 +6,9 @@ CPU part: the host algebra of ``functional._FieldHead`` (statistics from moments
 update) against the four ATen modules in float64, with the device entry points replaced by torch ops
 (tests/cpu_kernels.py).  GPU part: every device entry point against those same torch ops evaluated in float64 on the
 device, and the whole stage / the whole backbone against the ATen modules.  The kernels were written after the last
-GPU minutes of round 1 were spent: they compile for sm_100a but have not run on hardware yet, the backbone uses them
-only with BH_FIELD_HEAD=fused, and the GPU tests are opt-in (BH_TEST_UNVERIFIED=1) until their first run on a B200.
+GPU minutes of round 1 were spent.  What pins them without a GPU: the host emulation below (the .cu file itself compiled
+for the host, checked against torch ops and under ThreadSanitizer).  On a GPU the backbone uses them only after the
+device's self-test passed (bihome_b200/autotune.py); the GPU tests here follow the same verdict.
 """
 import copy
 import os
@@ -18,8 +19,15 @@ import torch
 import cpu_kernels
 from conftest import rel_l2
 
-unverified = pytest.mark.skipif(os.environ.get('BH_TEST_UNVERIFIED') != '1',
-                                reason='K6 has not run on hardware yet: opt in with BH_TEST_UNVERIFIED=1')
+@pytest.fixture
+def k6_on_this_device():
+    """K6 runs on a device only after its self-test (bihome_b200/autotune.py, in a child process) passed there; the GPU
+    tests below follow that verdict, or BH_TEST_UNVERIFIED=1 forces them (first bring-up on hardware)"""
+    if os.environ.get('BH_TEST_UNVERIFIED') == '1':
+        return
+    import bihome_b200.functional as F
+    if not (torch.cuda.is_available() and F.field_head_enabled(torch.device('cuda', 0))):
+        pytest.skip("K6 did not pass this device's self-test (or BH_FIELD_HEAD=aten): the backbone uses the ATen modules")
 
 
 def make_stage(dtype, device='cpu', seed=0):
@@ -100,13 +108,44 @@ def test_aten_path_drops_the_cancelled_bias_exactly(dtype, tol, gtol):
     assert rel_l2(net._layer8_aten(x).detach().numpy(), ref.layer8(x).detach().numpy()) < tol
 
 
-def test_backbone_switch_is_opt_in(monkeypatch):
+def test_backbone_switch(monkeypatch, tmp_path):
+    """BH_FIELD_HEAD forces the choice; unset, a CUDA device's cached self-test verdict decides (parity AND speed)"""
+    import tempfile
+
     import bihome_b200.functional as F
-    monkeypatch.delenv('BH_FIELD_HEAD', raising=False)
-    assert not F.field_head_enabled()
+    from bihome_b200 import autotune
     monkeypatch.setenv('BH_FIELD_HEAD', 'fused')
     assert F.field_head_enabled()
+    monkeypatch.setenv('BH_FIELD_HEAD', 'aten')
+    assert not F.field_head_enabled(torch.device('cuda', 0))
+    monkeypatch.delenv('BH_FIELD_HEAD', raising=False)
+    assert not F.field_head_enabled() and not F.field_head_enabled(torch.device('cpu'))
     assert not F.field_head_supported(make_stage(torch.float32), torch.zeros(1, 16, 4, 4))      # CPU tensor: ATen modules
+    monkeypatch.setattr(tempfile, 'tempdir', str(tmp_path))
+    monkeypatch.setattr(torch.cuda, 'get_device_name', lambda i: 'emulated B200')
+    calls = []
+    for verdict, want in (({'ok': True, 'fused_ms': 1.0, 'aten_ms': 5.0}, True), ({'ok': True, 'fused_ms': 6.0, 'aten_ms': 5.0}, False),
+                          ({'ok': False, 'err': 'train gx mismatch'}, False)):
+        monkeypatch.setattr(autotune, '_choice', {})
+        monkeypatch.setattr(autotune, '_probe_in_child', lambda index, v=verdict: calls.append(index) or v)
+        for f in tmp_path.iterdir():
+            f.unlink()
+        assert F.field_head_enabled(torch.device('cuda', 1)) is want
+        assert F.field_head_enabled(torch.device('cuda', 1)) is want          # per-process cache
+        monkeypatch.setattr(autotune, '_choice', {})
+        assert F.field_head_enabled(torch.device('cuda', 1)) is want          # on-disk cache: no second self-test
+    assert calls == [1, 1, 1]
+
+
+def test_self_test_procedure_on_the_stand_in_kernels(monkeypatch):
+    """the child's parity + timing procedure itself, run on CPU with the device entry points replaced by torch ops"""
+    from bihome_b200 import autotune
+    cpu_kernels.install(monkeypatch)
+    verdict = autotune.compare_and_time(torch.device('cpu'), timing_batch=1)
+    assert verdict['ok'] and verdict['worst'] < 0.5 and verdict['fused_ms'] > 0 and verdict['aten_ms'] > 0, verdict
+    import bihome_b200.functional as F
+    monkeypatch.setattr(F, '_fh_fwd', lambda *a: cpu_kernels.fh_fwd(*a) * 1.01)               # a wrong kernel is caught
+    assert not autotune.compare_and_time(torch.device('cpu'), timing_batch=1)['ok']
 
 
 # ------------------------------------------------------------------------------------------------ host emulation
@@ -189,9 +228,8 @@ def test_no_data_race_under_thread_sanitizer():
 
 # ------------------------------------------------------------------------------------------------ GPU (opt-in)
 @pytest.mark.gpu
-@unverified
 @pytest.mark.parametrize('B,H,W', [(1, 4, 8), (3, 9, 7), (2, 128, 128), (5, 33, 65)])
-def test_device_entry_points_vs_float64(B, H, W):
+def test_device_entry_points_vs_float64(k6_on_this_device, B, H, W):
     import bihome_b200.functional as F
     gen = torch.Generator().manual_seed(B * 100 + H)
     x = torch.relu(torch.randn(B, 16, H, W, generator=gen) + 0.3).cuda().contiguous(memory_format=torch.channels_last)
@@ -221,8 +259,7 @@ def test_device_entry_points_vs_float64(B, H, W):
 
 
 @pytest.mark.gpu
-@unverified
-def test_stage_and_backbone_vs_aten(monkeypatch):
+def test_stage_and_backbone_vs_aten(k6_on_this_device, monkeypatch):
     import bihome_b200.functional as F
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False

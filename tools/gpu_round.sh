@@ -14,8 +14,11 @@ fi
 if has u; then
   BH_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_field_head.py -m gpu -q > gpurun_out/pytest_unverified_$TAG.log 2>&1; echo "unverified rc=$?"
   tail -5 gpurun_out/pytest_unverified_$TAG.log
-  timeout 600 python bench.py --field-head fused --no-cpu-baseline > gpurun_out/bench_fused_$TAG.json 2> gpurun_out/bench_fused_$TAG.err; echo "bench fused rc=$?"
-  tail -c 1500 gpurun_out/bench_fused_$TAG.json
+  timeout 120 python -m bihome_b200.autotune 0 > gpurun_out/fieldhead_selftest_$TAG.json 2>&1; cat gpurun_out/fieldhead_selftest_$TAG.json
+  for side in fused aten; do
+    timeout 600 python bench.py --field-head $side --no-cpu-baseline > gpurun_out/bench_${side}_$TAG.json 2> gpurun_out/bench_${side}_$TAG.err; echo "bench $side rc=$?"
+    tail -c 1200 gpurun_out/bench_${side}_$TAG.json
+  done
 fi
 if has s; then
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_$TAG.log
