@@ -148,6 +148,36 @@ def test_self_test_procedure_on_the_stand_in_kernels(monkeypatch):
     assert not autotune.compare_and_time(torch.device('cpu'), timing_batch=1)['ok']
 
 
+@pytest.mark.parametrize('name', ['zeng-bihome-lr-1e-3', 'zeng-orig-lr-1e-3'])
+def test_zeng_configs_with_the_fused_head_match_the_reference(monkeypatch, name):
+    """the whole shipped Zeng models with layer8 routed through functional.field_head (stand-in device ops): loss and
+    parameter gradients of the unmodified reference model for the same weights and batch (build container only)"""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip('reference tree not present')
+    import bihome_b200.functional as F
+    import test_configs_end_to_end as E
+    monkeypatch.setenv('BH_FIELD_HEAD', 'fused')
+    real = F.field_head_supported
+    calls = []
+
+    class OnDevice:                              # the geometry check minus "is on a CUDA device"
+        def __init__(self, t):
+            self.is_cuda, self.dtype, self._t = True, t.dtype, t
+
+        def dim(self):
+            return self._t.dim()
+
+    def supported(stage, x):
+        calls.append(1)
+        return real(stage, OnDevice(x))
+    monkeypatch.setattr(F, 'field_head_supported', supported)
+    monkeypatch.setattr(torch.Tensor, 'is_cuda', property(lambda self: True))
+    path = os.path.join(ref_import.REFERENCE_ROOT, 'config', 'pds-coco', name + '.yaml')
+    E.test_training_step_matches_reference(monkeypatch, path)
+    assert calls
+
+
 # ------------------------------------------------------------------------------------------------ host emulation
 EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu')
 
