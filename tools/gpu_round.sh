@@ -15,6 +15,7 @@ if has u; then
   BH_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_field_head.py -m gpu -q > gpurun_out/pytest_unverified_$TAG.log 2>&1; echo "unverified rc=$?"
   tail -5 gpurun_out/pytest_unverified_$TAG.log
   timeout 120 python -m bihome_b200.autotune 0 > gpurun_out/fieldhead_selftest_$TAG.json 2>&1; cat gpurun_out/fieldhead_selftest_$TAG.json
+  timeout 300 python tools/microbench.py --field-head > gpurun_out/microbench_fieldhead_$TAG.jsonl 2>&1; cat gpurun_out/microbench_fieldhead_$TAG.jsonl
   for side in fused aten; do
     timeout 600 python bench.py --field-head $side --no-cpu-baseline > gpurun_out/bench_${side}_$TAG.json 2> gpurun_out/bench_${side}_$TAG.err; echo "bench $side rc=$?"
     tail -c 1200 gpurun_out/bench_${side}_$TAG.json

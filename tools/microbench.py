@@ -144,6 +144,31 @@ def bench_small(B, P, t):
            (2 * 3 * (128 + 64) ** 2 + 2 * 4 * 128 * 128) * B)
 
 
+def bench_field_head(B, P, t):
+    """K6 (csrc/fieldhead.cu) entry points and the whole stage, fused against the four ATen modules, at [B,16,P,P]"""
+    from bihome_b200 import autotune
+    n = B * P * P
+    x = torch.relu(torch.randn(B, 16, P, P, device='cuda') + 0.3).contiguous(memory_format=torch.channels_last)
+    W1, b1 = torch.randn(128, 16, device='cuda') * 0.3, torch.randn(128, device='cuda')
+    W2, b2 = torch.randn(2, 128, device='cuda') * 0.2, torch.randn(2, device='cuda')
+    g = torch.randn(B, 2, P, P, device='cuda')
+    gx = torch.empty_like(x)
+    a, M = torch.randn(16, device='cuda'), torch.randn(16, 16, device='cuda')
+    shape = {'B': B, 'P': P}
+    report('fieldhead_moments', shape, t(lambda: F._fh_moments(x)), 64 * n)
+    report('fieldhead_fwd', shape, t(lambda: F._fh_fwd(x, W1, b1, W2, b2)), (64 + 8) * n)
+    report('fieldhead_bwd', shape, t(lambda: F._fh_bwd(x, W1, b1, W2, g)), (64 + 8 + 64) * n)
+    report('fieldhead_affine', shape, t(lambda: F._fh_affine(x, a, M, gx)), (64 + 64 + 64) * n)
+    fused, aten = autotune._stage(torch.device('cuda')), autotune._stage(torch.device('cuda'))
+
+    def step(fn):
+        xa = x.detach().requires_grad_(True)
+        (fn(xa) * g).sum().backward()
+    total = (64 + 64 + 8 + 64 + 8 + 64 + 192) * n      # moments + fwd + bwd + affine
+    report('field head fwd+bwd, K6', shape, t(lambda: step(lambda v: F.field_head(fused, v))), total)
+    report('field head fwd+bwd, ATen modules', shape, t(lambda: step(aten)), total)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--sweep', action='store_true')
@@ -152,6 +177,7 @@ def main():
     ap.add_argument('--warp-only', action='store_true', help='time only the 1-channel image warp (forward + backward)')
     ap.add_argument('--dirty', action='store_true', help='flush by memset only (leaves the L2 full of dirty lines: adds their write-back to every timing)')
     ap.add_argument('--loss-cl', action='store_true', help='time the fused loss for every cluster size (BH_LOSS_CL knob)')
+    ap.add_argument('--field-head', action='store_true', help='time K6 (the Zeng field head) against the ATen modules')
     a = ap.parse_args()
     torch.manual_seed(0)
     if a.once:
@@ -167,6 +193,10 @@ def main():
         torch.cuda.synchronize()
         return
     t = Timer(a.iters, dirty=a.dirty)
+    if a.field_head:
+        for B in (64, 256):
+            bench_field_head(B, 128, t)
+        return
     if a.loss_cl:
         for cl in (1, 2, 4, 8):
             os.environ['BH_LOSS_CL'] = str(cl)
