@@ -39,7 +39,7 @@ if has l; then
 fi
 if has n; then
   timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:"bihome_|warp_fwd|warp_bwd|mask_pooled|dlt4_|dltn_|pairgen_|mace_|fieldhead_|moments_|affine_acc" -c 64 -f \
+      -k regex:"bihome_|warp_fwd|warp_bwd|mask_pooled|dlt4_|dltn_|pairgen_|mace_|fieldhead_|moments_|affine_acc" -c 112 -f \
       -o gpurun_out/prof_kernels_$TAG python tools/microbench.py --once > gpurun_out/once_$TAG.log 2>&1; echo "ncu full rc=$?"
 fi
 ls -la gpurun_out
