@@ -30,7 +30,7 @@ constexpr int kFhThreads = 128;      // == hidden units of the shipped head: pha
 constexpr int kFhTile = 32;          // pixels per backward tile (lane = pixel in phase 1)
 constexpr int kFhPad = kFhTile + 1;  // row pitch of the [hidden][pixel] tiles: conflict-free in both phases
 constexpr int kMomTile = 128;        // pixels per moments tile
-constexpr int kMomThreads = 160;     // 136 pairs (i <= k) + 16 sums, rounded up to whole warps
+constexpr int kMomThreads = 288;     // 16 sums + 16 x 16 second moments = 272 statistics, rounded up to whole warps
 
 template <int CIN>
 __device__ __forceinline__ void load_pixel(const float* __restrict__ x, long long p, float (&v)[CIN]) {
@@ -43,24 +43,17 @@ __device__ __forceinline__ void load_pixel(const float* __restrict__ x, long lon
 }
 
 // ---- moments ------------------------------------------------------------------------------------------------------
-// partials[cta][0..CIN) = sum_p x_i ; partials[cta][CIN + pair(i,k)] = sum_p x_i x_k for i <= k (row-major upper triangle)
+// partials[cta][0..CIN) = sum_p x_i ; partials[cta][CIN + i*CIN + k] = sum_p x_i x_k (the full symmetric matrix: the
+// redundant half costs nothing in a kernel that waits for memory, and the host side needs no index juggling)
 template <int CIN>
 __global__ void __launch_bounds__(kMomThreads) moments_kernel(const float* __restrict__ x, double* __restrict__ partials,
                                                              long long n_pix) {
-    constexpr int kPairs = CIN * (CIN + 1) / 2;
+    constexpr int kStats = CIN + CIN * CIN;
+    static_assert(kStats <= kMomThreads, "one thread per statistic");
     __shared__ __align__(16) float sx[kMomTile * CIN];
     const int t = threadIdx.x;
-    // which statistic this thread owns
-    int i = 0, k = 0;
-    const bool is_sum = t < CIN;
-    const bool is_pair = t >= CIN && t < CIN + kPairs;
-    if (is_pair) {
-        int r = t - CIN;
-        while (r >= CIN - i) { r -= CIN - i; ++i; }
-        k = i + r;
-    } else if (is_sum) {
-        i = k = t;
-    }
+    const bool is_sum = t < CIN, active = t < kStats;
+    const int i = is_sum ? t : (t - CIN) / CIN, k = is_sum ? t : (t - CIN) % CIN;
     double acc = 0.0;
     const long long n_tiles = (n_pix + kMomTile - 1) / kMomTile;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -74,7 +67,7 @@ __global__ void __launch_bounds__(kMomThreads) moments_kernel(const float* __res
             reinterpret_cast<float4*>(sx)[q] = v;
         }
         __syncthreads();
-        if (is_sum || is_pair) {
+        if (active) {
             float s = 0.0f;
             if (is_sum) {
 #pragma unroll 8
@@ -86,7 +79,7 @@ __global__ void __launch_bounds__(kMomThreads) moments_kernel(const float* __res
             acc += static_cast<double>(s);
         }
     }
-    if (is_sum || is_pair) partials[static_cast<long long>(blockIdx.x) * (CIN + kPairs) + t] = acc;
+    if (active) partials[static_cast<long long>(blockIdx.x) * kStats + t] = acc;
 }
 
 // ---- forward ------------------------------------------------------------------------------------------------------
@@ -324,7 +317,7 @@ extern "C" int bh_fieldhead_supported(int cin, int hid) { return cin == 16 && hi
 extern "C" int bh_fieldhead_grid(int what, long long n_pix) {
     using namespace bh;
     if (n_pix <= 0) return 0;
-    if (what == 0) return fh_grid((n_pix + kMomTile - 1) / kMomTile, 8);   // moments
+    if (what == 0) return fh_grid((n_pix + kMomTile - 1) / kMomTile, 7);   // moments: 7 x 288 threads per SM
     return fh_grid((n_pix + kFhTile - 1) / kFhTile, 5);                    // backward: 37 KB of shared memory per CTA
 }
 

@@ -405,15 +405,11 @@ def _fh_moments(x):
     n = B * H * W
     lib = cabi.lib()
     grid = lib.bh_fieldhead_grid(0, n)
-    pairs = C * (C + 1) // 2
-    parts = torch.empty(grid, C + pairs, device=x.device, dtype=torch.float64)
+    parts = torch.empty(grid, C + C * C, device=x.device, dtype=torch.float64)
     with torch.cuda.device(x.device), _timed('bh_fieldhead_moments'):
         cabi.check(lib.bh_fieldhead_moments(_ptr(x), _ptr(parts), n, C, _stream()), 'bh_fieldhead_moments')
     s = parts.sum(0)
-    iu = torch.triu_indices(C, C, device=x.device)
-    upper = torch.zeros(C, C, device=x.device, dtype=torch.float64)
-    upper[iu[0], iu[1]] = s[C:]
-    return s[:C], upper + upper.triu(1).t()
+    return s[:C], s[C:].view(C, C)
 
 
 def _fh_fwd(x, W1, b1, W2, b2):

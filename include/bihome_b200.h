@@ -166,8 +166,8 @@ int bh_pairgen_apply(const uint8_t* images, const int32_t* index, const double* 
  * running statistics applied by the caller: bihome_b200/functional.py), W2 [2,hid], b2 [2].
  *   bh_fieldhead_supported   1 for the compiled geometry (cin = 16, hid = 128), else 0 -> the caller keeps ATen.
  *   bh_fieldhead_grid        CTAs the moments (what = 0) / backward (what = 1) launch uses == rows of `partials`.
- *   bh_fieldhead_moments     partials [grid, cin + cin(cin+1)/2] double: per-CTA sums of x_i, then of x_i x_k for
- *                            i <= k (row-major upper triangle); the caller adds the rows (fixed order).
+ *   bh_fieldhead_moments     partials [grid, cin + cin*cin] double: per-CTA sums of x_i, then of x_i x_k (the full
+ *                            symmetric matrix, row-major); the caller adds the rows (fixed order).
  *   bh_fieldhead_fwd         out = W2 relu(W1 x + b1) + b2.
  *   bh_fieldhead_bwd         gx [n_pix, cin] = d/dx (overwritten); partials [grid, hid*cin + hid + 2*hid + 2] float:
  *                            per-CTA { gW1 | gb1 | gW2 | gb2 }, the caller adds the rows.

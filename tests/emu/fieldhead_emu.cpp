@@ -31,7 +31,7 @@ int main() {
     const long long n = static_cast<long long>(B) * HW;
     std::vector<float> x(n * 16), W1(128 * 16), b1(128), W2(256), b2(2), out(n * 2), g(n * 2), gx(n * 16), a(16), M(256);
     std::vector<float> parts(grid * (128 * 16 + 3 * 128 + 2));
-    std::vector<double> mom(grid * (16 + 136));
+    std::vector<double> mom(grid * (16 + 256));
     auto fill = [](std::vector<float>& v) { for (auto& e : v) e = static_cast<float>(rand()) / RAND_MAX - 0.4f; };
     fill(x); fill(W1); fill(b1); fill(W2); fill(b2); fill(g); fill(a); fill(M);
     emu_moments(x.data(), mom.data(), n, grid);
