@@ -91,6 +91,7 @@ def cpu_oracle_run(steps, warmup, batch, threads):
     bcfg['PRETRAINED_RESNET'] = False
     torch.manual_seed(0)
     model = OracleModel(Rethinking.Model(**bcfg), cfg['MODEL']['HEAD'])
+    model.backbone.skip_cancelled_bias = False      # the reference's op sequence, literally
     model.train()
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=cfg['SOLVER']['LR'])
     g = torch.Generator().manual_seed(1)
