@@ -243,7 +243,10 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': LOSS_BYTES_PER_PAIR * B}
     kernels = {k: {'launches': len(v), 'avg_ms': sum(v) / len(v)} for k, v in sorted(kt.items())}
     # the other two bandwidth kernels of the path, same accounting (K2 270 336 B, K2b 270 408 B per pair)
-    for name, per_pair in (('bh_warp_fwd', 270336), ('bh_warp_bwd', 270408), ('bh_bihome_fwd_bwd', LOSS_BYTES_PER_PAIR)):
+    px = 128 * 128          # K6 works per pixel of one backbone pass: 64 B in, 8 B field, 64 B input gradient
+    for name, per_pair in (('bh_warp_fwd', 270336), ('bh_warp_bwd', 270408), ('bh_bihome_fwd_bwd', LOSS_BYTES_PER_PAIR),
+                           ('bh_fieldhead_moments', 64 * px), ('bh_fieldhead_fwd', 72 * px), ('bh_fieldhead_bwd', 136 * px),
+                           ('bh_fieldhead_affine', 192 * px)):
         if name in kernels and kernels[name]['avg_ms'] > 0:
             gbs = per_pair * B / (kernels[name]['avg_ms'] * 1e-3) / 1e9
             kernels[name].update({'algorithmic_GBps': gbs, 'frac_of_hbm_peak': gbs / peak})
