@@ -106,7 +106,7 @@ def perspective_field_target(corners, delta, patch_size):
     rows_u = torch.stack([x, y, one, zero, zero, zero, -x * u, -y * u], dim=-1)
     rows_v = torch.stack([zero, zero, zero, x, y, one, -x * v, -y * v], dim=-1)
     A = torch.cat([rows_u, rows_v], dim=1)                                   # [B,8,8]
-    h = torch.linalg.solve(A, torch.cat([u, v], dim=1).unsqueeze(-1)).squeeze(-1)
+    h = torch.linalg.solve_ex(A, torch.cat([u, v], dim=1).unsqueeze(-1))[0].squeeze(-1)     # _ex: no host sync
     P = int(patch_size)
     r = torch.arange(P, device=src.device, dtype=torch.float64)
     px = (src[:, 0, 0].view(B, 1, 1) + r.view(1, 1, P)).expand(B, P, P)
