@@ -4,11 +4,10 @@ the 16-channel input.
 
 CPU part: the host algebra of ``functional._FieldHead`` (statistics from moments, fold, their adjoints, running-statistics
 update) against the four ATen modules in float64, with the device entry points replaced by torch ops
-(tests/cpu_kernels.py).  GPU part: every device entry point against those same torch ops evaluated in float64 on the
-device, and the whole stage / the whole backbone against the ATen modules.  The kernels were written after the last
-GPU minutes of round 1 were spent.  What pins them without a GPU: the host emulation below (the .cu file itself compiled
-for the host, checked against torch ops and under ThreadSanitizer).  On a GPU the backbone uses them only after the
-device's self-test passed (bihome_b200/autotune.py); the GPU tests here follow the same verdict.
+(tests/cpu_kernels.py); the kernels themselves on a host emulator (the .cu file compiled for the host, checked against
+torch ops and under ThreadSanitizer); the per-device choice between K6 and the ATen modules (bihome_b200/autotune.py).
+The kernels were written after the last GPU minutes of round 1 were spent: this file is what pins them without a GPU,
+tests/test_gpu_zzz_field_head.py is the device side.
 """
 import copy
 import os
@@ -18,17 +17,6 @@ import torch
 
 import cpu_kernels
 from conftest import rel_l2
-
-@pytest.fixture
-def k6_on_this_device():
-    """K6 runs on a device only after its self-test (bihome_b200/autotune.py, in a child process) passed there; the GPU
-    tests below follow that verdict, or BH_TEST_UNVERIFIED=1 forces them (first bring-up on hardware)"""
-    if os.environ.get('BH_TEST_UNVERIFIED') == '1':
-        return
-    import bihome_b200.functional as F
-    if not (torch.cuda.is_available() and F.field_head_enabled(torch.device('cuda', 0))):
-        pytest.skip("K6 did not pass this device's self-test (or BH_FIELD_HEAD=aten): the backbone uses the ATen modules")
-
 
 def make_stage(dtype, device='cpu', seed=0):
     torch.manual_seed(seed)
@@ -253,62 +241,3 @@ def test_no_data_race_under_thread_sanitizer():
     if 'FATAL: ThreadSanitizer' in r.stderr and 'data race' not in r.stderr:
         pytest.skip('ThreadSanitizer cannot run here: ' + r.stderr.strip().splitlines()[0])
     assert r.returncode == 0 and 'data race' not in r.stderr and r.stdout.startswith('ok'), r.stderr[-2000:]
-
-
-# ------------------------------------------------------------------------------------------------ GPU (opt-in)
-@pytest.mark.gpu
-@pytest.mark.parametrize('B,H,W', [(1, 4, 8), (3, 9, 7), (2, 128, 128), (5, 33, 65)])
-def test_device_entry_points_vs_float64(k6_on_this_device, B, H, W):
-    import bihome_b200.functional as F
-    gen = torch.Generator().manual_seed(B * 100 + H)
-    x = torch.relu(torch.randn(B, 16, H, W, generator=gen) + 0.3).cuda().contiguous(memory_format=torch.channels_last)
-    W1 = (torch.randn(128, 16, generator=gen) * 0.3).cuda()
-    b1 = torch.randn(128, generator=gen).cuda()
-    W2 = (torch.randn(2, 128, generator=gen) * 0.2).cuda()
-    b2 = torch.randn(2, generator=gen).cuda()
-    g = torch.randn(B, 2, H, W, generator=gen).cuda()
-    d = lambda t: t.double()
-    s1, s2 = F._fh_moments(x)
-    r1, r2 = cpu_kernels.fh_moments(x)
-    assert rel_l2(s1.cpu().numpy(), r1.cpu().numpy()) < 1e-6 and rel_l2(s2.cpu().numpy(), r2.cpu().numpy()) < 1e-6
-    out = F._fh_fwd(x, W1, b1, W2, b2)
-    ref = cpu_kernels.fh_fwd(d(x), d(W1), d(b1), d(W2), d(b2))
-    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
-    got = F._fh_bwd(x, W1, b1, W2, g)
-    want = cpu_kernels.fh_bwd(d(x), d(W1), d(b1), d(W2), d(g))
-    for a, b, name in zip(got, want, ('gx', 'gW1', 'gb1', 'gW2', 'gb2')):
-        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, name
-    a, M = torch.randn(16, generator=gen).cuda(), torch.randn(16, 16, generator=gen).cuda()
-    gx = got[0].clone()
-    F._fh_affine(x, a, M, gx)
-    want_gx = cpu_kernels.fh_affine(d(x), d(a), d(M), d(got[0]).clone())
-    assert rel_l2(gx.cpu().numpy(), want_gx.cpu().numpy()) < 1e-5
-    again = F._fh_bwd(x, W1, b1, W2, g)
-    assert all(torch.equal(p, q) for p, q in zip(got, again))           # fixed-order partial sums: bit reproducible
-
-
-@pytest.mark.gpu
-def test_stage_and_backbone_vs_aten(k6_on_this_device, monkeypatch):
-    import bihome_b200.functional as F
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    compare_stage(F, make_stage(torch.float32, 'cuda'), torch.float32, 'cuda', (4, 16, 64, 64), 2e-5)
-    from bihome_b200.backbones import Rethinking
-    kw = dict(IMAGE_SIZE=128, PATCH_KEYS=['patch_1', 'patch_2'], TARGET_KEYS=['pf_hat_12', 'pf_hat_21'], RESNET_BLOCK='ResNet34',
-              PRETRAINED_RESNET=False, VARIANT='DoubleLine')
-    torch.manual_seed(1)
-    net = Rethinking.Model(**kw).cuda().to(memory_format=torch.channels_last).train()
-    twin = copy.deepcopy(net)
-    p1, p2 = torch.rand(4, 1, 128, 128).cuda(), torch.rand(4, 1, 128, 128).cuda()
-    g = torch.randn(4, 2, 128, 128).cuda()
-    res = []
-    for model, mode in ((net, 'fused'), (twin, 'aten')):
-        monkeypatch.setenv('BH_FIELD_HEAD', mode)
-        out = model({'patch_1': p1, 'patch_2': p2})
-        loss = (out['pf_hat_12'] * g).sum() + (out['pf_hat_21'] * g.flip(0)).sum()
-        grads = torch.autograd.grad(loss, [p for p in model.parameters()], allow_unused=True)
-        res.append((out['pf_hat_12'].detach(), grads))
-    assert rel_l2(res[0][0].cpu().numpy(), res[1][0].cpu().numpy()) < 1e-4
-    num = sum(float(((a - b).double() ** 2).sum()) for a, b in zip(*[r[1] for r in res]) if a is not None)
-    den = sum(float((b.double() ** 2).sum()) for b in res[1][1] if b is not None)
-    assert (num / den) ** 0.5 < 1e-3

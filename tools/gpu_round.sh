@@ -12,7 +12,7 @@ if has t; then
   tail -5 gpurun_out/pytest_$TAG.log
 fi
 if has u; then
-  BH_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_field_head.py -m gpu -q > gpurun_out/pytest_unverified_$TAG.log 2>&1; echo "unverified rc=$?"
+  BH_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_zzz_field_head.py -q > gpurun_out/pytest_unverified_$TAG.log 2>&1; echo "unverified rc=$?"
   tail -5 gpurun_out/pytest_unverified_$TAG.log
   timeout 120 python -m bihome_b200.autotune 0 > gpurun_out/fieldhead_selftest_$TAG.json 2>&1; cat gpurun_out/fieldhead_selftest_$TAG.json
   timeout 300 python tools/microbench.py --field-head > gpurun_out/microbench_fieldhead_$TAG.jsonl 2>&1; cat gpurun_out/microbench_fieldhead_$TAG.jsonl
