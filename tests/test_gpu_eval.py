@@ -7,6 +7,13 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _aten_field_head(monkeypatch):
+    """these tests pin the K1-K5 path and the entry points; the Zeng backbone's last stage stays on the ATen modules here
+    whatever the device's K6 self-test says (K6 has its own file, tests/test_gpu_zzz_field_head.py)"""
+    monkeypatch.setenv('BH_FIELD_HEAD', 'aten')
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIG = os.path.join(ROOT, 'config', 'pds-coco', 'zeng-bihome-lr-1e-3.yaml')
 

@@ -81,3 +81,23 @@ def test_stage_and_backbone_vs_aten(k6_on_this_device, monkeypatch):
     num = sum(float(((a - b).double() ** 2).sum()) for a, b in zip(*[r[1] for r in res]) if a is not None)
     den = sum(float((b.double() ** 2).sum()) for b in res[1][1] if b is not None)
     assert (num / den) ** 0.5 < 1e-3
+
+
+@pytest.mark.gpu
+def test_training_entry_point_with_the_fused_head(k6_on_this_device, monkeypatch, tmp_path):
+    """train.py / eval.py on the shipped Zeng config with layer8 on K6: steps run, weights stay finite, the checkpoint
+    carries the BatchNorm buffers K6 maintains, evaluation (K6's eval-mode fold) gives a finite MACE"""
+    import numpy as np
+    from conftest import load_entry
+    monkeypatch.setenv('BH_FIELD_HEAD', 'fused')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    config = os.path.join(root, 'config', 'pds-coco', 'zeng-bihome-lr-1e-3.yaml')
+    train, ev = load_entry('train'), load_entry('eval')
+    log_dir = os.path.join(str(tmp_path), 'log')
+    train.main(config, batch_size=8, max_steps=3, synthetic_pool=8, log_dir=log_dir)
+    blob = torch.load(os.path.join(log_dir, 'model_000003.pth'), map_location='cpu', weights_only=False)
+    assert blob['step'] == 3
+    assert all(torch.isfinite(v).all() for v in blob['model'].values() if torch.is_floating_point(v))
+    assert int(blob['model']['0.layer8.1.num_batches_tracked']) == 6          # two backbone passes per step
+    assert float(blob['model']['0.layer8.1.running_var'].min()) > 0
+    assert np.isfinite(ev.main(config, os.path.join(log_dir, 'model_000003.pth'), batch_size=8, samples=16))
