@@ -147,7 +147,7 @@ def golden_photometric_noop(PHO, NO):
     print('photometric/noop', {k: v.shape for k, v in out.items() if k.startswith(('photo', 'noop'))})
 
 
-def golden_perceptual_variants(PH):
+def golden_perceptual_variants(PH, CA=None):
     B, P = 3, 64
     base_kw = head_kwargs('config/s-coco/detone-bihome-lr-5e-3.yaml', P)
     g = torch.Generator().manual_seed(45)
@@ -170,13 +170,17 @@ def golden_perceptual_variants(PH):
         'double_aware_margin': dict(TRIPLET_LOSS='double-line', TRIPLET_MARGIN=0.05, TRIPLET_AGGREGATION='channel-aware'),
         'double_aware_inf_masks': dict(TRIPLET_LOSS='double-line', TRIPLET_MARGIN='inf', TRIPLET_AGGREGATION='channel-aware',
                                        MASK_KEYS=['mask_1', 'mask_2']),
+        # 'dual': the content-aware backbone's own feature extractor adds a second, full-resolution triplet term (:407-441)
+        'double_dual': dict(TRIPLET_LOSS='double-line-dual', TRIPLET_MARGIN='inf', TRIPLET_AGGREGATION='channel-agnostic'),
     }
+    out.update(_state(TinyContentBackbone(CA, True), 'dual_w_'))
     for name, over in cases.items():
         kw = dict(base_kw)
         kw.update(over)
         double = 'double' in kw['TRIPLET_LOSS']
         for tag, dt in DTYPES:
-            model = PH.Model(backbone=torch.nn.Identity(), **kw)
+            backbone = TinyContentBackbone(CA, True).to(dt) if 'dual' in name else torch.nn.Identity()
+            model = PH.Model(backbone=backbone, **kw)
             model.auxiliary_resnet = TinyExtractor().to(dt)
             model.auxiliary_resnet.with_projection_head = None
             a = d12.to(dt).requires_grad_(True)
@@ -225,7 +229,7 @@ def main():
     warnings.filterwarnings('ignore')
     golden_triplet(ref_import.load('src.heads.TripletHead'), ref_import.load('src.backbones.ContentAware'))
     golden_photometric_noop(ref_import.load('src.heads.PhotometricHead'), ref_import.load('src.heads.NoOpHead'))
-    golden_perceptual_variants(ref_import.load('src.heads.PerceptualHead'))
+    golden_perceptual_variants(ref_import.load('src.heads.PerceptualHead'), ref_import.load('src.backbones.ContentAware'))
     golden_all_points(ref_import.load('src.data.transforms'))
 
 

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import rel_l2
-from test_head_mirrors import PERCEPTUAL_CASES, TRIPLET_CASES, perceptual_kwargs, triplet_forward
+from test_head_mirrors import PERCEPTUAL_CASES, TRIPLET_CASES, perceptual_backbone, perceptual_kwargs, triplet_forward
 
 pytestmark = pytest.mark.gpu
 
@@ -33,7 +33,7 @@ def test_perceptual_variants_golden(golden, name):
     from bihome_b200.heads import PerceptualHead as PH
     from oracle.make_golden import TinyExtractor
     g = golden('perceptual_variants_P64.npz')
-    model = PH.Model(backbone=torch.nn.Identity(), **perceptual_kwargs(64, **PERCEPTUAL_CASES[name])).cuda()
+    model = PH.Model(backbone=perceptual_backbone(g, name, torch.float32, 'cuda'), **perceptual_kwargs(64, **PERCEPTUAL_CASES[name])).cuda()
     model.auxiliary_resnet = TinyExtractor().cuda()
     a, b = cu(g['delta_12']).requires_grad_(True), cu(g['delta_21']).requires_grad_(True)
     data = {'patch_1': cu(g['patch_1']), 'patch_2': cu(g['patch_2']), 'delta_hat_12': a, 'delta_hat_21': b,

@@ -47,7 +47,15 @@ PERCEPTUAL_CASES = {
     'double_aware_margin': dict(TRIPLET_LOSS='double-line', TRIPLET_MARGIN=0.05, TRIPLET_AGGREGATION='channel-aware'),
     'double_aware_inf_masks': dict(TRIPLET_LOSS='double-line', TRIPLET_MARGIN='inf', TRIPLET_AGGREGATION='channel-aware',
                                    MASK_KEYS=['mask_1', 'mask_2']),
+    'double_dual': dict(TRIPLET_LOSS='double-line-dual', TRIPLET_MARGIN='inf', TRIPLET_AGGREGATION='channel-agnostic'),
 }
+
+
+def perceptual_backbone(g, name, dtype=torch.float64, device='cpu'):
+    """Identity, except for the 'dual' variants, whose extra term runs the content-aware backbone's feature extractor"""
+    if 'dual' not in name:
+        return torch.nn.Identity()
+    return content_backbone(g, 'dual', True).to(dtype).to(device)
 
 
 @pytest.mark.parametrize('name', sorted(PERCEPTUAL_CASES))
@@ -55,7 +63,7 @@ def test_perceptual_variants_match_reference(F, golden, name):
     """reference PerceptualHead.triplet_resnet_loss variants (:320-714) -- values and gradients w.r.t. the offsets"""
     from bihome_b200.heads import PerceptualHead as PH
     g = golden('perceptual_variants_P64.npz')
-    model = PH.Model(backbone=torch.nn.Identity(), **perceptual_kwargs(64, **PERCEPTUAL_CASES[name]))
+    model = PH.Model(backbone=perceptual_backbone(g, name), **perceptual_kwargs(64, **PERCEPTUAL_CASES[name]))
     model.auxiliary_resnet = tiny_extractor()
     a, b = t64(g['delta_12']).requires_grad_(True), t64(g['delta_21']).requires_grad_(True)
     data = {'patch_1': t64(g['patch_1']), 'patch_2': t64(g['patch_2']), 'delta_hat_12': a, 'delta_hat_21': b,
