@@ -43,6 +43,14 @@ def bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu, m1=None, m2=None):
     return loss_b, parts
 
 
+def dltn(points1, points2, choice=None):
+    from oracle import kornia050 as K
+    if choice is not None:
+        idx = choice.reshape(points1.shape[0], -1, 1).repeat(1, 1, 2)
+        points1, points2 = torch.gather(points1, 1, idx), torch.gather(points2, 1, idx)
+    return K.find_homography_dlt(points1, points2)
+
+
 def dltn_field(field, choice, four_points):
     delta, H, _ = R.zeng_delta_hat(field, choice.shape[1], 1, choice.reshape(-1))
     return H.reshape(-1, 3, 3), delta.reshape(-1, 4, 2)
@@ -89,7 +97,7 @@ def fh_affine(x, a, M, gx):
 def install(monkeypatch):
     import bihome_b200.functional as F
     for name, fn in (('dlt4', dlt4), ('warp', warp), ('coverage_mask', coverage_mask), ('bihome_loss', bihome_loss),
-                     ('dltn_field', dltn_field), ('mace', mace), ('_fh_moments', fh_moments), ('_fh_fwd', fh_fwd),
+                     ('dltn', dltn), ('dltn_field', dltn_field), ('mace', mace), ('_fh_moments', fh_moments), ('_fh_fwd', fh_fwd),
                      ('_fh_bwd', fh_bwd), ('_fh_affine', fh_affine)):
         monkeypatch.setattr(F, name, fn)
     return F

@@ -185,6 +185,52 @@ def test_noop_head_matches_reference(F, golden):
         head4.predict_homography({'delta_hat_12': d})
 
 
+@pytest.mark.parametrize('version,n', [('one-line', 4), ('double-line', 1), ('', 3)])
+def test_dsac_heads_match_the_reference_module(F, version, n):
+    """perspective-field heads with several hypotheses (DSAC scoring, score-weighted loss and offsets) and the feature-
+    returning mode (TRIPLET_LOSS '' -> external nn loss), against the reference module itself with the same torch seed"""
+    PH_ref = _reference().load('src.heads.PerceptualHead')
+    from bihome_b200.heads import PerceptualHead as PH
+    P, B, M = 32, 2, 24
+    kw = perceptual_kwargs(P, TRIPLET_LOSS=version, TRIPLET_MARGIN=1.0 if version == 'one-line' else 'inf', DELTA_HAT_KEYS=[],
+                           PF_KEYS=['pf_hat_12', 'pf_hat_21'], RANSAC_HYPOTHESIS_NO=n, POINTS_PER_HYPOTHESIS=M)
+    gen = torch.Generator().manual_seed(13)
+    ys, xs = torch.meshgrid(torch.arange(P, dtype=DT), torch.arange(P, dtype=DT), indexing='ij')
+    flow = torch.stack([0.05 * xs - 0.02 * ys + 1.5, 0.03 * ys + 0.01 * xs - 2.0]).unsqueeze(0).repeat(B, 1, 1, 1)
+    pf12 = flow + 0.2 * torch.randn(B, 2, P, P, generator=gen, dtype=DT)
+    pf21 = -flow + 0.2 * torch.randn(B, 2, P, P, generator=gen, dtype=DT)
+    p1, p2 = torch.rand(B, 1, P, P, generator=gen, dtype=DT), torch.rand(B, 1, P, P, generator=gen, dtype=DT)
+    res = []
+    for mod in (PH_ref, PH):
+        model = mod.Model(backbone=torch.nn.Identity(), **kw)
+        model.auxiliary_resnet = tiny_extractor()
+        model.auxiliary_resnet.with_projection_head = None
+        if True:
+            # both cache their coordinate field in float32 (reference :139): pre-populate the caches in float64 like the
+            # golden generator does, so that both sides evaluate the same float64 function
+            with torch.no_grad():
+                _, cf, fp = model.forward_map_field(pf12.float(), None, None)
+            model.coordinate_field_12 = model.coordinate_field_21 = cf.double()
+            model.four_points_12 = model.four_points_21 = fp.double()
+        a, b = pf12.clone().requires_grad_(True), pf21.clone().requires_grad_(True)
+        torch.manual_seed(5)
+        out = model({'patch_1': p1, 'patch_2': p2, 'pf_hat_12': a, 'pf_hat_21': b})
+        if version == '':
+            f2, f1w, _, delta_hat = out
+            loss = (f2 - f1w).abs().sum()
+        else:
+            loss, _, delta_hat = out
+        grads = torch.autograd.grad(loss, (a, b), allow_unused=True)
+        res.append((loss.detach(), delta_hat.detach(), grads))
+    (lr, dr, gr), (lo, do, go) = res
+    assert abs(float(lo) - float(lr)) < 1e-8 * abs(float(lr))
+    assert rel_l2(do.numpy(), dr.numpy()) < 1e-8
+    for x, y in zip(go, gr):
+        assert (x is None) == (y is None)
+        if y is not None:
+            assert rel_l2(x.numpy(), y.numpy()) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------------
 # whole networks: compared with the reference tree itself (build container only)
 # ------------------------------------------------------------------------------------------------
