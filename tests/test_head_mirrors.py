@@ -231,6 +231,39 @@ def test_dsac_heads_match_the_reference_module(F, version, n):
             assert rel_l2(x.numpy(), y.numpy()) < 1e-6
 
 
+@pytest.mark.parametrize('strategy,version', [('upsample-patch-2x', 'double-line'), ('upsample-patch-4x', 'one-line'),
+                                              ('upsample-patch-2x', 'one-line')])
+def test_upsampling_strategies_match_the_reference_module(F, strategy, version):
+    """SAMPLING_STRATEGY 'upsample-patch-2x/4x' (reference :353-396): features of the bilinearly enlarged patches, masks
+    pooled by what is left of the extractor's stride (2 or 1)"""
+    PH_ref = _reference().load('src.heads.PerceptualHead')
+    from bihome_b200.heads import PerceptualHead as PH
+    P, B = 32, 3
+    kw = perceptual_kwargs(P, SAMPLING_STRATEGY=strategy, TRIPLET_LOSS=version,
+                           TRIPLET_MARGIN='inf' if version == 'double-line' else 0.7)
+    gen = torch.Generator().manual_seed(17)
+    lo = torch.rand(B, 1, 9, 9, generator=gen, dtype=DT)
+    p1 = torch.nn.functional.interpolate(lo, size=(P, P), mode='bicubic', align_corners=True)
+    p2 = 0.5 * p1 + 0.5 * torch.rand(B, 1, P, P, generator=gen, dtype=DT)
+    d12 = (torch.rand(B, 4, 2, generator=gen, dtype=DT) * 2 - 1) * 6
+    d21 = -d12 + torch.rand(B, 4, 2, generator=gen, dtype=DT)
+    res = []
+    for mod in (PH_ref, PH):
+        model = mod.Model(backbone=torch.nn.Identity(), **kw)
+        model.auxiliary_resnet = tiny_extractor()
+        model.auxiliary_resnet.with_projection_head = None
+        a, b = d12.clone().requires_grad_(True), d21.clone().requires_grad_(True)
+        loss, _, _ = model({'patch_1': p1, 'patch_2': p2, 'delta_hat_12': a, 'delta_hat_21': b})
+        res.append((loss.detach(), torch.autograd.grad(loss, (a, b), allow_unused=True)))
+    (lr, gr), (lo_, go) = res
+    # FIX: the fused path takes the exact coverage mask, the reference warps ones through its float32-born grid
+    assert abs(float(lo_) - float(lr)) < 1e-6 * abs(float(lr))
+    for x, y in zip(go, gr):
+        assert (x is None) == (y is None)
+        if y is not None:
+            assert rel_l2(x.numpy(), y.numpy()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # whole networks: compared with the reference tree itself (build container only)
 # ------------------------------------------------------------------------------------------------
