@@ -264,6 +264,33 @@ def test_upsampling_strategies_match_the_reference_module(F, strategy, version):
             assert rel_l2(x.numpy(), y.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize('layer,projection', [(1, None), (2, None), (1, [[64, 32], [32, 16]])])
+def test_auxiliary_resnet_matches_the_reference_module(layer, projection):
+    """the frozen feature extractor (reference :15-76): parameter names, the 1 -> 3 channel repeat folded into conv1,
+    deeper output layers, the optional projection head; train-mode BatchNorm as in the reference"""
+    PH_ref = _reference().load('src.heads.PerceptualHead')
+    from bihome_b200.heads import PerceptualHead as PH
+    kw = dict(AUXILIARY_RESNET='resnet18', AUXILIARY_RESNET_OUTPUT_LAYER=layer, AUXILIARY_RESNET_FREEZE=True)
+    if projection is not None:
+        kw['WITH_PROJECTION_HEAD'] = projection
+    torch.manual_seed(4)
+    ref = PH_ref.AuxiliaryResnet(**kw).double()
+    ours = PH.AuxiliaryResnet(AUXILIARY_RESNET_PRETRAINED=False, **kw).double()
+    assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    assert not any(p.requires_grad for p in ours.resnet.parameters())
+    gen = torch.Generator().manual_seed(8)
+    for channels in (1, 3):
+        x = torch.rand(2, channels, 64, 64, generator=gen, dtype=DT)
+        for mode in ('train', 'eval'):
+            getattr(ref, mode)()
+            getattr(ours, mode)()
+            a, b = ref(x), ours(x)
+            assert a.shape == b.shape and rel_l2(b.detach().numpy(), a.detach().numpy()) < 1e-12, (channels, mode)
+    for (name, p), (_, q) in zip(ours.named_buffers(), ref.named_buffers()):
+        assert torch.allclose(p, q, rtol=1e-12, atol=1e-14), name          # the running statistics moved together
+
+
 # ------------------------------------------------------------------------------------------------
 # whole networks: compared with the reference tree itself (build container only)
 # ------------------------------------------------------------------------------------------------
