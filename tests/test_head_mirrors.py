@@ -309,6 +309,12 @@ def _reference():
                           MASK_KEYS=['mask_1', 'mask_2'], FIX_MASK=False, MASK_NORMALIZATION_STRENGTH=0.5,
                           FEATURE_KEYS=['feature_1', 'feature_2'], TARGET_KEYS=['delta_hat_12', 'delta_hat_21'])),
     ('HomographyNet', dict(IMAGE_SIZE=128, PATCH_KEYS=['patch_1', 'patch_2'], TARGET_KEYS=['delta_hat_12'])),
+    ('ResNet34', dict(VARIANT='DoubleLine', IMAGE_SIZE=128, PRETRAINED_RESNET=False, PATCH_KEYS=['patch_1', 'patch_2'],
+                      TARGET_KEYS=['delta_hat_12', 'delta_hat_21'])),
+    ('Rethinking', dict(VARIANT='DoubleLine', IMAGE_SIZE=128, RESNET_BLOCK='ResNet34', PRETRAINED_RESNET=False,
+                        PATCH_KEYS=['patch_1', 'patch_2'], TARGET_KEYS=['pf_hat_12', 'pf_hat_21'])),
+    ('Rethinking', dict(VARIANT='OneLine', IMAGE_SIZE=128, RESNET_BLOCK='ResNet50', PRETRAINED_RESNET=False,
+                        PATCH_KEYS=['patch_1', 'patch_2'], TARGET_KEYS=['pf_hat_12'])),
 ])
 def test_backbone_mirrors_match_reference_modules(module, kwargs):
     """same parameter names and shapes, same initialisation stream, same outputs for the same weights and inputs"""
@@ -323,7 +329,8 @@ def test_backbone_mirrors_match_reference_modules(module, kwargs):
     assert all(rs[k].shape == os_[k].shape for k in rs)
     ours.load_state_dict(rs)
     g = torch.Generator().manual_seed(1)
-    p1, p2 = torch.rand(4, 1, 128, 128, generator=g), torch.rand(4, 1, 128, 128, generator=g)
+    n = 2 if module == 'Rethinking' else 4
+    p1, p2 = torch.rand(n, 1, 128, 128, generator=g), torch.rand(n, 1, 128, 128, generator=g)
     for mode in ('train', 'eval'):
         getattr(ref, mode)()
         getattr(ours, mode)()
@@ -331,7 +338,7 @@ def test_backbone_mirrors_match_reference_modules(module, kwargs):
         b = ours({'patch_1': p1, 'patch_2': p2})
         assert sorted(a.keys()) == sorted(b.keys())
         for k in a:
-            assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), (mode, k)
+            assert torch.allclose(a[k], b[k], rtol=1e-4, atol=2e-5), (mode, k, float((a[k] - b[k]).abs().max()))
     a = ref.predict_homography({'patch_1': p1, 'patch_2': p2})
     b = ours.predict_homography({'patch_1': p1, 'patch_2': p2})
     assert sorted(a.keys()) == sorted(b.keys())
