@@ -3,11 +3,12 @@
 Works in the build container only (the GPU box has no /root/reference); used by
 oracle/make_golden.py and by the CPU tests that are skipped when the tree is absent.
 
-Three shims make the reference importable on this image:
+Four shims make the reference importable on this image:
   * ``kornia``             -> oracle.kornia050 (restated 0.5.0 functions)
   * ``matplotlib.pyplot``  -> empty stub (only src/data/coco/dataset.py:5 imports it)
   * ``torchvision.models.resnet*(pretrained=True)`` -> seeded random init (no network);
     hit by src/heads/PerceptualHead.py:22.
+  * ``torch.hub._download_url_to_file`` -> today's public name (src/utils/model_zoo.py:9-16; never called).
 """
 import importlib
 import os
@@ -34,7 +35,12 @@ def _install_shims():
             sys.modules['matplotlib'] = mpl
             sys.modules['matplotlib.pyplot'] = plt
     import torch
+    import torch.hub
     import torchvision.models as tvm
+    # src/utils/model_zoo.py:9-16 imports a private downloader that newer torch renamed; nothing here downloads
+    for name, value in (('_download_url_to_file', torch.hub.download_url_to_file),):
+        if not hasattr(torch.hub, name):
+            setattr(torch.hub, name, value)
     if not getattr(tvm, '_bihome_oracle_patched', False):
         for name in ('resnet18', 'resnet34', 'resnet50'):
             orig = getattr(tvm, name)

@@ -154,3 +154,36 @@ def test_rescale_center_crop_matches_reference_rule():
     for h, w in ((480, 640), (640, 480), (240, 320), (500, 333), (427, 640)):
         out = rescale_center_crop(np.zeros((h, w, 3), np.uint8))
         assert out.shape == (240, 320, 3)
+
+
+def test_checkpoints_are_interchangeable_with_the_reference_checkpointer(tmp_path):
+    """files written by the reference's CheckPointer (src/utils/checkpoint.py:32-53) resume here, and the other way
+    round: same file names, same dictionary, same last_checkpoint.txt protocol (build container only)"""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip('reference tree not present')
+    RefCheckPointer = ref_import.load('src.utils.checkpoint').CheckPointer
+    from bihome_b200.utils.checkpoint import CheckPointer
+
+    def trio(seed):
+        torch.manual_seed(seed)
+        model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[2, 4], gamma=0.1)
+        model(torch.randn(5, 4)).sum().backward()
+        opt.step()
+        sched.step()
+        return model, opt, sched
+
+    for writer, reader, sub in ((RefCheckPointer, CheckPointer, 'ref_to_ours'), (CheckPointer, RefCheckPointer, 'ours_to_ref')):
+        d = str(tmp_path / sub)
+        os.makedirs(d, exist_ok=True)
+        m1, o1, s1 = trio(1)
+        writer(m1, o1, s1, d, save_to_disk=True, device='cpu').save('model_000007', step=7)
+        m2, o2, s2 = trio(2)
+        extra = reader(m2, o2, s2, d, save_to_disk=False, device='cpu').load()
+        assert extra['step'] == 7
+        for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+            assert torch.equal(a, b), k
+        assert s2.state_dict() == s1.state_dict()
+        assert o2.state_dict()['param_groups'] == o1.state_dict()['param_groups']
