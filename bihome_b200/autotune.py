@@ -138,8 +138,9 @@ def compare_and_time(dev, timing_batch=64):
     worst = 0.0
     gen = torch.Generator().manual_seed(1)
     # float32 on both sides: a ReLU unit within round-off of zero may switch between the two evaluations and move the
-    # input gradient of one pixel by ~10 % -- the bounds leave room for a few such pixels, a wrong kernel is off by O(1)
-    bounds = {'out': 1e-4, 'gx': 3e-2, 'param': 1e-2, 'buffer': 1e-4}
+    # input gradient of one pixel by ~10 %, and a library may still pick a TF32 kernel for the ATen side's 1x1
+    # convolutions (1e-3) -- the bounds leave room for both; a wrong kernel is off by O(0.1 - 1)
+    bounds = {'out': 5e-3, 'gx': 5e-2, 'param': 3e-2, 'buffer': 5e-3}
     for mode, shape in (('train', (3, 16, 40, 56)), ('train', (2, 16, 33, 17)), ('eval', (2, 16, 32, 32))):
         getattr(fused, mode)()
         getattr(aten, mode)()
