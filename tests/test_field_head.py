@@ -28,6 +28,26 @@ def make_stage(dtype, device='cpu', seed=0):
     return stage.to(dtype).to(device)
 
 
+def mute_knife_edge_pixels(g, pre, eps):
+    """zero the upstream gradient of every pixel that has a hidden unit within `eps` of its ReLU threshold: whether such
+    a unit counts as active depends on the last bit of the pre-activation (summation order, float32 vs float64), and
+    a single switched unit would move the compared gradients by far more than the tolerances below"""
+    near = (pre.abs() < eps).any(dim=1, keepdim=True)              # pre [B,hid,H,W] -> [B,1,H,W]
+    return g * (~near).to(g.dtype)
+
+
+def hidden_preactivation(stage, x):
+    """BatchNorm output of `stage` in float64 without touching its buffers (batch statistics in training)"""
+    conv, bn = stage[0], stage[1]
+    y = torch.nn.functional.conv2d(x.double(), conv.weight.double(), conv.bias.double())
+    if bn.training:
+        mean, var = y.mean(dim=(0, 2, 3)), y.var(dim=(0, 2, 3), unbiased=False)
+    else:
+        mean, var = bn.running_mean.double(), bn.running_var.double()
+    scale = bn.weight.double() / torch.sqrt(var + bn.eps)
+    return (y - mean.view(1, -1, 1, 1)) * scale.view(1, -1, 1, 1) + bn.bias.double().view(1, -1, 1, 1)
+
+
 def compare_stage(F, stage, dtype, device, shape, tol, modes=('train', 'train', 'eval')):
     ref = copy.deepcopy(stage)
     gen = torch.Generator().manual_seed(3)
@@ -36,6 +56,7 @@ def compare_stage(F, stage, dtype, device, shape, tol, modes=('train', 'train', 
         getattr(ref, mode)()
         x = torch.relu(torch.randn(*shape, generator=gen) + 0.3).to(dtype).to(device).contiguous(memory_format=torch.channels_last)
         g = torch.randn(shape[0], 2, shape[2], shape[3], generator=gen).to(dtype).to(device)
+        g = mute_knife_edge_pixels(g, hidden_preactivation(ref, x), 1e-9 if dtype == torch.float64 else 1e-4)
         xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
         oa, ob = F.field_head(stage, xa), ref(xb)
         assert oa.shape == ob.shape and oa.is_contiguous()
