@@ -157,7 +157,7 @@ def run_ours(args):
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        net = engine.data_parallel(model, local)
     opt, sched = engine.build_optimizer(cfg, model)
     t = gpu_pairs.transform_args(cfg['DATA']['TRANSFORMS'])
     pool = gpu_pairs.synthetic_pool(args.pool, device=dev)

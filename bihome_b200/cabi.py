@@ -26,6 +26,7 @@ SIGNATURES = {
     'bh_pairgen_draw': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
     'bh_pairgen_apply': (_i, [_vp] * 6 + [_i, _i, _i, _i, _i, _d, _d, _vp]),
     'bh_mace': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'bh_tune_set': (_i, [ctypes.c_char_p, _i]),
     'bh_fieldhead_supported': (_i, [_i, _i]),
     'bh_fieldhead_grid': (_i, [_i, ctypes.c_longlong]),
     'bh_fieldhead_moments': (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp]),

@@ -1,8 +1,11 @@
 // Library-level entry points: version, error text, launch counter, MACE.
+#include <string.h>
+
 #include "bh_common.cuh"
 
 namespace bh {
 unsigned long long g_launch_count = 0;
+int g_tune[kTuneCount] = {0};
 
 // train.py:401-404 / eval.py:133-134: mean over B*4 corners of the Euclidean corner error
 __global__ void __launch_bounds__(256) mace_kernel(const float* __restrict__ gt, const float* __restrict__ hat,
@@ -34,6 +37,17 @@ extern "C" const char* bh_strerror(int code) {
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "bihome_b200: unknown error code";
+}
+
+extern "C" int bh_tune_set(const char* key, int value) {
+    if (!key) return BH_E_NULL;
+    static const char* const names[] = {"warp_path", "loss_variant", "loss_cluster"};
+    for (int k = 0; k < 3; ++k)
+        if (strcmp(key, names[k]) == 0) {
+            bh::g_tune[k] = value;
+            return BH_OK;
+        }
+    return BH_E_UNSUPPORTED;
 }
 
 extern "C" int bh_mace(const float* delta_gt, const float* delta_hat, float* out, int B, bh_stream_t stream) {

@@ -11,7 +11,31 @@
 
 namespace bh {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SM count of the current device (B200: 148 = 2 dies x 74); persistent grids are sized in multiples of it.  Queried once
+// per device ordinal; 148 when no device is visible (the build container), so that grid arithmetic stays testable there.
+inline int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        cudaGetLastError();
+        return 148;
+    }
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 148;
+        }
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+#define kNumSMs (::bh::num_sms())
+
+// Tuning switches of tools/microbench.py (bh_tune_set, include/bihome_b200.h): process-global, never touched by the product
+// path -- every entry point picks its kernel from its arguments alone while these hold their default 0.
+enum TuneKey { kTuneWarpPath = 0, kTuneLossVariant = 1, kTuneLossCluster = 2, kTuneCount = 8 };
+extern int g_tune[kTuneCount];
 
 // Every kernel launch in the library goes through BH_LAUNCH_CHECK so the launch counter that
 // bench.py reports (gpu_launches) cannot drift from what really ran.

@@ -762,8 +762,8 @@ extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* 
     const int nvec = vec ? a.hw / 4 : a.hw;
     int CL = (B >= 2 * kNumSMs) ? 2 : (B >= kNumSMs ? 4 : 8);
     while (CL > 1 && nvec / CL < kLanes) CL >>= 1;
-    if (const char* e = getenv("BH_LOSS_CL")) {   // tuning knob (tools/microbench.py --loss-cl): cluster size 1, 2, 4 or 8
-        const int f = atoi(e);
+    {   // microbenchmark switch (bh_tune_set "loss_cluster"): cluster size 1, 2, 4 or 8; 0 = the rule above
+        const int f = g_tune[kTuneLossCluster];
         if (f == 1 || f == 2 || f == 4 || f == 8) CL = f;
     }
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -773,9 +773,9 @@ extern "C" int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* 
         // Measured on B200 (tools/microbench.py --loss-cl, C = 64, h = w = 32): the persistent stream wins while the whole
         // job is a few dozen tiles per CTA (B = 256: 84 % of the HBM peak against 72 % for the cluster kernels, which run
         // 2.3 waves there); from B = 1024 on the clustered TMA kernel does (94 - 100 % against 86 - 90 %).
-        const char* force = getenv("BH_LOSS_VARIANT");   // tuning knob: "ldg", "cluster", "stream"
-        const bool want_stream = force ? force[0] == 's' : B < 512;
-        const bool want_tma = force ? force[0] != 'l' : true;
+        const int force = g_tune[kTuneLossVariant];   // microbenchmark switch (bh_tune_set "loss_variant"): 1 ldg, 2 cluster, 3 stream
+        const bool want_stream = force ? force == 3 : B < 512;
+        const bool want_tma = force ? force != 1 : true;
         if (vec && pow2 && quads <= 64 && want_stream) {
             // persistent TMA-staged stream + per-sample finish
             const int per_lane = quads > 32 ? 2 : 1;

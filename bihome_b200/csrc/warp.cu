@@ -13,6 +13,8 @@
 //   generic: anything else (scalar, strided).
 // Backward produces dH by a fixed-order per-sample reduction (bit-reproducible, no atomics); the image
 // gradient (dead work on the biHomE path: the source never requires grad) is an optional red.global.add.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "bh_common.cuh"
 
 namespace bh {
@@ -1081,6 +1083,323 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
 }
 
 // =================================================================================================
+// tile path (NCHW planes, the default): one CTA per 32x32 output tile, the source box staged by ONE tiled TMA copy.
+//
+//   work item  = a 32x32 tile of output pixels of one plane: 8192 CTAs of 4 warps for the north-star batch (512 planes of
+//                128x128), eight or more of them resident per SM -- the hardware block scheduler balances the load (no
+//                persistent rounds, no tail), and the DRAM latency of one CTA's box is covered by its neighbours' math.
+//   source box = bounding box of the tile's four projected corners (a projective map with w > 0 sends the tile to a convex
+//                quadrilateral), fetched with cp.async.bulk.tensor.3d (SASS UTMALDG) through one of three tensor maps
+//                over [planes, Hs, Ws] whose boxes are 36x36, 48x48 and 64x64 floats.  The box may sit anywhere, also
+//                partly or wholly outside the plane: TMA fills what is out of bounds with ZEROS, which is exactly
+//                grid_sample's zeros padding -- the sampler has no border case at all (no clamp, no predicate, no zero
+//                frame to write).  Tiles whose box exceeds 64x64 (down-sampling by more than 2) or whose w changes sign read
+//                the plane through the read-only cache with predicated taps.
+//   sampling   = a warp owns 32 columns x 8 rows, lanes on consecutive columns (coalesced 128-byte row stores), four packed
+//                row pairs in flight per lane (fp32x2 arithmetic, magic-number floor, see above).
+//   pooled mask= analytic coverage, 4x4 mean; a warp whose 32x8 region maps strictly inside the source writes ones.
+//   backward   = same staging; the upstream gradient rows of a lane's column are plain coalesced loads issued before the
+//                wait on the box; nine sums per warp (butterfly), per-CTA partials in shared memory, one partial row per
+//                tile, fixed-order finish kernel behind a programmatic dependent launch.
+// =================================================================================================
+struct alignas(64) TileMaps {
+    CUtensorMap m[3];
+};
+constexpr int kTile = 32;
+constexpr int kTileThreads = 128;
+constexpr int kTileBoxMax = 64;
+constexpr int kTileSmem = kTileBoxMax * kTileBoxMax * 4;
+__host__ __device__ constexpr int tile_box(int sel) { return sel == 0 ? 36 : (sel == 1 ? 48 : 64); }
+
+__device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, int c0, int r0, int plane, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(plane), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TileGeom {
+    int plane, b, c, x_lo, y_lo, x_hi, y_hi;
+    int c0, r0, sel;   // source box origin and tensor-map index; sel < 0: no box (predicated global taps)
+};
+// Every lane of every warp computes the same geometry (uniform control flow, no shared header).
+__device__ __forceinline__ TileGeom tile_geom(const Hmat& hm, int tile, int tiles_x, int tiles_per_plane, int C, int Ho, int Wo) {
+    TileGeom g;
+    g.plane = tile / tiles_per_plane;
+    const int t = tile - g.plane * tiles_per_plane, ty = t / tiles_x, tx = t - ty * tiles_x;
+    g.b = g.plane / C;
+    g.c = g.plane - g.b * C;
+    g.x_lo = tx * kTile; g.y_lo = ty * kTile;
+    g.x_hi = min(Wo, g.x_lo + kTile); g.y_hi = min(Ho, g.y_lo + kTile);
+    const int k = threadIdx.x & 3;
+    float u, v, w;
+    project_rcp(hm, static_cast<float>((k & 1) ? g.x_hi - 1 : g.x_lo), static_cast<float>((k & 2) ? g.y_hi - 1 : g.y_lo), u, v, w);
+    // 1e5: the corner coordinates carry ~4e-7 relative error (reciprocal + 3 roundings), covered by the 0.05 px guard
+    const bool good = quad_all(w > 0.0f && fabsf(u) < 1.0e5f && fabsf(v) < 1.0e5f);
+    const float umin = quad_min(u), umax = quad_max(u), vmin = quad_min(v), vmax = quad_max(v);
+    g.c0 = static_cast<int>(floorf(umin - 0.05f));
+    g.r0 = static_cast<int>(floorf(vmin - 0.05f));
+    const int need = good ? max(static_cast<int>(floorf(umax + 0.05f)) + 2 - g.c0, static_cast<int>(floorf(vmax + 0.05f)) + 2 - g.r0) : (1 << 30);
+    g.sel = need <= tile_box(0) ? 0 : (need <= tile_box(1) ? 1 : (need <= tile_box(2) ? 2 : -1));
+    // broadcast quad 0's verdict: all quads hold the same numbers, this only pins the compiler to uniform values
+    g.c0 = __shfl_sync(0xffffffffu, g.c0, 0); g.r0 = __shfl_sync(0xffffffffu, g.r0, 0); g.sel = __shfl_sync(0xffffffffu, g.sel, 0);
+    return g;
+}
+// is the 32x8 region of this warp sampled strictly inside the source (coverage == 1, no coverage gradient)?
+__device__ __forceinline__ bool region_inside(const Hmat& hm, int xa, int xb, int ya, int yb, int Hs, int Ws) {
+    const int k = threadIdx.x & 3;
+    float u, v, w;
+    project_rcp(hm, static_cast<float>((k & 1) ? xb : xa), static_cast<float>((k & 2) ? yb : ya), u, v, w);
+    const bool in = quad_all(w > 0.0f && (u >= 0.001f) && (v >= 0.001f) && (u < static_cast<float>(Ws - 1) - 0.001f) &&
+                             (v < static_cast<float>(Hs - 1) - 0.001f));
+    return __shfl_sync(0xffffffffu, in ? 1 : 0, 0) != 0;
+}
+__device__ __forceinline__ Window tile_window(const void* stage, const TileGeom& g, const float* plane_ptr, int Ws) {
+    Window wd;
+    wd.shared = g.sel >= 0;
+    wd.xpred = false;
+    if (wd.shared) {
+        wd.pitch = tile_box(g.sel);
+        // byte address of source pixel (0, 0) relative to the box, minus the bias the magic-number floor leaves in `lin`
+        const uint32_t origin = static_cast<uint32_t>(-g.r0 * wd.pitch - g.c0) - static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(wd.pitch + 1);
+        wd.base_s32 = smem_u32(stage) + origin * 4u;
+        wd.taps = nullptr;
+    } else {
+        wd.pitch = Ws;
+        wd.base_s32 = 0u;
+        wd.taps = plane_ptr;
+    }
+    return wd;
+}
+
+// 8 rows of one column out of the staged box: values (and coordinates for the coverage)
+template <int kPitch>
+__device__ __forceinline__ void tile_sample8(const Hmat& hm, const ColProj& cp, const Window& wd, float yg, float ymax, f2 (&u2)[4],
+                                             f2 (&v2)[4], f2 (&o2)[4]) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        f2 r2;
+        project_col2(hm, cp, pk(fminf(yg + 2.0f * p, ymax), fminf(yg + (2.0f * p + 1.0f), ymax)), u2[p], v2[p], r2);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) o2[p] = lerp2(cell_at2<kPitch>(u2[p], v2[p], wd, false, 0));
+}
+
+template <bool kMask>
+__global__ void __launch_bounds__(kTileThreads, 8)
+    warp_fwd_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ src, const float* __restrict__ H,
+                         float* __restrict__ out, float* __restrict__ mask_pooled, int C, int Hs, int Ws, int Ho, int Wo, int tiles_x,
+                         int tiles_per_plane) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const Hmat hm = load_h(H, tile / tiles_per_plane / C);
+    const TileGeom g = tile_geom(hm, tile, tiles_x, tiles_per_plane, C, Ho, Wo);
+    __syncthreads();   // barrier initialised
+    if (threadIdx.x == 0 && g.sel >= 0) {
+        const uint32_t box = static_cast<uint32_t>(tile_box(g.sel));
+        mbar_expect_tx(&bar, box * box * 4u);
+        tma_load_box(stage, &maps.m[g.sel], g.c0, g.r0, g.plane, &bar);
+    }
+    const int x = g.x_lo + lane, y0 = g.y_lo + 8 * warp;
+    const bool xin = x < g.x_hi;
+    // lanes / rows beyond a partial tile recompute its last column / row: every tap stays inside the staged box
+    const ColProj cp = col_proj(hm, static_cast<float>(min(x, g.x_hi - 1)));
+    const float yg = static_cast<float>(y0), ymax = static_cast<float>(g.y_hi - 1);
+    // coverage first: it needs no source data and fills the time the box is in flight
+    bool inside = true;
+    if (kMask && g.c == 0 && y0 < g.y_hi) inside = region_inside(hm, g.x_lo, g.x_hi - 1, y0, min(y0 + 7, g.y_hi - 1), Hs, Ws);
+    const Window wd = tile_window(stage, g, src + static_cast<size_t>(g.plane) * Hs * Ws, Ws);
+    float o8[8];
+    float m_top = 1.0f, m_bot = 1.0f;
+    if (g.sel >= 0) {
+        f2 u2[4], v2[4], o2[4];
+        mbar_wait(&bar, 0u);
+        if (g.sel == 0) tile_sample8<36>(hm, cp, wd, yg, ymax, u2, v2, o2);
+        else if (g.sel == 1) tile_sample8<48>(hm, cp, wd, yg, ymax, u2, v2, o2);
+        else tile_sample8<64>(hm, cp, wd, yg, ymax, u2, v2, o2);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) upk(o2[p], o8[2 * p], o8[2 * p + 1]);
+        if (kMask && !inside) {
+            const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
+            float cv[8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float u0, u1, v0, v1;
+                upk(u2[p], u0, u1);
+                upk(v2[p], v0, v1);
+                cv[2 * p] = cover1(u0, Wsf) * cover1(v0, Hsf);
+                cv[2 * p + 1] = cover1(u1, Wsf) * cover1(v1, Hsf);
+            }
+            m_top = (cv[0] + cv[1]) + (cv[2] + cv[3]);
+            m_bot = (cv[4] + cv[5]) + (cv[6] + cv[7]);
+        }
+    } else {
+        m_top = m_bot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float u, v, rw, nw, ne, sw, se;
+            project_col(hm, cp, yg + static_cast<float>(j), u, v, rw);
+            const Taps t = make_taps_fast(u, v, Ws, Hs);
+            global_taps(t, wd.taps, Ws, nw, ne, sw, se);
+            o8[j] = blend(t, nw, ne, sw, se);
+            if (kMask) {
+                const float cvr = cover(t);
+                if (j < 4) m_top += cvr; else m_bot += cvr;
+            }
+        }
+        inside = false;
+    }
+    if (xin) {
+        float* og = out + (static_cast<size_t>(g.plane) * Ho + y0) * Wo + x;
+        if (y0 + 8 <= g.y_hi) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_stream1(og + j * Wo, o8[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (y0 + j < g.y_hi) st_stream1(og + j * Wo, o8[j]);
+        }
+    }
+    if (kMask && g.c == 0 && y0 < g.y_hi) {
+        if (!inside) {
+            m_top += __shfl_xor_sync(0xffffffffu, m_top, 1); m_top += __shfl_xor_sync(0xffffffffu, m_top, 2);
+            m_bot += __shfl_xor_sync(0xffffffffu, m_bot, 1); m_bot += __shfl_xor_sync(0xffffffffu, m_bot, 2);
+            m_top *= 0.0625f; m_bot *= 0.0625f;
+        }
+        if (xin && (lane & 3) == 0) {
+            float* mc = mask_pooled + (static_cast<size_t>(g.b) * (Ho >> 2) + (y0 >> 2)) * (Wo >> 2) + (x >> 2);
+            mc[0] = m_top;
+            if (y0 + 4 < g.y_hi) mc[Wo >> 2] = m_bot;
+        }
+    }
+}
+
+// dH partial sums of one tile.  kImage: upstream image gradient given (source box staged); kMask: pooled-mask upstream
+// (pool == 4) folded into the same pass on the tiles of channel 0.  partials[tile][9].
+template <bool kImage, bool kMask>
+__global__ void __launch_bounds__(kTileThreads, 8)
+    warp_bwd_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ src, const float* __restrict__ H,
+                         const float* __restrict__ gOut, const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C,
+                         int Hs, int Ws, int Ho, int Wo, int tiles_x, int tiles_per_plane) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float red[4][9];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finish kernel may be scheduled; it waits for this grid
+    if (kImage && threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const Hmat hm = load_h(H, tile / tiles_per_plane / C);
+    TileGeom g = tile_geom(hm, tile, tiles_x, tiles_per_plane, C, Ho, Wo);
+    if (!kImage) g.sel = -1;
+    __syncthreads();
+    if (kImage && threadIdx.x == 0 && g.sel >= 0) {
+        const uint32_t box = static_cast<uint32_t>(tile_box(g.sel));
+        mbar_expect_tx(&bar, box * box * 4u);
+        tma_load_box(stage, &maps.m[g.sel], g.c0, g.r0, g.plane, &bar);
+    }
+    const int x = g.x_lo + lane, y0 = g.y_lo + 8 * warp;
+    const bool xin = x < g.x_hi, live = xin && y0 < g.y_hi;
+    // the upstream gradients of this lane's column: issued now, consumed after the box has landed
+    float g8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g8[j] = 0.0f;
+    if (kImage && live) {
+        const float* gp = gOut + (static_cast<size_t>(g.plane) * Ho + y0) * Wo + x;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (y0 + j < g.y_hi) g8[j] = ld_stream1(gp + j * Wo);
+    }
+    bool mask_live = false;
+    float gm_top = 0.0f, gm_bot = 0.0f;
+    if (kMask && g.c == 0 && y0 < g.y_hi) {
+        mask_live = !region_inside(hm, g.x_lo, g.x_hi - 1, y0, min(y0 + 7, g.y_hi - 1), Hs, Ws);
+        if (mask_live && xin) {
+            const float* mc = gMaskPooled + (static_cast<size_t>(g.b) * (Ho >> 2) + (y0 >> 2)) * (Wo >> 2) + (x >> 2);
+            gm_top = __ldg(mc) * 0.0625f;
+            if (y0 + 4 < g.y_hi) gm_bot = __ldg(mc + (Wo >> 2)) * 0.0625f;
+        }
+    }
+    const float xf = static_cast<float>(min(x, g.x_hi - 1));
+    const ColProj cp = col_proj(hm, xf);
+    const float yg = static_cast<float>(y0), ymax = static_cast<float>(g.y_hi - 1);
+    const Window wd = tile_window(stage, g, kImage ? src + static_cast<size_t>(g.plane) * Hs * Ws : nullptr, Ws);
+    const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
+    StripSums2 t;
+    t.sa = t.say = t.sb = t.sby = t.sc = t.scy = dup2(0.0f);
+    if (kImage && g.sel >= 0) mbar_wait(&bar, 0u);
+    if (live && (kImage || mask_live)) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const f2 y2 = pk(fminf(yg + 2.0f * p, ymax), fminf(yg + (2.0f * p + 1.0f), ymax));
+            f2 u2, v2, r2, gu = dup2(0.0f), gv = dup2(0.0f);
+            project_col2(hm, cp, y2, u2, v2, r2);
+            float u0, u1, v0, v1;
+            upk(u2, u0, u1);
+            upk(v2, v0, v1);
+            if (kImage) {
+                const f2 g2 = pk(g8[2 * p], g8[2 * p + 1]);
+                f2 du, dv;
+                if (g.sel >= 0) {
+                    Cell8 c;
+                    if (g.sel == 0) c = cell_at2<36>(u2, v2, wd, false, 0);
+                    else if (g.sel == 1) c = cell_at2<48>(u2, v2, wd, false, 0);
+                    else c = cell_at2<64>(u2, v2, wd, false, 0);
+                    cell_grad2(c, du, dv);
+                } else {
+                    float d0, e0, d1, e1, nw, ne, sw, se;
+                    const Taps t0 = make_taps_fast(u0, v0, Ws, Hs), t1 = make_taps_fast(u1, v1, Ws, Hs);
+                    global_taps(t0, wd.taps, Ws, nw, ne, sw, se);
+                    blend_grad(t0, nw, ne, sw, se, d0, e0);
+                    global_taps(t1, wd.taps, Ws, nw, ne, sw, se);
+                    blend_grad(t1, nw, ne, sw, se, d1, e1);
+                    du = pk(d0, d1);
+                    dv = pk(e0, e1);
+                }
+                gu = mul2(g2, du);
+                gv = mul2(g2, dv);
+            }
+            if (kMask && mask_live) {
+                const float gm = p < 2 ? gm_top : gm_bot;
+                gu = fma2(dup2(gm), pk(cover1(v0, Hsf) * cover1_grad(u0, Wsf), cover1(v1, Hsf) * cover1_grad(u1, Wsf)), gu);
+                gv = fma2(dup2(gm), pk(cover1(u0, Wsf) * cover1_grad(v0, Hsf), cover1(u1, Wsf) * cover1_grad(v1, Hsf)), gv);
+            }
+            // rows below the output (partial tiles) carry g = 0 and gm = 0: no contribution
+            sums_add2(t, gu, gv, u2, v2, r2, y2);
+        }
+    }
+    float acc[9];
+    {
+        float sa, say, sb, sby, sc, scy, hi;
+        upk(t.sa, sa, hi); sa += hi;
+        upk(t.say, say, hi); say += hi;
+        upk(t.sb, sb, hi); sb += hi;
+        upk(t.sby, sby, hi); sby += hi;
+        upk(t.sc, sc, hi); sc += hi;
+        upk(t.scy, scy, hi); scy += hi;
+        acc[0] = sa * xf; acc[1] = say; acc[2] = sa;
+        acc[3] = sb * xf; acc[4] = sby; acc[5] = sb;
+        acc[6] = -(sc * xf); acc[7] = -scy; acc[8] = -sc;
+    }
+    float r, r8;
+    warp_reduce9(acc, r, r8);
+    if ((lane & 3) == 0) red[warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
+    if (lane == 0) red[warp][8] = r8;
+    __syncthreads();
+    if (threadIdx.x < 9)
+        partials[static_cast<size_t>(tile) * 9 + threadIdx.x] =
+            (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// =================================================================================================
 // generic + nhwc paths
 // =================================================================================================
 struct Layout {
@@ -1262,6 +1581,7 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void warp_bwd_finish_kernel(const float* __restrict__ partials, float* __restrict__ gH, int B, int chunks) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the partials are complete and visible
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 9) return;
     const int b = i / 9, k = i - b * 9;
@@ -1357,6 +1677,87 @@ inline int launch_bwd_ring(const float* src, const float* H, const float* gOut, 
     return launch_status();
 }
 
+// ---- tile path: host side ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// NCHW planes whose rows are a whole number of 16-byte units: what a tiled tensor map can describe
+inline bool tile_ok(const float* src, int Hs, int Ws, int Ho, int Wo, long long planes, int channels_last) {
+    const long long tiles = planes * blocks_of(Wo, kTile) * blocks_of(Ho, kTile);
+    return g_tune[kTuneWarpPath] == 0 && !channels_last && (Ws & 3) == 0 && aligned16(src) && Hs < (1 << 20) && Ws < (1 << 20) && Ho < (1 << 20) &&
+           Wo < (1 << 20) && planes < (1ll << 31) && tiles < (1ll << 31) - 1024 && tensor_map_encoder() != nullptr;
+}
+inline int make_tile_maps(TileMaps& maps, const float* src, long long planes, int Hs, int Ws) {
+    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(Ws), static_cast<cuuint64_t>(Hs), static_cast<cuuint64_t>(planes)};
+    const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(Ws) * 4u, static_cast<cuuint64_t>(Ws) * Hs * 4u};
+    const cuuint32_t estride[3] = {1u, 1u, 1u};
+    for (int k = 0; k < 3; ++k) {
+        const cuuint32_t box[3] = {static_cast<cuuint32_t>(tile_box(k)), static_cast<cuuint32_t>(tile_box(k)), 1u};
+        const CUresult r = tensor_map_encoder()(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3u, const_cast<float*>(src), gdim, gstride, box,
+                                                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return BH_E_UNSUPPORTED;
+    }
+    return BH_OK;
+}
+inline int launch_fwd_tile(const float* src, const float* H, float* out, float* mask_pooled, int B, int C, int Hs, int Ws, int Ho, int Wo,
+                           bool fuse_mask, cudaStream_t stream) {
+    TileMaps maps;
+    const long long planes = static_cast<long long>(B) * C;
+    int rc = make_tile_maps(maps, src, planes, Hs, Ws);
+    if (rc != BH_OK) return rc;
+    const int tiles_x = blocks_of(Wo, kTile), tpp = tiles_x * blocks_of(Ho, kTile);
+    auto kern = fuse_mask ? warp_fwd_tile_kernel<true> : warp_fwd_tile_kernel<false>;
+    kern<<<static_cast<unsigned>(planes * tpp), kTileThreads, kTileSmem, stream>>>(maps, src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo, tiles_x, tpp);
+    return launch_status();
+}
+inline int tile_bwd_chunks(int Cw, int Ho, int Wo) { return Cw * blocks_of(Wo, kTile) * blocks_of(Ho, kTile); }
+inline int launch_bwd_tile(const float* src, const float* H, const float* gOut, const float* gMaskPooled, float* partials, int B, int Cw,
+                           int Hs, int Ws, int Ho, int Wo, cudaStream_t stream) {
+    TileMaps maps;
+    const long long planes = static_cast<long long>(B) * Cw;
+    if (gOut) {
+        int rc = make_tile_maps(maps, src, planes, Hs, Ws);
+        if (rc != BH_OK) return rc;
+    } else {
+        memset(&maps, 0, sizeof(maps));
+    }
+    const int tiles_x = blocks_of(Wo, kTile), tpp = tiles_x * blocks_of(Ho, kTile);
+    void (*kern)(const TileMaps, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int);
+    if (gOut && gMaskPooled) kern = warp_bwd_tile_kernel<true, true>;
+    else if (gOut) kern = warp_bwd_tile_kernel<true, false>;
+    else kern = warp_bwd_tile_kernel<false, true>;
+    kern<<<static_cast<unsigned>(planes * tpp), kTileThreads, gOut ? kTileSmem : 0, stream>>>(maps, src, H, gOut, gMaskPooled, partials, Cw, Hs, Ws,
+                                                                                            Ho, Wo, tiles_x, tpp);
+    return launch_status();
+}
+// the fixed-order sum behind a programmatic dependent launch: its blocks are resident when the producer grid drains
+inline int launch_bwd_finish(const float* partials, float* gH, int B, int chunks, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((B * 9 + 127) / 128);
+    cfg.blockDim = dim3(128);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, warp_bwd_finish_kernel, partials, gH, B, chunks);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    return launch_status();
+}
+
 }  // namespace bh
 
 extern "C" int bh_warp_fwd(const float* src, const float* H, float* out, float* mask_pooled, int B, int C, int Hs, int Ws,
@@ -1373,7 +1774,11 @@ extern "C" int bh_warp_fwd(const float* src, const float* H, float* out, float* 
     bool mask_done = (mask_pooled == nullptr);
     if (src) {
         const long long n_items64 = static_cast<long long>(B) * C * blocks_of(Wo, 64) * blocks_of(Ho, 64);
-        if (ring_ok(Hs, Ws, Ho, Wo, channels_last) && n_items64 < (1ll << 31) - 1024) {
+        if (tile_ok(src, Hs, Ws, Ho, Wo, static_cast<long long>(B) * C, channels_last)) {
+            const bool fuse_mask = mask_pooled && pool == 4 && (Ho % 4) == 0 && (Wo % 4) == 0;
+            rc = launch_fwd_tile(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream);
+            mask_done = mask_done || fuse_mask;
+        } else if (ring_ok(Hs, Ws, Ho, Wo, channels_last) && n_items64 < (1ll << 31) - 1024) {
             const bool fuse_mask = mask_pooled && pool == 4;
             rc = ring_blk(Hs, Ws) == 128 ? launch_fwd_ring<128>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream)
                                          : launch_fwd_ring<64>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream);
@@ -1407,7 +1812,9 @@ extern "C" size_t bh_warp_bwd_workspace_bytes(int B, int C, int Hs, int Ws, int 
     const int Cw = C > 0 ? C : 1;
     const int rc64 = ring_bwd_chunks<64>(Cw, Ho, Wo), rc128 = ring_bwd_chunks<128>(Cw, Ho, Wo);
     const size_t ring = static_cast<size_t>(B) * (rc64 > rc128 ? rc64 : rc128) * 9 * sizeof(float);
-    return generic > ring ? generic : ring;
+    const size_t tile = static_cast<size_t>(B) * tile_bwd_chunks(Cw, Ho, Wo) * 9 * sizeof(float);
+    const size_t m = generic > ring ? generic : ring;
+    return m > tile ? m : tile;
 }
 
 extern "C" int bh_warp_bwd(const float* src, const float* H, const float* gOut, const float* gMaskPooled, float* gH,
@@ -1425,6 +1832,16 @@ extern "C" int bh_warp_bwd(const float* src, const float* H, const float* gOut, 
     const bool mask4 = gMaskPooled == nullptr || pool == 4;
     const int Cw = gOut ? C : 1;   // coverage-only work has one "plane" per sample
     const long long n_items64 = static_cast<long long>(B) * Cw * blocks_of(Wo, 64) * blocks_of(Ho, 64);
+    const bool mask4_tiles = gMaskPooled == nullptr || (pool == 4 && (Ho % 4) == 0 && (Wo % 4) == 0);
+    if (!gSrc && mask4_tiles && tile_ok(gOut ? src : H, Hs, gOut ? Ws : 4, Ho, Wo, static_cast<long long>(B) * Cw, gOut ? channels_last : 0)) {
+        const int chunks = tile_bwd_chunks(Cw, Ho, Wo);
+        const size_t need = static_cast<size_t>(B) * chunks * 9 * sizeof(float);
+        if (!workspace || workspace_bytes < need) return BH_E_WORKSPACE;
+        float* partials = static_cast<float*>(workspace);
+        const int rc = launch_bwd_tile(src, H, gOut, gMaskPooled, partials, B, Cw, Hs, Ws, Ho, Wo, stream);
+        if (rc != BH_OK) return rc;
+        return launch_bwd_finish(partials, gH, B, chunks, stream);
+    }
     if (!gSrc && mask4 && ring_ok(Hs, Ws, Ho, Wo, gOut ? channels_last : 0) && n_items64 < (1ll << 31) - 1024) {
         const bool planes = ring_blk(Hs, Ws) == 128;
         const int chunks = planes ? ring_bwd_chunks<128>(Cw, Ho, Wo) : ring_bwd_chunks<64>(Cw, Ho, Wo);

@@ -152,7 +152,17 @@ class GpuPairLoader:
         return {'patch_1': p1, 'patch_2': p2, 'delta': delta, 'corners': corners.float(), 'target': target}
 
     def __iter__(self):
-        for _ in range(self.steps):
+        return self.batches(self.steps)
+
+    def batches(self, n):
+        """the next n batches of the stream (a resumed run finishes a partially trained epoch with fewer than len(self))"""
+        for _ in range(int(n)):
+            yield self.next_batch()
+
+    def shard(self, rank, world):
+        """batches rank, rank + world, ... of one epoch of the stream that starts at step 0 (data-parallel evaluation)"""
+        for i in range(int(rank), self.steps, int(world)):
+            self.step = i
             yield self.next_batch()
 
 

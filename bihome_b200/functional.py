@@ -59,6 +59,11 @@ class _timed:
         return False
 
 
+def tune(key, value):
+    """microbenchmark / test switch (bh_tune_set in include/bihome_b200.h); 0 restores the default choice"""
+    cabi.check(cabi.lib().bh_tune_set(str(key).encode(), int(value)), 'bh_tune_set')
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 

@@ -100,8 +100,8 @@ int bh_warp_bwd(const float* src, const float* H, const float* gOut, const float
  * launch when gscale[b] == 1 -- the autograd backward calls it with the upstream gradient.
  * One or two stream-ordered launches depending on layout and batch (cluster kernel; TMA-ring cluster kernel; persistent
  * TMA stream + per-sample finish -- DESIGN.md section 4); g_m1w / g_m2w double as scratch between them, every output is
- * final when the call's last launch completes.  Tuning knobs read from the environment at call time, for the
- * microbenchmark only: BH_LOSS_VARIANT = ldg | cluster | stream, BH_LOSS_CL = 1 | 2 | 4 | 8.
+ * final when the call's last launch completes.  The kernel is chosen from the arguments alone (bh_tune_set below can
+ * force one for the microbenchmark).
  * ------------------------------------------------------------------------------------------- */
 int bh_bihome_fwd_bwd(const float* f1, const float* f2, const float* f1w, const float* f2w, const float* m1,
                       const float* m2, const float* m1w, const float* m2w, const float* H12, const float* H21,
@@ -189,6 +189,17 @@ int bh_fieldhead_affine(const float* x, const float* a, const float* M, float* g
  * out: 1 float (overwritten).
  * ------------------------------------------------------------------------------------------- */
 int bh_mace(const float* delta_gt, const float* delta_hat, float* out, int B, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Microbenchmark-only switch (tools/microbench.py): forces one of several equivalent kernels behind an entry point so
+ * that they can be timed against each other.  Process-global; every key defaults to 0 = "choose from the arguments",
+ * which is the only state the product path (bihome_b200/, train.py, eval.py, bench.py) ever runs in.
+ *   "warp_path"    0 tile kernels (TMA box per 32x32 tile), 1 the persistent ring kernels
+ *   "loss_variant" 0 auto, 1 ldg cluster kernel, 2 TMA cluster kernel, 3 persistent TMA stream
+ *   "loss_cluster" 0 auto, 1 | 2 | 4 | 8 CTAs per cluster
+ * returns BH_E_UNSUPPORTED for an unknown key.
+ * ------------------------------------------------------------------------------------------- */
+int bh_tune_set(const char* key, int value);
 
 #ifdef __cplusplus
 }

@@ -77,3 +77,50 @@ def test_rank_seeded_loaders_use_disjoint_streams():
     from bihome_b200.data.gpu_pairs import rank_seed
     assert len({rank_seed(42, r) for r in range(8)}) == 8
     assert rank_seed(42, 0) != rank_seed(43, 0)
+
+
+class BnNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(1, 3, 3, padding=1)
+        self.bn = torch.nn.BatchNorm2d(3)
+
+    def forward(self, x):
+        return self.bn(self.conv(x)).square().mean()
+
+
+def bn_worker(rank, world, port, out):
+    from bihome_b200 import engine
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = BnNet()
+    ddp = engine.data_parallel(model)              # the wrapper train.py and bench.py use
+    x = torch.randn(6, 1, 8, 8, generator=torch.Generator().manual_seed(10 + rank)) + 3.0 * rank
+    for _ in range(2):                             # the second forward is where broadcast_buffers=True would overwrite
+        ddp(x).backward()
+    torch.save({'mean': model.bn.running_mean.clone(), 'var': model.bn.running_var.clone(),
+                'grad': model.conv.weight.grad.clone()}, out + str(rank))
+    dist.destroy_process_group()
+
+
+def test_batchnorm_statistics_stay_rank_local(tmp_path):
+    """no SyncBN and no buffer broadcast -- every rank keeps the running statistics of ITS batches
+    (the reference's per-GPU BatchNorm), while gradients are still averaged."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / 'bn.pt')
+    mp.spawn(bn_worker, args=(2, port, out), nprocs=2, join=True)
+    got = [torch.load(out + str(r)) for r in range(2)]
+    assert not torch.allclose(got[0]['mean'], got[1]['mean'], atol=1e-3)
+    assert torch.allclose(got[0]['grad'], got[1]['grad'])
+    for rank in range(2):
+        torch.manual_seed(0)
+        model = BnNet()
+        x = torch.randn(6, 1, 8, 8, generator=torch.Generator().manual_seed(10 + rank)) + 3.0 * rank
+        for _ in range(2):
+            model(x)
+        assert torch.allclose(got[rank]['mean'], model.bn.running_mean, atol=1e-6)
+        assert torch.allclose(got[rank]['var'], model.bn.running_var, atol=1e-6)

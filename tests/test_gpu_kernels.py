@@ -149,8 +149,16 @@ def _kernel_cells(H32, Ho, Wo):
     return torch.from_numpy(np.floor(u)), torch.from_numpy(np.floor(v))
 
 
+@pytest.fixture(params=['tile', 'ring'])
+def warp_path(request, F):
+    """both NCHW implementations behind bh_warp_fwd / bh_warp_bwd: the tile kernels (default) and the persistent ring"""
+    F.tune('warp_path', 1 if request.param == 'ring' else 0)
+    yield request.param
+    F.tune('warp_path', 0)
+
+
 @pytest.mark.parametrize('B,C,Hs,Ws,Ho,Wo,nhwc', WARP_SHAPES)
-def test_warp_paths_vs_oracle(F, B, C, Hs, Ws, Ho, Wo, nhwc):
+def test_warp_paths_vs_oracle(F, warp_path, B, C, Hs, Ws, Ho, Wo, nhwc):
     gen = torch.Generator().manual_seed(B * 1000 + C)
     img = torch.rand(B, C, Hs, Ws, generator=gen, dtype=torch.float64).float().double()
     H = _rand_h(B, min(Hs, Ws), gen).float().double()
@@ -200,7 +208,7 @@ def _warp_direct_autograd(img, H, Ho, Wo, cells=None):
 
 
 @pytest.mark.parametrize('pool', [1, 2, 4, 8])
-def test_pooled_mask_and_gradient(F, pool):
+def test_pooled_mask_and_gradient(F, warp_path, pool):
     gen = torch.Generator().manual_seed(pool)
     B, P = 6, 64
     H = _rand_h(B, P, gen, scale=0.4)
@@ -236,6 +244,8 @@ def test_rejects_cpu_tensors(F):
 
 
 # ----------------------------------------------------------------------------------------------- K3
+LOSS_VARIANTS = {'ldg': 1, 'cluster': 2, 'stream': 3}      # bh_tune_set("loss_variant", .)
+
 def _loss_inputs(B, C, h, w, seed, user_masks=False):
     gen = torch.Generator().manual_seed(seed)
     f = [torch.relu(torch.randn(B, C, h, w, generator=gen, dtype=torch.float64)) for _ in range(4)]
@@ -305,9 +315,12 @@ def test_bihome_loss_vs_oracle(F, B, C, h, w, nhwc, user_masks, in_grads):
 ])
 def test_bihome_loss_channels_last_variants(F, monkeypatch, variant, B, C, h, w, user_masks, in_grads):
     """the three channels-last kernels (cluster + LDG, cluster + TMA ring, persistent TMA stream + finish) against the
-    float64 oracle on the same inputs; BH_LOSS_VARIANT is the library's tuning knob (read at every call)"""
-    monkeypatch.setenv('BH_LOSS_VARIANT', variant)
-    test_bihome_loss_vs_oracle(F, B, C, h, w, True, user_masks, in_grads)
+    float64 oracle on the same inputs; bh_tune_set("loss_variant") is the library's microbenchmark switch"""
+    F.tune('loss_variant', LOSS_VARIANTS[variant])
+    try:
+        test_bihome_loss_vs_oracle(F, B, C, h, w, True, user_masks, in_grads)
+    finally:
+        F.tune('loss_variant', 0)
 
 
 def test_bihome_loss_variants_agree_on_gradients(F, monkeypatch):
@@ -317,11 +330,12 @@ def test_bihome_loss_variants_agree_on_gradients(F, monkeypatch):
     cl = lambda t: t.float().cuda().contiguous(memory_format=torch.channels_last)
     outs = []
     for variant in ('ldg', 'cluster', 'stream'):
-        monkeypatch.setenv('BH_LOSS_VARIANT', variant)
+        F.tune('loss_variant', LOSS_VARIANTS[variant])
         a = [cl(f[2]).requires_grad_(True), cl(f[3]).requires_grad_(True)]
         loss_b, _ = F.bihome_loss(cl(f[0]), cl(f[1]), a[0], a[1], m1w.float().cuda(), m2w.float().cuda(), H12.float().cuda(),
                                   H21.float().cuda(), 0.01)
         outs.append(torch.autograd.grad(loss_b.sum(), a))
+    F.tune('loss_variant', 0)
     for other in outs[1:]:
         assert torch.allclose(outs[0][0], other[0], rtol=2e-6, atol=0) and torch.allclose(outs[0][1], other[1], rtol=2e-6, atol=0)
 

@@ -9,7 +9,9 @@ import numpy as np
 import pytest
 import torch
 
+import cpu_kernels
 from conftest import rel_l2
+from test_gpu_kernels import _kernel_cells, _warp_direct_autograd
 from test_head_mirrors import PERCEPTUAL_CASES, TRIPLET_CASES, perceptual_backbone, perceptual_kwargs, triplet_forward
 
 pytestmark = pytest.mark.gpu
@@ -49,15 +51,65 @@ def test_perceptual_variants_golden(golden, name):
         assert rel_l2(grads[1].cpu().numpy(), g[name + '_g21_64']) < tol
 
 
+def _one_sided_reference(g, name, monkeypatch, H_device):
+    """The reference's float64 evaluation with every bilinear cell fixed to the one the kernel picked.
+
+    d out/dH is one-sided where a sampling coordinate sits on an integer.  The fixture's third sample has such a pixel:
+    u(y=9, x=16) is 1.7e-7 px from an integer, below float32 resolution at that coordinate (1e-6), so float32 and
+    float64 evaluations may legitimately land in neighbouring cells there; the value is continuous, the derivative
+    jumps (3.6e-3 of that sample's gradient -- the whole of round 1's failure, reproduced on CPU by
+    tools/debug_triplet.py).  Either one-sided derivative is a valid answer at such a pixel, and only there."""
+    F = cpu_kernels.install(monkeypatch)
+    cells = _kernel_cells(H_device, 32, 32)
+
+    def warp_fixed(src, H, out_h, out_w, pool=None):
+        out = _warp_direct_autograd(src, H, out_h, out_w, cells if H.shape[0] == cells[0].shape[0] else
+                                    tuple(c[:H.shape[0]] for c in cells))
+        if pool:
+            return out, cpu_kernels.coverage_mask(H, src.shape[-2:], (out_h, out_w), pool)
+        return out
+    monkeypatch.setattr(F, 'warp', warp_fixed)
+    _, g12, g21, _, _ = triplet_forward(g, name, torch.float64, 'cpu')
+    return g12.numpy(), None if g21 is None else g21.numpy()
+
+
+def _knife_edge_samples(g, P=32, eps=2e-6):
+    """indices into cat(delta_12, delta_21) whose sampling grid has a coordinate within float32 resolution of an integer"""
+    d = torch.cat([torch.as_tensor(g['delta_12']), torch.as_tensor(g['delta_21'])]).double()
+    h = cpu_kernels.dlt4(d, size=(P, P)).reshape(-1, 9).numpy()[:, :, None, None]
+    ys, xs = np.meshgrid(np.arange(float(P)), np.arange(float(P)), indexing='ij')
+    w = h[:, 6] * xs + h[:, 7] * ys + h[:, 8]
+    u = (h[:, 0] * xs + h[:, 1] * ys + h[:, 2]) / w
+    v = (h[:, 3] * xs + h[:, 4] * ys + h[:, 5]) / w
+    near = np.minimum(np.abs(u - np.round(u)), np.abs(v - np.round(v))).reshape(len(d), -1).min(1)
+    return [int(i) for i in np.nonzero(near < eps)[0]]
+
+
+def _assert_grad(got, golden64, one_sided, knife, offset):
+    for b in range(golden64.shape[0]):
+        err = rel_l2(got[b], golden64[b])
+        if (b + offset) in knife:
+            err = min(err, rel_l2(got[b], one_sided[b]))
+        assert err < GRAD_TOL, (b, err)
+
+
 @pytest.mark.parametrize('name', sorted(TRIPLET_CASES))
-def test_triplet_head_golden(golden, name):
+def test_triplet_head_golden(golden, name, monkeypatch):
+    import bihome_b200.functional as F
     g = golden('triplet_head_P32.npz')
+    knife = _knife_edge_samples(g)
+    assert knife == [2]                      # documented above; any other sample must match the golden as is
     loss, g12, g21, gnorm, conv1 = triplet_forward(g, name, torch.float32, 'cuda')
+    d = torch.cat([cu(g['delta_12']), cu(g['delta_21'])])
+    H_device = F.dlt4(d, size=(32, 32)).cpu().numpy()
     ref = float(g[name + '_loss64'])
     assert abs(loss.item() - ref) < LOSS_TOL * abs(ref)
-    assert rel_l2(g12.cpu().numpy(), g[name + '_g12_64']) < GRAD_TOL
+    B = g['delta_12'].shape[0]
+    s12, s21 = _one_sided_reference(g, name, monkeypatch, H_device)
+    _assert_grad(g12.cpu().numpy(), g[name + '_g12_64'], s12, knife, 0)
     if g21 is not None:
-        assert rel_l2(g21.cpu().numpy(), g[name + '_g21_64']) < GRAD_TOL
+        _assert_grad(g21.cpu().numpy(), g[name + '_g21_64'], s21, knife, B)
+    # parameter gradients depend on the warped VALUES only (continuous across cells): compared as they are
     assert abs(gnorm - float(g[name + '_gparam_norm64'])) < GRAD_TOL * float(g[name + '_gparam_norm64'])
     assert rel_l2(conv1.cpu().numpy(), g[name + '_gfe_conv1_64']) < GRAD_TOL
 

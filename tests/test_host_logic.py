@@ -187,3 +187,52 @@ def test_checkpoints_are_interchangeable_with_the_reference_checkpointer(tmp_pat
             assert torch.equal(a, b), k
         assert s2.state_dict() == s1.state_dict()
         assert o2.state_dict()['param_groups'] == o1.state_dict()['param_groups']
+
+
+def test_reference_optimizer_state_loads_into_the_engine(tmp_path):
+    """the 'optimizer' entry of a reference-written model_%06d.pth (Adam over ALL model.parameters(), frozen extractor
+    included: reference train.py:703-707) must fit engine.build_optimizer's param groups, and the other way round --
+    a real biHomE config, not a toy model (build container only)"""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip('reference tree not present')
+    RefCheckPointer = ref_import.load('src.utils.checkpoint').CheckPointer
+    from bihome_b200 import engine
+    from bihome_b200.utils.checkpoint import CheckPointer
+    cfg = engine.load_config(os.path.join(ROOT, 'config', 's-coco', 'detone-bihome-lr-5e-3.yaml'))
+    bcfg, hcfg = dict(cfg['MODEL']['BACKBONE']), dict(cfg['MODEL']['HEAD'])
+    bcfg['PRETRAINED_RESNET'] = False
+
+    def ref_trio():
+        rb = ref_import.load('src.backbones.' + bcfg['NAME']).Model(**bcfg)
+        model = torch.nn.Sequential(rb, ref_import.load('src.heads.' + hcfg['NAME']).Model(rb, **hcfg))
+        s = cfg['SOLVER']
+        opt = torch.optim.Adam(model.parameters(), lr=s['LR'], betas=(s['MOMENTUM_1'], s['MOMENTUM_2']), weight_decay=0)
+        return model, opt, torch.optim.lr_scheduler.MultiStepLR(opt, milestones=s['MILESTONES'], gamma=s['LR_DECAY'])
+
+    def our_trio():
+        model = engine.build_model(cfg, pretrained=False)
+        return (model,) + engine.build_optimizer(cfg, model)
+
+    def one_step(model, opt, sched):
+        for p in model.parameters():
+            if p.requires_grad:
+                p.grad = torch.full_like(p, 1e-3)
+        opt.step()
+        sched.step()
+
+    for make_w, W, make_r, R, sub in ((ref_trio, RefCheckPointer, our_trio, CheckPointer, 'ref_to_ours'),
+                                      (our_trio, CheckPointer, ref_trio, RefCheckPointer, 'ours_to_ref')):
+        d = str(tmp_path / sub)
+        os.makedirs(d, exist_ok=True)
+        m1, o1, s1 = make_w()
+        one_step(m1, o1, s1)
+        W(m1, o1, s1, d, save_to_disk=True, device='cpu').save('model_000001', step=1)
+        m2, o2, s2 = make_r()
+        assert R(m2, o2, s2, d, save_to_disk=False, device='cpu').load()['step'] == 1
+        sd1, sd2 = o1.state_dict(), o2.state_dict()
+        assert sd1['param_groups'] == sd2['param_groups']
+        assert sorted(sd1['state']) == sorted(sd2['state']) and len(sd1['state']) > 0
+        for k in sd1['state']:
+            assert torch.equal(sd1['state'][k]['exp_avg'], sd2['state'][k]['exp_avg'])
+        one_step(m2, o2, s2)          # and training goes on

@@ -71,16 +71,18 @@ def report(name, shape, ms, nbytes):
                       'frac_of_measured_peak': round(gbs / PEAK, 3)}), flush=True)
 
 
-def rand_h(B, P):
-    d = (torch.rand(B, 4, 2, device='cuda') * 2 - 1) * (P / 4)
+def rand_h(B, P, scale=0.25):
+    d = (torch.rand(B, 4, 2, device='cuda') * 2 - 1) * (P * scale)
     return F.dlt4(d, size=(P, P)), d
 
 
-def bench_image_warp(B, P, t):
+def bench_image_warp(B, P, t, scale=0.25, tag=''):
     """north-star path: 1-channel patches, both directions batched (2B planes), pooled 4x4 mask fused.
-    Timed as raw C-ABI calls on preallocated buffers (the autograd wrapper costs ~50 us of CPU per call)."""
+    Timed as raw C-ABI calls on preallocated buffers (the autograd wrapper costs ~50 us of CPU per call).
+    scale: corner offsets are U(-scale P, scale P) -- 0.25 is the data set's worst case (rho = 32 at P = 128), 0.02 what an
+    untrained network predicts (bench.py's in-situ launches)."""
     img = torch.rand(2 * B, 1, P, P, device='cuda')
-    H, _ = rand_h(2 * B, P)
+    H, _ = rand_h(2 * B, P, scale)
     H = H.detach().contiguous()
     out, mask = torch.empty_like(img), torch.empty(2 * B, P // 4, P // 4, device='cuda')
     gO, gM = torch.randn_like(out), torch.randn_like(mask)
@@ -95,9 +97,17 @@ def bench_image_warp(B, P, t):
     def bwd():
         cabi.check(LIB.bh_warp_bwd(ptr(img), ptr(H), ptr(gO), ptr(gM), ptr(gH), None, 2 * B, 1, P, P, P, P, 4, 0, ptr(ws), nws, st), 'bwd')
     pair = 2 * (4 * P * P + 4 * P * P + 4 * (P // 4) ** 2)            # read src + write out + write pooled mask, 2 directions
-    report('warp_fwd(image+mask)', {'B': B, 'P': P}, t(fwd), pair * B)
+    report('warp_fwd(image+mask)' + tag, {'B': B, 'P': P, 'offsets': scale}, t(fwd), pair * B)
     pairb = 2 * (4 * P * P + 4 * P * P + 4 * (P // 4) ** 2 + 36)
-    report('warp_bwd(dH)', {'B': B, 'P': P}, t(bwd), pairb * B)
+    report('warp_bwd(dH)' + tag, {'B': B, 'P': P, 'offsets': scale}, t(bwd), pairb * B)
+
+
+def bench_copy(B, P, t):
+    """calibration: a device-to-device copy of the same 2B planes (read + write = the warp's traffic minus the masks) --
+    what fraction of the 2 GiB-copy peak of MEASURED_PEAKS.json a transfer of this size can reach at all"""
+    a = torch.rand(2 * B, 1, P, P, device='cuda')
+    b = torch.empty_like(a)
+    report('copy (same planes, torch copy_)', {'B': B, 'P': P}, t(lambda: b.copy_(a)), 2 * a.numel() * 4)
 
 
 def bench_feature_warp(B, P, C, t):
@@ -200,22 +210,27 @@ def main():
         return
     if a.loss_cl:
         for cl in (1, 2, 4, 8):
-            os.environ['BH_LOSS_CL'] = str(cl)
-            print(json.dumps({'BH_LOSS_CL': cl}))
+            F.tune('loss_cluster', cl)
+            print(json.dumps({'loss_cluster': cl}))
             for B in (256, 1024):
                 bench_loss(B, 128, 64, t, True)
                 bench_loss(B, 128, 64, t, False)
-        os.environ.pop('BH_LOSS_CL')
-        for var in ('ldg', 'cluster', 'stream'):
-            os.environ['BH_LOSS_VARIANT'] = var
-            print(json.dumps({'BH_LOSS_VARIANT': var}))
+        F.tune('loss_cluster', 0)
+        for k, var in enumerate(('ldg', 'cluster', 'stream')):
+            F.tune('loss_variant', k + 1)
+            print(json.dumps({'loss_variant': var}))
             for B in (256, 1024, 4096):
                 bench_loss(B, 128, 64, t, True)
-        os.environ.pop('BH_LOSS_VARIANT')
+        F.tune('loss_variant', 0)
         return
     if a.warp_only:
         for B, P in ((256, 128), (1024, 128), (4096, 128), (256, 256), (64, 512)):
-            bench_image_warp(B, P, t)
+            bench_copy(B, P, t)
+            for path, tag in ((0, ' [tile]'), (1, ' [ring]')):
+                F.tune('warp_path', path)
+                for scale in (0.02, 0.25):
+                    bench_image_warp(B, P, t, scale, tag)
+            F.tune('warp_path', 0)
         return
     print(json.dumps({'peak_GBps_measured': PEAK, 'timing': 'cuda events, L2 flushed (256 MB written, then 256 MB read: clean lines) before every launch, mean of %d' % a.iters}))
     shapes = [(256, 128, 64)]

@@ -85,8 +85,12 @@ def forward_loss(model, data, loss_fn):
 def train_one_epoch(model, loader, optimizer, gradient_clip, scheduler, loss_fn, epoch, steps_per_epoch, checkpointer,
                     checkpoint_arguments, log_step, summary_writer, self_supervised=False, log_verbose=False, max_steps=None):
     model.train()
-    step = epoch * steps_per_epoch
-    for iter_no, data in enumerate(loader):
+    # a checkpoint written in the middle of an epoch (--max_steps) resumes at the iteration after it: no step is repeated
+    # and no TensorBoard step number is reused
+    skip = min(max(checkpoint_arguments['step'] - epoch * steps_per_epoch, 0), steps_per_epoch)
+    step = epoch * steps_per_epoch + skip
+    batches = loader.batches(steps_per_epoch - skip) if hasattr(loader, 'batches') else loader
+    for iter_no, data in enumerate(batches, start=skip):
         step = epoch * steps_per_epoch + iter_no + 1
         logging_step = step % log_step == 0
         optimizer.zero_grad(set_to_none=True)
@@ -117,19 +121,32 @@ def train_one_epoch(model, loader, optimizer, gradient_clip, scheduler, loss_fn,
     return step
 
 
-def eval_one_epoch(model, loader, loss_fn, epoch, steps_per_epoch, summary_writer, self_supervised=False, log_verbose=False):
+def eval_one_epoch(model, loader, loss_fn, epoch, steps_per_epoch, summary_writer, self_supervised=False, log_verbose=False,
+                   rank=0, world=1):
+    """reference train.py:432-487.  Under DDP the test batches are dealt round-robin to the ranks (batch i of the seeded
+    test stream goes to rank i % world) and the three sums meet in one all-reduce: no rank idles in a collective while
+    rank 0 evaluates alone, and the mean is the one a single process computes."""
     model.eval()
     losses, maces = [], []
     with torch.no_grad():
-        for iter_no, data in enumerate(loader):
+        shard = loader.shard(rank, world) if world > 1 else loader
+        for iter_no, data in enumerate(shard):
             loss, delta_gt, delta_hat = forward_loss(model, data, loss_fn)
             losses.append(loss.detach().float())
             if self_supervised and delta_gt is not None:
                 maces.append(F.mace(delta_gt.float(), delta_hat.float()))
             if log_verbose:
                 print('Epoch: {} iter: {}/{} loss: {}'.format(epoch, iter_no + 1, len(loader), loss.item()))
-    mean_loss = float(torch.stack(losses).mean()) if losses else float('nan')
-    mean_mace = float(torch.stack(maces).mean()) if maces else float('nan')
+    dev = next(model.parameters()).device
+    zero = torch.zeros((), device=dev)
+    sums = torch.stack([torch.stack(losses).sum() if losses else zero, zero + len(losses),
+                        torch.stack(maces).sum() if maces else zero, zero + len(maces)]).double()
+    if world > 1:
+        dist.all_reduce(sums)
+    sums = sums.tolist()
+    mean_loss = sums[0] / sums[1] if sums[1] else float('nan')
+    mean_mace = sums[2] / sums[3] if sums[3] else float('nan')
+    maces = sums[3] > 0
     summary_writer.add_scalars('loss', {'test': mean_loss}, (epoch + 1) * steps_per_epoch)
     if maces:
         summary_writer.add_scalars('mace', {'test': mean_mace}, (epoch + 1) * steps_per_epoch)
@@ -139,9 +156,11 @@ def eval_one_epoch(model, loader, loss_fn, epoch, steps_per_epoch, summary_write
 
 def do_train(model, train_loader, test_loader, optimizer, gradient_clip, scheduler, loss_fn, epochs, steps_per_epoch,
              checkpointer, checkpoint_arguments, log_dir='logs', log_step=1, self_supervised=False, log_verbose=False,
-             rank=0, max_steps=None):
+             rank=0, max_steps=None, world=1):
     writer = make_summary_writer(log_dir, enabled=rank == 0)
     start_epoch = checkpoint_arguments['step'] // steps_per_epoch
+    if hasattr(train_loader, 'step'):
+        train_loader.step = checkpoint_arguments['step']      # the pair stream continues where the checkpoint left it
     for epoch in range(start_epoch, epochs):
         if rank == 0:
             print('Training epoch: {}'.format(epoch))
@@ -153,12 +172,14 @@ def do_train(model, train_loader, test_loader, optimizer, gradient_clip, schedul
             done = step - epoch * steps_per_epoch
             print('  {} steps in {:.1f} s ({:.0f} image pairs/s per GPU)'.format(
                 done, time.perf_counter() - t0, done * train_loader.batch_size / (time.perf_counter() - t0)))
-        if test_loader is not None and rank == 0:
-            print('Testing epoch: {}'.format(epoch))
+        if test_loader is not None:
+            if rank == 0:
+                print('Testing epoch: {}'.format(epoch))
             test_loader.step = 0        # the same test pairs every epoch (reference: seeded sampler + seeded transforms)
             mean_loss, mean_mace = eval_one_epoch(_plain(model), test_loader, loss_fn, epoch, steps_per_epoch, writer,
-                                                  self_supervised, log_verbose)
-            print('  test loss {:.4f}  MACE {:.4f}'.format(mean_loss, mean_mace))
+                                                  self_supervised, log_verbose, rank, world)
+            if rank == 0:
+                print('  test loss {:.4f}  MACE {:.4f}'.format(mean_loss, mean_mace))
         if max_steps is not None and step >= max_steps:
             break
     writer.close()
@@ -168,7 +189,7 @@ def _plain(model):
     return model.module if isinstance(model, torch.nn.parallel.DistributedDataParallel) else model
 
 
-def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, channels_last=True, log_dir=None):
+def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, channels_last=True, log_dir=None, init_seed=0):
     config = engine.load_config(config_file_path)
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
@@ -184,7 +205,7 @@ def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, 
     test_loader = make_pair_loader(config, 'test', device, 0, batch_size, max(8, synthetic_pool // 8)) \
         if 'TEST_SPLIT' in config['DATA'] else None
 
-    torch.manual_seed(0)            # identical initial weights on every rank
+    torch.manual_seed(init_seed)    # identical initial weights on every rank (--init_seed; the reference leaves it unseeded)
     model = engine.build_model(config).to(device)
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
@@ -198,7 +219,9 @@ def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, 
 
     log_dir = log_dir or config['LOGGING']['DIR']
     restart_lr = 'RESTART_LEARNING_RATE' in solver and solver['RESTART_LEARNING_RATE']
-    checkpointer = CheckPointer(model, None if restart_lr else optimizer, None if restart_lr else scheduler, log_dir,
+    # reference train.py:723-728: RESTART_LEARNING_RATE withholds the optimizer only; the scheduler is always restored, so
+    # the milestones stay aligned with the global step
+    checkpointer = CheckPointer(model, None if restart_lr else optimizer, scheduler, log_dir,
                                 save_to_disk=rank == 0, device=str(device))
     extra = checkpointer.load()
     arguments = {'step': 0}
@@ -207,16 +230,17 @@ def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, 
         blob = torch.load(config['MODEL']['PRETRAINED'], map_location='cpu', weights_only=False)
         model.load_state_dict(blob['model'])
     if restart_lr:
-        checkpointer.optimizer, checkpointer.scheduler = optimizer, scheduler
+        checkpointer.optimizer = optimizer
 
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        net = engine.data_parallel(model, local)
         checkpointer.model = net
     self_supervised = 'SELF_SUPERVISED' in config['DATA'] and config['DATA']['SELF_SUPERVISED'] or isinstance(loss_fn, str)
     do_train(net, train_loader, test_loader, optimizer, gradient_clip, scheduler, loss_fn, solver['NUM_EPOCHS'],
              len(train_loader), checkpointer, arguments, log_dir=log_dir, log_step=config['LOGGING']['STEP'],
-             self_supervised=self_supervised, log_verbose=config['LOGGING'].get('VERBOSE', False), rank=rank, max_steps=max_steps)
+             self_supervised=self_supervised, log_verbose=config['LOGGING'].get('VERBOSE', False), rank=rank, max_steps=max_steps,
+             world=world)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -230,5 +254,6 @@ if __name__ == '__main__':
     ap.add_argument('--synthetic_pool', type=int, default=256, help='synthetic images per GPU when the dataset is absent')
     ap.add_argument('--log_dir', type=str, default=None, help='override LOGGING.DIR')
     ap.add_argument('--nchw', dest='channels_last', action='store_false')
+    ap.add_argument('--init_seed', type=int, default=0, help='torch seed for the initial weights (same on every rank)')
     a = ap.parse_args()
-    main(a.config_file, a.batch_size, a.max_steps, a.synthetic_pool, a.channels_last, a.log_dir)
+    main(a.config_file, a.batch_size, a.max_steps, a.synthetic_pool, a.channels_last, a.log_dir, a.init_seed)
