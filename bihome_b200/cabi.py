@@ -25,6 +25,7 @@ SIGNATURES = {
     'bh_dltn_bwd': (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
     'bh_pairgen_draw': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _vp]),
     'bh_pairgen_apply': (_i, [_vp] * 6 + [_i, _i, _i, _i, _i, _d, _d, _vp]),
+    'bh_pairgen_image': (_i, [_vp] * 4 + [_i, _i, _i, _i, _d, _d, _vp]),
     'bh_mace': (_i, [_vp, _vp, _vp, _i, _vp]),
     'bh_tune_set': (_i, [ctypes.c_char_p, _i]),
     'bh_fieldhead_supported': (_i, [_i, _i]),

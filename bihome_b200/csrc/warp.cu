@@ -1089,12 +1089,14 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
 //                128x128), eight or more of them resident per SM -- the hardware block scheduler balances the load (no
 //                persistent rounds, no tail), and the DRAM latency of one CTA's box is covered by its neighbours' math.
 //   source box = bounding box of the tile's four projected corners (a projective map with w > 0 sends the tile to a convex
-//                quadrilateral), fetched with cp.async.bulk.tensor.3d (SASS UTMALDG) through one of three tensor maps
-//                over [planes, Hs, Ws] whose boxes are 36x36, 48x48 and 64x64 floats.  The box may sit anywhere, also
+//                quadrilateral), its left edge rounded down to a multiple of four floats (TMA wants the first byte of a box
+//                on a 16-byte boundary: other offsets raise an illegal-instruction fault, tools/probes/tma_probe.cu),
+//                fetched with cp.async.bulk.tensor.3d (SASS UTMALDG) through one of three tensor maps over
+//                [planes, Hs, Ws] whose boxes are 40x36 and 56x52 floats.  The box may sit anywhere, also
 //                partly or wholly outside the plane: TMA fills what is out of bounds with ZEROS, which is exactly
 //                grid_sample's zeros padding -- the sampler has no border case at all (no clamp, no predicate, no zero
-//                frame to write).  Tiles whose box exceeds 64x64 (down-sampling by more than 2) or whose w changes sign read
-//                the plane through the read-only cache with predicated taps.
+//                frame to write).  Tiles whose box exceeds 56x52 (local scale above ~1.5) or whose w changes sign read the
+//                plane through the read-only cache with predicated taps.
 //   sampling   = a warp owns 32 columns x 8 rows, lanes on consecutive columns (coalesced 128-byte row stores), four packed
 //                row pairs in flight per lane (fp32x2 arithmetic, magic-number floor, see above).
 //   pooled mask= analytic coverage, 4x4 mean; a warp whose 32x8 region maps strictly inside the source writes ones.
@@ -1103,13 +1105,15 @@ __global__ void __launch_bounds__(RingCfg<kBlk>::kThreads, RingCfg<kBlk>::kCtasP
 //                tile, fixed-order finish kernel behind a programmatic dependent launch.
 // =================================================================================================
 struct alignas(64) TileMaps {
-    CUtensorMap m[3];
+    CUtensorMap m[2];
 };
 constexpr int kTile = 32;
-constexpr int kTileThreads = 128;
-constexpr int kTileBoxMax = 64;
-constexpr int kTileSmem = kTileBoxMax * kTileBoxMax * 4;
-__host__ __device__ constexpr int tile_box(int sel) { return sel == 0 ? 36 : (sel == 1 ? 48 : 64); }
+// box k: height 36 / 52 rows (local scale up to ~1.0 / ~1.5), width = height + 4 (the slack of the aligned left edge).
+// 11.6 KB of shared memory per CTA: nineteen CTAs fit an SM, the register file decides the occupancy.
+constexpr int kTileBoxes = 2;
+__host__ __device__ constexpr int tile_box_h(int sel) { return sel == 0 ? 36 : 52; }
+__host__ __device__ constexpr int tile_box_w(int sel) { return tile_box_h(sel) + 4; }
+constexpr int kTileSmem = tile_box_w(kTileBoxes - 1) * tile_box_h(kTileBoxes - 1) * 4;
 
 __device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* map, int c0, int r0, int plane, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -1118,32 +1122,49 @@ __device__ __forceinline__ void tma_load_box(void* smem_dst, const CUtensorMap* 
                  : "memory");
 }
 
-struct TileGeom {
-    int plane, b, c, x_lo, y_lo, x_hi, y_hi;
-    int c0, r0, sel;   // source box origin and tensor-map index; sel < 0: no box (predicated global taps)
+// Geometry of a tile.  Warp 0 computes it (every lane projects one corner, quads combine), its lane 0 initialises the
+// barrier and issues the box copy straight away -- nothing between the H load and the TMA request but ~60 instructions --
+// and publishes {c0, r0, sel, inside} in shared memory for the other warps.
+struct TileHeader {
+    int c0, r0, sel, inside;   // box origin, tensor-map index (< 0: no box, predicated global taps), tile sampled strictly inside
 };
-// Every lane of every warp computes the same geometry (uniform control flow, no shared header).
-__device__ __forceinline__ TileGeom tile_geom(const Hmat& hm, int tile, int tiles_x, int tiles_per_plane, int C, int Ho, int Wo) {
-    TileGeom g;
-    g.plane = tile / tiles_per_plane;
-    const int t = tile - g.plane * tiles_per_plane, ty = t / tiles_x, tx = t - ty * tiles_x;
-    g.b = g.plane / C;
-    g.c = g.plane - g.b * C;
+struct TileIndex {
+    long long plane;
+    int b, c, x_lo, y_lo, x_hi, y_hi;
+};
+// grid = (tiles per plane, planes low, planes high): no integer division on the way to the tile's coordinates except the
+// exact multiply-high by tiles_x_magic = ceil(2^32 / tiles_x) (t < 65536)
+__device__ __forceinline__ TileIndex tile_index(int tiles_x, unsigned tiles_x_magic, int C, int Ho, int Wo) {
+    TileIndex g;
+    g.plane = static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y;
+    const int t = blockIdx.x, ty = tiles_x == 1 ? t : static_cast<int>(__umulhi(static_cast<unsigned>(t), tiles_x_magic)), tx = t - ty * tiles_x;
+    if (C == 1) { g.b = static_cast<int>(g.plane); g.c = 0; }
+    else { g.b = static_cast<int>(g.plane / C); g.c = static_cast<int>(g.plane - static_cast<long long>(g.b) * C); }
     g.x_lo = tx * kTile; g.y_lo = ty * kTile;
     g.x_hi = min(Wo, g.x_lo + kTile); g.y_hi = min(Ho, g.y_lo + kTile);
+    return g;
+}
+// warp 0, all lanes
+__device__ __forceinline__ TileHeader tile_header(const Hmat& hm, const TileIndex& g, int Hs, int Ws, bool stage) {
     const int k = threadIdx.x & 3;
     float u, v, w;
     project_rcp(hm, static_cast<float>((k & 1) ? g.x_hi - 1 : g.x_lo), static_cast<float>((k & 2) ? g.y_hi - 1 : g.y_lo), u, v, w);
     // 1e5: the corner coordinates carry ~4e-7 relative error (reciprocal + 3 roundings), covered by the 0.05 px guard
     const bool good = quad_all(w > 0.0f && fabsf(u) < 1.0e5f && fabsf(v) < 1.0e5f);
     const float umin = quad_min(u), umax = quad_max(u), vmin = quad_min(v), vmax = quad_max(v);
-    g.c0 = static_cast<int>(floorf(umin - 0.05f));
-    g.r0 = static_cast<int>(floorf(vmin - 0.05f));
-    const int need = good ? max(static_cast<int>(floorf(umax + 0.05f)) + 2 - g.c0, static_cast<int>(floorf(vmax + 0.05f)) + 2 - g.r0) : (1 << 30);
-    g.sel = need <= tile_box(0) ? 0 : (need <= tile_box(1) ? 1 : (need <= tile_box(2) ? 2 : -1));
-    // broadcast quad 0's verdict: all quads hold the same numbers, this only pins the compiler to uniform values
-    g.c0 = __shfl_sync(0xffffffffu, g.c0, 0); g.r0 = __shfl_sync(0xffffffffu, g.r0, 0); g.sel = __shfl_sync(0xffffffffu, g.sel, 0);
-    return g;
+    TileHeader h;
+    h.c0 = static_cast<int>(floorf(umin - 0.05f)) & ~3;
+    h.r0 = static_cast<int>(floorf(vmin - 0.05f));
+    const int need_w = static_cast<int>(floorf(umax + 0.05f)) + 2 - h.c0, need_h = static_cast<int>(floorf(vmax + 0.05f)) + 2 - h.r0;
+    h.sel = -1;
+    if (good && stage) {
+#pragma unroll
+        for (int s = kTileBoxes - 1; s >= 0; --s)
+            if (need_w <= tile_box_w(s) && need_h <= tile_box_h(s)) h.sel = s;
+    }
+    h.inside = (good && umin >= 0.001f && vmin >= 0.001f && umax < static_cast<float>(Ws - 1) - 0.001f &&
+                vmax < static_cast<float>(Hs - 1) - 0.001f) ? 1 : 0;
+    return h;
 }
 // is the 32x8 region of this warp sampled strictly inside the source (coverage == 1, no coverage gradient)?
 __device__ __forceinline__ bool region_inside(const Hmat& hm, int xa, int xb, int ya, int yb, int Hs, int Ws) {
@@ -1154,14 +1175,14 @@ __device__ __forceinline__ bool region_inside(const Hmat& hm, int xa, int xb, in
                              (v < static_cast<float>(Hs - 1) - 0.001f));
     return __shfl_sync(0xffffffffu, in ? 1 : 0, 0) != 0;
 }
-__device__ __forceinline__ Window tile_window(const void* stage, const TileGeom& g, const float* plane_ptr, int Ws) {
+__device__ __forceinline__ Window tile_window(const void* stage, const TileHeader& h, const float* plane_ptr, int Ws) {
     Window wd;
-    wd.shared = g.sel >= 0;
+    wd.shared = h.sel >= 0;
     wd.xpred = false;
     if (wd.shared) {
-        wd.pitch = tile_box(g.sel);
+        wd.pitch = tile_box_w(h.sel);
         // byte address of source pixel (0, 0) relative to the box, minus the bias the magic-number floor leaves in `lin`
-        const uint32_t origin = static_cast<uint32_t>(-g.r0 * wd.pitch - g.c0) - static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(wd.pitch + 1);
+        const uint32_t origin = static_cast<uint32_t>(-h.r0 * wd.pitch - h.c0) - static_cast<uint32_t>(kMagicBits) * static_cast<uint32_t>(wd.pitch + 1);
         wd.base_s32 = smem_u32(stage) + origin * 4u;
         wd.taps = nullptr;
     } else {
@@ -1171,58 +1192,65 @@ __device__ __forceinline__ Window tile_window(const void* stage, const TileGeom&
     }
     return wd;
 }
+// prologue shared by forward and backward: returns the header; on return the box copy (if any) is in flight
+__device__ __forceinline__ TileHeader tile_prologue(const TileMaps& maps, const Hmat& hm, const TileIndex& g, int Hs, int Ws, bool stage_src,
+                                                    void* stage, uint64_t* bar, TileHeader* shared_hdr) {
+    if (threadIdx.x < 32) {
+        const TileHeader h = tile_header(hm, g, Hs, Ws, stage_src);
+        if (threadIdx.x == 0) {
+            *shared_hdr = h;
+            if (h.sel >= 0) {
+                mbar_init(bar, 1);
+                fence_mbar_init();
+                mbar_expect_tx(bar, static_cast<uint32_t>(tile_box_w(h.sel) * tile_box_h(h.sel)) * 4u);
+                tma_load_box(stage, &maps.m[h.sel], h.c0, h.r0, static_cast<int>(g.plane), bar);
+            }
+        }
+    }
+    __syncthreads();   // header and barrier visible
+    return *shared_hdr;
+}
 
 // 8 rows of one column out of the staged box: values (and coordinates for the coverage)
-template <int kPitch>
+// rows of a packed pair; partial tiles (kFull = false) clamp to the tile's last row: every tap stays inside the staged box
+template <bool kFull>
+__device__ __forceinline__ f2 tile_rows(float yg, int p, float ymax) {
+    if (kFull) return add2(dup2(yg), pk(2.0f * p, 2.0f * p + 1.0f));
+    return pk(fminf(yg + 2.0f * p, ymax), fminf(yg + (2.0f * p + 1.0f), ymax));
+}
+template <int kPitch, bool kFull>
 __device__ __forceinline__ void tile_sample8(const Hmat& hm, const ColProj& cp, const Window& wd, float yg, float ymax, f2 (&u2)[4],
                                              f2 (&v2)[4], f2 (&o2)[4]) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         f2 r2;
-        project_col2(hm, cp, pk(fminf(yg + 2.0f * p, ymax), fminf(yg + (2.0f * p + 1.0f), ymax)), u2[p], v2[p], r2);
+        project_col2(hm, cp, tile_rows<kFull>(yg, p, ymax), u2[p], v2[p], r2);
     }
 #pragma unroll
     for (int p = 0; p < 4; ++p) o2[p] = lerp2(cell_at2<kPitch>(u2[p], v2[p], wd, false, 0));
 }
 
-template <bool kMask>
-__global__ void __launch_bounds__(kTileThreads, 8)
-    warp_fwd_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ src, const float* __restrict__ H,
-                         float* __restrict__ out, float* __restrict__ mask_pooled, int C, int Hs, int Ws, int Ho, int Wo, int tiles_x,
-                         int tiles_per_plane) {
-    extern __shared__ __align__(128) unsigned char stage[];
-    __shared__ __align__(8) uint64_t bar;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const Hmat hm = load_h(H, tile / tiles_per_plane / C);
-    const TileGeom g = tile_geom(hm, tile, tiles_x, tiles_per_plane, C, Ho, Wo);
-    __syncthreads();   // barrier initialised
-    if (threadIdx.x == 0 && g.sel >= 0) {
-        const uint32_t box = static_cast<uint32_t>(tile_box(g.sel));
-        mbar_expect_tx(&bar, box * box * 4u);
-        tma_load_box(stage, &maps.m[g.sel], g.c0, g.r0, g.plane, &bar);
-    }
-    const int x = g.x_lo + lane, y0 = g.y_lo + 8 * warp;
-    const bool xin = x < g.x_hi;
-    // lanes / rows beyond a partial tile recompute its last column / row: every tap stays inside the staged box
-    const ColProj cp = col_proj(hm, static_cast<float>(min(x, g.x_hi - 1)));
+// one pass of a warp: 32 columns x 8 rows starting at row y0.  kWo = 128: the north-star geometry (Wo == 128, whole tiles
+// only) -- store offsets are immediates and the partial-tile clamps and predicates drop out; kWo = 0: run-time sizes.
+template <bool kMask, int kWo>
+__device__ __forceinline__ void tile_fwd_pass(const Hmat& hm, const TileIndex& g, const TileHeader& h, const Window& wd, const ColProj& cp,
+                                              int x, bool xin, int y0, float* __restrict__ out, float* __restrict__ mask_pooled, int Hs,
+                                              int Ws, int Ho, int Wo_rt) {
+    constexpr bool kFull = kWo > 0;
+    const int Wo = kFull ? kWo : Wo_rt;
+    if (!kFull && y0 >= g.y_hi) return;
+    const int lane = threadIdx.x & 31;
     const float yg = static_cast<float>(y0), ymax = static_cast<float>(g.y_hi - 1);
-    // coverage first: it needs no source data and fills the time the box is in flight
+    const bool want_mask = kMask && g.c == 0;
+    // coverage of a tile that is not wholly inside: per 32x8 region first
     bool inside = true;
-    if (kMask && g.c == 0 && y0 < g.y_hi) inside = region_inside(hm, g.x_lo, g.x_hi - 1, y0, min(y0 + 7, g.y_hi - 1), Hs, Ws);
-    const Window wd = tile_window(stage, g, src + static_cast<size_t>(g.plane) * Hs * Ws, Ws);
+    if (want_mask && !h.inside) inside = region_inside(hm, g.x_lo, g.x_hi - 1, y0, min(y0 + 7, g.y_hi - 1), Hs, Ws);
     float o8[8];
     float m_top = 1.0f, m_bot = 1.0f;
-    if (g.sel >= 0) {
+    if (h.sel >= 0) {
         f2 u2[4], v2[4], o2[4];
-        mbar_wait(&bar, 0u);
-        if (g.sel == 0) tile_sample8<36>(hm, cp, wd, yg, ymax, u2, v2, o2);
-        else if (g.sel == 1) tile_sample8<48>(hm, cp, wd, yg, ymax, u2, v2, o2);
-        else tile_sample8<64>(hm, cp, wd, yg, ymax, u2, v2, o2);
+        if (h.sel == 0) tile_sample8<tile_box_w(0), kFull>(hm, cp, wd, yg, ymax, u2, v2, o2);
+        else tile_sample8<tile_box_w(1), kFull>(hm, cp, wd, yg, ymax, u2, v2, o2);
 #pragma unroll
         for (int p = 0; p < 4; ++p) upk(o2[p], o8[2 * p], o8[2 * p + 1]);
         if (kMask && !inside) {
@@ -1244,7 +1272,7 @@ __global__ void __launch_bounds__(kTileThreads, 8)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float u, v, rw, nw, ne, sw, se;
-            project_col(hm, cp, yg + static_cast<float>(j), u, v, rw);
+            project_col(hm, cp, fminf(yg + static_cast<float>(j), ymax), u, v, rw);
             const Taps t = make_taps_fast(u, v, Ws, Hs);
             global_taps(t, wd.taps, Ws, nw, ne, sw, se);
             o8[j] = blend(t, nw, ne, sw, se);
@@ -1255,9 +1283,9 @@ __global__ void __launch_bounds__(kTileThreads, 8)
         }
         inside = false;
     }
-    if (xin) {
-        float* og = out + (static_cast<size_t>(g.plane) * Ho + y0) * Wo + x;
-        if (y0 + 8 <= g.y_hi) {
+    if (kFull || xin) {
+        float* og = out + (g.plane * Ho + y0) * Wo + x;
+        if (kFull || y0 + 8 <= g.y_hi) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) st_stream1(og + j * Wo, o8[j]);
         } else {
@@ -1266,114 +1294,166 @@ __global__ void __launch_bounds__(kTileThreads, 8)
                 if (y0 + j < g.y_hi) st_stream1(og + j * Wo, o8[j]);
         }
     }
-    if (kMask && g.c == 0 && y0 < g.y_hi) {
+    if (want_mask) {
         if (!inside) {
             m_top += __shfl_xor_sync(0xffffffffu, m_top, 1); m_top += __shfl_xor_sync(0xffffffffu, m_top, 2);
             m_bot += __shfl_xor_sync(0xffffffffu, m_bot, 1); m_bot += __shfl_xor_sync(0xffffffffu, m_bot, 2);
             m_top *= 0.0625f; m_bot *= 0.0625f;
         }
-        if (xin && (lane & 3) == 0) {
+        if ((kFull || xin) && (lane & 3) == 0) {
             float* mc = mask_pooled + (static_cast<size_t>(g.b) * (Ho >> 2) + (y0 >> 2)) * (Wo >> 2) + (x >> 2);
             mc[0] = m_top;
-            if (y0 + 4 < g.y_hi) mc[Wo >> 2] = m_bot;
+            if (kFull || y0 + 4 < g.y_hi) mc[Wo >> 2] = m_bot;
         }
     }
 }
 
-// dH partial sums of one tile.  kImage: upstream image gradient given (source box staged); kMask: pooled-mask upstream
-// (pool == 4) folded into the same pass on the tiles of channel 0.  partials[tile][9].
-template <bool kImage, bool kMask>
-__global__ void __launch_bounds__(kTileThreads, 8)
-    warp_bwd_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ src, const float* __restrict__ H,
-                         const float* __restrict__ gOut, const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C,
-                         int Hs, int Ws, int Ho, int Wo, int tiles_x, int tiles_per_plane) {
+// kWarps = 4: a warp owns 8 rows of the tile; kWarps = 2: 16 rows in two passes (the per-thread prologue -- H, column
+// projection, window set-up -- is paid once per 16 pixels instead of 8)
+template <bool kMask, int kWarps, int kWo, int kMinBlocks>
+__global__ void __launch_bounds__(32 * kWarps, kMinBlocks)
+    warp_fwd_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ src, const float* __restrict__ H,
+                         float* __restrict__ out, float* __restrict__ mask_pooled, int C, int Hs, int Ws, int Ho, int Wo, int tiles_x,
+                         unsigned tiles_x_magic, long long n_planes) {
     extern __shared__ __align__(128) unsigned char stage[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ float red[4][9];
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finish kernel may be scheduled; it waits for this grid
-    if (kImage && threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
+    __shared__ TileHeader hdr;
+    const TileIndex g = tile_index(tiles_x, tiles_x_magic, C, Ho, Wo);
+    if (g.plane >= n_planes) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const Hmat hm = load_h(H, tile / tiles_per_plane / C);
-    TileGeom g = tile_geom(hm, tile, tiles_x, tiles_per_plane, C, Ho, Wo);
-    if (!kImage) g.sel = -1;
-    __syncthreads();
-    if (kImage && threadIdx.x == 0 && g.sel >= 0) {
-        const uint32_t box = static_cast<uint32_t>(tile_box(g.sel));
-        mbar_expect_tx(&bar, box * box * 4u);
-        tma_load_box(stage, &maps.m[g.sel], g.c0, g.r0, g.plane, &bar);
-    }
-    const int x = g.x_lo + lane, y0 = g.y_lo + 8 * warp;
-    const bool xin = x < g.x_hi, live = xin && y0 < g.y_hi;
-    // the upstream gradients of this lane's column: issued now, consumed after the box has landed
-    float g8[8];
+    const Hmat hm = load_h(H, g.b);
+    const TileHeader h = tile_prologue(maps, hm, g, Hs, Ws, true, stage, &bar, &hdr);
+    const int x = g.x_lo + lane;
+    const bool xin = x < g.x_hi;
+    // lanes / rows beyond a partial tile recompute its last column / row: every tap stays inside the staged box
+    const ColProj cp = col_proj(hm, static_cast<float>(min(x, g.x_hi - 1)));
+    const Window wd = tile_window(stage, h, h.sel >= 0 ? nullptr : src + g.plane * Hs * Ws, Ws);
+    if (h.sel >= 0) mbar_wait(&bar, 0u);
+    constexpr int kPasses = 4 / kWarps;
+#pragma unroll 1
+    for (int pass = 0; pass < kPasses; ++pass)
+        tile_fwd_pass<kMask, kWo>(hm, g, h, wd, cp, x, xin, g.y_lo + 8 * (warp * kPasses + pass), out, mask_pooled, Hs, Ws, Ho, Wo);
+}
+
+// dH partial sums of one tile.  kImage: upstream image gradient given (source box staged); kMask: pooled-mask upstream
+// (pool == 4) folded into the same pass on the tiles of channel 0.  partials[plane][tile][9].
+template <bool kImage, int kWo>
+__device__ __forceinline__ void tile_load_g8(float (&g8)[8], const float* __restrict__ gOut, const TileIndex& g, int x, bool xin, int y0, int Ho,
+                                             int Wo_rt) {
+    constexpr bool kFull = kWo > 0;
+    const int Wo = kFull ? kWo : Wo_rt;
 #pragma unroll
     for (int j = 0; j < 8; ++j) g8[j] = 0.0f;
-    if (kImage && live) {
-        const float* gp = gOut + (static_cast<size_t>(g.plane) * Ho + y0) * Wo + x;
+    if (kImage && (kFull || (xin && y0 < g.y_hi))) {
+        const float* gp = gOut + (g.plane * Ho + y0) * Wo + x;
+        if (kFull || y0 + 8 <= g.y_hi) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (y0 + j < g.y_hi) g8[j] = ld_stream1(gp + j * Wo);
-    }
-    bool mask_live = false;
-    float gm_top = 0.0f, gm_bot = 0.0f;
-    if (kMask && g.c == 0 && y0 < g.y_hi) {
-        mask_live = !region_inside(hm, g.x_lo, g.x_hi - 1, y0, min(y0 + 7, g.y_hi - 1), Hs, Ws);
-        if (mask_live && xin) {
-            const float* mc = gMaskPooled + (static_cast<size_t>(g.b) * (Ho >> 2) + (y0 >> 2)) * (Wo >> 2) + (x >> 2);
-            gm_top = __ldg(mc) * 0.0625f;
-            if (y0 + 4 < g.y_hi) gm_bot = __ldg(mc + (Wo >> 2)) * 0.0625f;
+            for (int j = 0; j < 8; ++j) g8[j] = ld_stream1(gp + j * Wo);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (y0 + j < g.y_hi) g8[j] = ld_stream1(gp + j * Wo);
         }
     }
+}
+// one pass of a warp of the backward: 32 columns x 8 rows starting at y0, sums into t
+template <bool kImage, bool kMask, int kWo>
+__device__ __forceinline__ void tile_bwd_pass(const Hmat& hm, const TileIndex& g, const TileHeader& h, const Window& wd, const ColProj& cp,
+                                              int x, bool xin, int y0, const float (&g8)[8], const float* __restrict__ gMaskPooled,
+                                              StripSums2& t, int Hs, int Ws, int Ho, int Wo_rt) {
+    constexpr bool kFull = kWo > 0;
+    const int Wo = kFull ? kWo : Wo_rt;
+    const bool live = kFull || (xin && y0 < g.y_hi);
+    bool mask_live = false;
+    float gm_top = 0.0f, gm_bot = 0.0f;
+    if (kMask && g.c == 0 && (kFull || y0 < g.y_hi) && !h.inside) {
+        mask_live = !region_inside(hm, g.x_lo, g.x_hi - 1, y0, min(y0 + 7, g.y_hi - 1), Hs, Ws);
+        if (mask_live && (kFull || xin)) {
+            const float* mc = gMaskPooled + (static_cast<size_t>(g.b) * (Ho >> 2) + (y0 >> 2)) * (Wo >> 2) + (x >> 2);
+            gm_top = __ldg(mc) * 0.0625f;
+            if (kFull || y0 + 4 < g.y_hi) gm_bot = __ldg(mc + (Wo >> 2)) * 0.0625f;
+        }
+    }
+    if (!(live && (kImage || mask_live))) return;
+    const float yg = static_cast<float>(y0), ymax = static_cast<float>(g.y_hi - 1);
+    const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const f2 y2 = tile_rows<kFull>(yg, p, ymax);
+        f2 u2, v2, r2, gu = dup2(0.0f), gv = dup2(0.0f);
+        project_col2(hm, cp, y2, u2, v2, r2);
+        float u0, u1, v0, v1;
+        upk(u2, u0, u1);
+        upk(v2, v0, v1);
+        if (kImage) {
+            const f2 g2 = pk(g8[2 * p], g8[2 * p + 1]);
+            f2 du, dv;
+            if (h.sel >= 0) {
+                Cell8 c;
+                if (h.sel == 0) c = cell_at2<tile_box_w(0)>(u2, v2, wd, false, 0);
+                else c = cell_at2<tile_box_w(1)>(u2, v2, wd, false, 0);
+                cell_grad2(c, du, dv);
+            } else {
+                float d0, e0, d1, e1, nw, ne, sw, se;
+                const Taps t0 = make_taps_fast(u0, v0, Ws, Hs), t1 = make_taps_fast(u1, v1, Ws, Hs);
+                global_taps(t0, wd.taps, Ws, nw, ne, sw, se);
+                blend_grad(t0, nw, ne, sw, se, d0, e0);
+                global_taps(t1, wd.taps, Ws, nw, ne, sw, se);
+                blend_grad(t1, nw, ne, sw, se, d1, e1);
+                du = pk(d0, d1);
+                dv = pk(e0, e1);
+            }
+            gu = mul2(g2, du);
+            gv = mul2(g2, dv);
+        }
+        if (kMask && mask_live) {
+            const float gm = p < 2 ? gm_top : gm_bot;
+            gu = fma2(dup2(gm), pk(cover1(v0, Hsf) * cover1_grad(u0, Wsf), cover1(v1, Hsf) * cover1_grad(u1, Wsf)), gu);
+            gv = fma2(dup2(gm), pk(cover1(u0, Wsf) * cover1_grad(v0, Hsf), cover1(u1, Wsf) * cover1_grad(v1, Hsf)), gv);
+        }
+        // rows below the output (partial tiles) carry g = 0 and gm = 0: no contribution
+        sums_add2(t, gu, gv, u2, v2, r2, y2);
+    }
+}
+
+// dH partial sums of one tile.  kImage: upstream image gradient given (source box staged); kMask: pooled-mask upstream
+// (pool == 4) folded into the same pass on the tiles of channel 0.  partials[plane][tile][9].
+template <bool kImage, bool kMask, int kWarps, int kWo, int kMinBlocks>
+__global__ void __launch_bounds__(32 * kWarps, kMinBlocks)
+    warp_bwd_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ src, const float* __restrict__ H,
+                         const float* __restrict__ gOut, const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C,
+                         int Hs, int Ws, int Ho, int Wo, int tiles_x, unsigned tiles_x_magic, long long n_planes) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ TileHeader hdr;
+    __shared__ float red[kWarps][9];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finish kernel may be scheduled; it waits for this grid
+    const TileIndex g = tile_index(tiles_x, tiles_x_magic, C, Ho, Wo);
+    if (g.plane >= n_planes) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Hmat hm = load_h(H, g.b);
+    const int x = g.x_lo + lane;
+    const bool xin = x < g.x_hi;
+    constexpr int kPasses = 4 / kWarps;
+    // the upstream gradients of this lane's column: the first pass' are issued before the box is even requested
+    float g8[8];
+    tile_load_g8<kImage, kWo>(g8, gOut, g, x, xin, g.y_lo + 8 * warp * kPasses, Ho, Wo);
+    const TileHeader h = tile_prologue(maps, hm, g, Hs, Ws, kImage, stage, &bar, &hdr);
     const float xf = static_cast<float>(min(x, g.x_hi - 1));
     const ColProj cp = col_proj(hm, xf);
-    const float yg = static_cast<float>(y0), ymax = static_cast<float>(g.y_hi - 1);
-    const Window wd = tile_window(stage, g, kImage ? src + static_cast<size_t>(g.plane) * Hs * Ws : nullptr, Ws);
-    const float Wsf = static_cast<float>(Ws), Hsf = static_cast<float>(Hs);
+    const Window wd = tile_window(stage, h, (kImage && h.sel < 0) ? src + g.plane * Hs * Ws : nullptr, Ws);
     StripSums2 t;
     t.sa = t.say = t.sb = t.sby = t.sc = t.scy = dup2(0.0f);
-    if (kImage && g.sel >= 0) mbar_wait(&bar, 0u);
-    if (live && (kImage || mask_live)) {
+    if (kImage && h.sel >= 0) mbar_wait(&bar, 0u);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const f2 y2 = pk(fminf(yg + 2.0f * p, ymax), fminf(yg + (2.0f * p + 1.0f), ymax));
-            f2 u2, v2, r2, gu = dup2(0.0f), gv = dup2(0.0f);
-            project_col2(hm, cp, y2, u2, v2, r2);
-            float u0, u1, v0, v1;
-            upk(u2, u0, u1);
-            upk(v2, v0, v1);
-            if (kImage) {
-                const f2 g2 = pk(g8[2 * p], g8[2 * p + 1]);
-                f2 du, dv;
-                if (g.sel >= 0) {
-                    Cell8 c;
-                    if (g.sel == 0) c = cell_at2<36>(u2, v2, wd, false, 0);
-                    else if (g.sel == 1) c = cell_at2<48>(u2, v2, wd, false, 0);
-                    else c = cell_at2<64>(u2, v2, wd, false, 0);
-                    cell_grad2(c, du, dv);
-                } else {
-                    float d0, e0, d1, e1, nw, ne, sw, se;
-                    const Taps t0 = make_taps_fast(u0, v0, Ws, Hs), t1 = make_taps_fast(u1, v1, Ws, Hs);
-                    global_taps(t0, wd.taps, Ws, nw, ne, sw, se);
-                    blend_grad(t0, nw, ne, sw, se, d0, e0);
-                    global_taps(t1, wd.taps, Ws, nw, ne, sw, se);
-                    blend_grad(t1, nw, ne, sw, se, d1, e1);
-                    du = pk(d0, d1);
-                    dv = pk(e0, e1);
-                }
-                gu = mul2(g2, du);
-                gv = mul2(g2, dv);
-            }
-            if (kMask && mask_live) {
-                const float gm = p < 2 ? gm_top : gm_bot;
-                gu = fma2(dup2(gm), pk(cover1(v0, Hsf) * cover1_grad(u0, Wsf), cover1(v1, Hsf) * cover1_grad(u1, Wsf)), gu);
-                gv = fma2(dup2(gm), pk(cover1(u0, Wsf) * cover1_grad(v0, Hsf), cover1(u1, Wsf) * cover1_grad(v1, Hsf)), gv);
-            }
-            // rows below the output (partial tiles) carry g = 0 and gm = 0: no contribution
-            sums_add2(t, gu, gv, u2, v2, r2, y2);
+    for (int pass = 0; pass < kPasses; ++pass) {
+        const int y0 = g.y_lo + 8 * (warp * kPasses + pass);
+        float gnext[8];
+        if (pass + 1 < kPasses) tile_load_g8<kImage, kWo>(gnext, gOut, g, x, xin, y0 + 8, Ho, Wo);   // in flight while this pass computes
+        tile_bwd_pass<kImage, kMask, kWo>(hm, g, h, wd, cp, x, xin, y0, g8, gMaskPooled, t, Hs, Ws, Ho, Wo);
+        if (pass + 1 < kPasses) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g8[j] = gnext[j];
         }
     }
     float acc[9];
@@ -1394,9 +1474,12 @@ __global__ void __launch_bounds__(kTileThreads, 8)
     if ((lane & 3) == 0) red[warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r;
     if (lane == 0) red[warp][8] = r8;
     __syncthreads();
-    if (threadIdx.x < 9)
-        partials[static_cast<size_t>(tile) * 9 + threadIdx.x] =
-            (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    if (threadIdx.x < 9) {
+        float sum = red[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < kWarps; ++k) sum += red[k][threadIdx.x];
+        partials[(static_cast<size_t>(g.plane) * gridDim.x + blockIdx.x) * 9 + threadIdx.x] = sum;
+    }
 }
 
 // =================================================================================================
@@ -1694,16 +1777,23 @@ inline EncodeTiledFn tensor_map_encoder() {
 
 // NCHW planes whose rows are a whole number of 16-byte units: what a tiled tensor map can describe
 inline bool tile_ok(const float* src, int Hs, int Ws, int Ho, int Wo, long long planes, int channels_last) {
-    const long long tiles = planes * blocks_of(Wo, kTile) * blocks_of(Ho, kTile);
+    const long long tpp = static_cast<long long>(blocks_of(Wo, kTile)) * blocks_of(Ho, kTile);
     return g_tune[kTuneWarpPath] == 0 && !channels_last && (Ws & 3) == 0 && aligned16(src) && Hs < (1 << 20) && Ws < (1 << 20) && Ho < (1 << 20) &&
-           Wo < (1 << 20) && planes < (1ll << 31) && tiles < (1ll << 31) - 1024 && tensor_map_encoder() != nullptr;
+           Wo < (1 << 20) && planes < (1ll << 30) && tpp < 65536 && tensor_map_encoder() != nullptr;
 }
+// resident CTAs per SM the tile kernels are compiled for (register budget 65536 / (128 threads x blocks))
+// grid = (tiles per plane, planes low, planes high); ceil(2^32 / tiles_x) for the exact multiply-high division
+inline dim3 tile_grid(long long planes, int tpp) {
+    const long long py = planes < 32768 ? planes : 32768;
+    return dim3(static_cast<unsigned>(tpp), static_cast<unsigned>(py), static_cast<unsigned>((planes + py - 1) / py));
+}
+inline unsigned tile_magic(int tiles_x) { return tiles_x <= 1 ? 0u : static_cast<unsigned>(((1ull << 32) + tiles_x - 1) / tiles_x); }
 inline int make_tile_maps(TileMaps& maps, const float* src, long long planes, int Hs, int Ws) {
     const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(Ws), static_cast<cuuint64_t>(Hs), static_cast<cuuint64_t>(planes)};
     const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(Ws) * 4u, static_cast<cuuint64_t>(Ws) * Hs * 4u};
     const cuuint32_t estride[3] = {1u, 1u, 1u};
-    for (int k = 0; k < 3; ++k) {
-        const cuuint32_t box[3] = {static_cast<cuuint32_t>(tile_box(k)), static_cast<cuuint32_t>(tile_box(k)), 1u};
+    for (int k = 0; k < kTileBoxes; ++k) {
+        const cuuint32_t box[3] = {static_cast<cuuint32_t>(tile_box_w(k)), static_cast<cuuint32_t>(tile_box_h(k)), 1u};
         const CUresult r = tensor_map_encoder()(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3u, const_cast<float*>(src), gdim, gstride, box,
                                                 estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1718,8 +1808,15 @@ inline int launch_fwd_tile(const float* src, const float* H, float* out, float* 
     int rc = make_tile_maps(maps, src, planes, Hs, Ws);
     if (rc != BH_OK) return rc;
     const int tiles_x = blocks_of(Wo, kTile), tpp = tiles_x * blocks_of(Ho, kTile);
-    auto kern = fuse_mask ? warp_fwd_tile_kernel<true> : warp_fwd_tile_kernel<false>;
-    kern<<<static_cast<unsigned>(planes * tpp), kTileThreads, kTileSmem, stream>>>(maps, src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo, tiles_x, tpp);
+    const bool four = (g_tune[kTuneWarpVariant] & 1) != 0;
+    void (*kern)(const TileMaps, const float*, const float*, float*, float*, int, int, int, int, int, int, unsigned, long long);
+    const bool star = Wo == 128 && (Ho % kTile) == 0;      // whole tiles of 128-pixel rows: the north-star geometry
+    if (four) kern = star ? (fuse_mask ? warp_fwd_tile_kernel<true, 4, 128, 12> : warp_fwd_tile_kernel<false, 4, 128, 12>)
+                          : (fuse_mask ? warp_fwd_tile_kernel<true, 4, 0, 12> : warp_fwd_tile_kernel<false, 4, 0, 12>);
+    else kern = star ? (fuse_mask ? warp_fwd_tile_kernel<true, 2, 128, 16> : warp_fwd_tile_kernel<false, 2, 128, 16>)
+                     : (fuse_mask ? warp_fwd_tile_kernel<true, 2, 0, 16> : warp_fwd_tile_kernel<false, 2, 0, 16>);
+    kern<<<tile_grid(planes, tpp), four ? 128 : 64, kTileSmem, stream>>>(maps, src, H, out, mask_pooled, C, Hs, Ws, Ho, Wo, tiles_x,
+                                                                         tile_magic(tiles_x), planes);
     return launch_status();
 }
 inline int tile_bwd_chunks(int Cw, int Ho, int Wo) { return Cw * blocks_of(Wo, kTile) * blocks_of(Ho, kTile); }
@@ -1734,12 +1831,21 @@ inline int launch_bwd_tile(const float* src, const float* H, const float* gOut, 
         memset(&maps, 0, sizeof(maps));
     }
     const int tiles_x = blocks_of(Wo, kTile), tpp = tiles_x * blocks_of(Ho, kTile);
-    void (*kern)(const TileMaps, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int);
-    if (gOut && gMaskPooled) kern = warp_bwd_tile_kernel<true, true>;
-    else if (gOut) kern = warp_bwd_tile_kernel<true, false>;
-    else kern = warp_bwd_tile_kernel<false, true>;
-    kern<<<static_cast<unsigned>(planes * tpp), kTileThreads, gOut ? kTileSmem : 0, stream>>>(maps, src, H, gOut, gMaskPooled, partials, Cw, Hs, Ws,
-                                                                                            Ho, Wo, tiles_x, tpp);
+    void (*kern)(const TileMaps, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, unsigned,
+                 long long);
+    const bool four = (g_tune[kTuneWarpVariant] & 1) != 0;
+    const bool star = Wo == 128 && (Ho % kTile) == 0;
+    if (gOut && gMaskPooled) {
+        if (star) kern = four ? warp_bwd_tile_kernel<true, true, 4, 128, 8> : warp_bwd_tile_kernel<true, true, 2, 128, 12>;
+        else kern = four ? warp_bwd_tile_kernel<true, true, 4, 0, 8> : warp_bwd_tile_kernel<true, true, 2, 0, 12>;
+    } else if (gOut) {
+        if (star) kern = four ? warp_bwd_tile_kernel<true, false, 4, 128, 8> : warp_bwd_tile_kernel<true, false, 2, 128, 12>;
+        else kern = four ? warp_bwd_tile_kernel<true, false, 4, 0, 8> : warp_bwd_tile_kernel<true, false, 2, 0, 12>;
+    } else {
+        kern = four ? warp_bwd_tile_kernel<false, true, 4, 0, 8> : warp_bwd_tile_kernel<false, true, 2, 0, 12>;
+    }
+    kern<<<tile_grid(planes, tpp), four ? 128 : 64, gOut ? kTileSmem : 0, stream>>>(maps, src, H, gOut, gMaskPooled, partials, Cw, Hs, Ws, Ho, Wo,
+                                                                                 tiles_x, tile_magic(tiles_x), planes);
     return launch_status();
 }
 // the fixed-order sum behind a programmatic dependent launch: its blocks are resident when the producer grid drains

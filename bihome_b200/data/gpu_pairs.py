@@ -18,9 +18,12 @@ from .. import functional as F
 
 def transform_args(transforms, name='HomographyNetPrep'):
     """pull [rho, patch_size, distort_keys, max_delta, target_gen] and the standardisation out of a DATA.TRANSFORMS list"""
-    out = {'rho': 32, 'patch_size': 128, 'max_delta': 32, 'mean': 0.443, 'std': 0.129, 'target_gen': '4_points'}
+    out = {'rho': 32, 'patch_size': 128, 'max_delta': 32, 'mean': 0.443, 'std': 0.129, 'target_gen': '4_points', 'image_keys': ()}
     for t in transforms:
         (k, v), = t.items()
+        if k == 'DictToTensor':
+            # whole images the model reads besides the patches (s-coco/nguyen-orig: PhotometricHead warps 'image_1')
+            out['image_keys'] = tuple(key for key in v[0] if key.startswith('image'))
         if k == name:
             out['rho'], out['patch_size'] = int(v[0]), int(v[1])
             if len(v) > 3:
@@ -127,13 +130,18 @@ class GpuPairLoader:
     """Iterable of batch dicts; ``len`` = steps per epoch (reference DatasetSampler.__len__)."""
 
     def __init__(self, pool, batch_size, samples_per_epoch, rho=32, patch_size=128, max_delta=32.0, mean=0.443, std=0.129,
-                 seed=42, rank=0, target_gen='4_points'):
+                 seed=42, rank=0, target_gen='4_points', image_keys=()):
         assert pool.is_cuda and pool.dtype == torch.uint8 and pool.dim() == 4
         self.pool = pool
         self.batch_size = int(batch_size)
         self.steps = int(samples_per_epoch) // self.batch_size
         self.cfg = dict(rho=int(rho), patch_size=int(patch_size), max_delta=float(max_delta), mean=float(mean), std=float(std))
         self.target_gen = target_gen
+        self.image_keys = tuple(image_keys)
+        unknown = [k for k in self.image_keys if k != 'image_1']
+        if unknown:
+            raise NotImplementedError('GpuPairLoader renders the patches and image_1; the config also asks for %s as tensors (no '
+                                      'shipped configuration reads them)' % unknown)
         self.seed = rank_seed(seed, rank)
         self.step = 0
 
@@ -149,7 +157,10 @@ class GpuPairLoader:
         self.step += 1
         corners = patch_corners(params[:, 22:24], c['patch_size'])           # pos_x, pos_y of the params table
         target = delta if self.target_gen == '4_points' else perspective_field_target(corners, delta, c['patch_size'])
-        return {'patch_1': p1, 'patch_2': p2, 'delta': delta, 'corners': corners.float(), 'target': target}
+        batch = {'patch_1': p1, 'patch_2': p2, 'delta': delta, 'corners': corners.float(), 'target': target}
+        if 'image_1' in self.image_keys:
+            batch['image_1'] = F.pairgen_image(self.pool, index, params, c['mean'], c['std'])
+        return batch
 
     def __iter__(self):
         return self.batches(self.steps)

@@ -388,6 +388,21 @@ def pairgen_apply(images, index, params, patch_size, mean=0.443, std=0.129):
     return p1, p2, delta
 
 
+def pairgen_image(images, index, params, mean=0.443, std=0.129):
+    """The whole first image of every pair through its photometric chain, grayscale, standardised: [B,1,Hi,Wi] -- the
+    'image_1' entry of the reference's batch (HomographyNetPrep + DictToGrayscale + DictStandardize + DictToTensor) that
+    PhotometricHead warps (src/heads/PhotometricHead.py:24)."""
+    if not images.is_cuda or images.dtype != torch.uint8:
+        raise RuntimeError('bihome_b200: the image pool must be a CUDA uint8 tensor [n,H,W,3] (no CPU fallback)')
+    n, hi, wi, _ = images.shape
+    B = index.shape[0]
+    out = torch.empty(B, 1, hi, wi, device=images.device, dtype=torch.float32)
+    with torch.cuda.device(images.device), _timed('bh_pairgen_image'):
+        cabi.check(cabi.lib().bh_pairgen_image(_ptr(images), _ptr(index.contiguous()), _ptr(params.contiguous()), _ptr(out), B, n, hi, wi,
+                                               float(mean), float(std), _stream()), 'bh_pairgen_image')
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def mace(delta_gt, delta_hat):
     """mean corner error over B*4 corners, as a 0-dim CUDA tensor (no host sync)."""

@@ -146,7 +146,10 @@ int bh_dltn_bwd(const float* p1, const float* p2, const float* field, const int6
  *   2 x {b_on, b_delta, contrast_first, c_on, c_alpha, s_on, s_alpha, h_on, h_delta, l_on, l_perm},
  *   pos_x, pos_y, delta[8].
  * bh_pairgen_draw fills params (and index) from a counter-based generator (seed, step, sample);
- * bh_pairgen_apply renders patch1, patch2 [B,1,P,P] (grayscale, standardised) and delta [B,4,2].
+ * bh_pairgen_apply renders patch1, patch2 [B,1,P,P] (grayscale, standardised) and delta [B,4,2];
+ * bh_pairgen_image renders image1 [B,1,Hi,Wi]: the whole first image through its photometric chain, grayscale,
+ *   standardised -- the 'image_1' entry the reference's PhotometricHead reads (src/heads/PhotometricHead.py:24,
+ *   config/s-coco/nguyen-orig-lr-5e-3.yaml LEARNING_KEYS).
  * ------------------------------------------------------------------------------------------- */
 #define BH_PAIR_NPARAM 32
 int bh_pairgen_draw(double* params, int32_t* index, int B, int n_img, int Hi, int Wi, int rho, int P,
@@ -154,6 +157,8 @@ int bh_pairgen_draw(double* params, int32_t* index, int B, int n_img, int Hi, in
 int bh_pairgen_apply(const uint8_t* images, const int32_t* index, const double* params, float* patch1,
                      float* patch2, float* delta, int B, int n_img, int Hi, int Wi, int P, double mean, double std,
                      bh_stream_t stream);
+int bh_pairgen_image(const uint8_t* images, const int32_t* index, const double* params, float* image1, int B, int n_img,
+                     int Hi, int Wi, double mean, double std, bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6  perspective-field head of the Zeng backbone (per-pixel 16 -> 128 -> 2 network with folded BatchNorm)
@@ -195,6 +200,7 @@ int bh_mace(const float* delta_gt, const float* delta_hat, float* out, int B, bh
  * that they can be timed against each other.  Process-global; every key defaults to 0 = "choose from the arguments",
  * which is the only state the product path (bihome_b200/, train.py, eval.py, bench.py) ever runs in.
  *   "warp_path"    0 tile kernels (TMA box per 32x32 tile), 1 the persistent ring kernels
+ *   "warp_variant" tile kernels: bit 0 = four warps per tile (8 rows each) instead of two (16 rows each)
  *   "loss_variant" 0 auto, 1 ldg cluster kernel, 2 TMA cluster kernel, 3 persistent TMA stream
  *   "loss_cluster" 0 auto, 1 | 2 | 4 | 8 CTAs per cluster
  * returns BH_E_UNSUPPORTED for an unknown key.

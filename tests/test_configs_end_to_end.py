@@ -19,7 +19,8 @@ def _configs():
     from oracle import ref_import
     if not ref_import.available():
         return []
-    return sorted(glob.glob(os.path.join(ref_import.REFERENCE_ROOT, 'config', 'pds-coco', '*.yaml')))
+    return sorted(glob.glob(os.path.join(ref_import.REFERENCE_ROOT, 'config', 'pds-coco', '*.yaml')) +
+                  glob.glob(os.path.join(ref_import.REFERENCE_ROOT, 'config', 's-coco', '*.yaml')))
 
 
 def _batch(B, P, gen):
@@ -32,7 +33,7 @@ def _batch(B, P, gen):
     return {'patch_1': p1, 'patch_2': p2, 'delta': delta, 'corners': corners}
 
 
-@pytest.mark.parametrize('path', _configs(), ids=lambda p: os.path.basename(p)[:-5])
+@pytest.mark.parametrize('path', _configs(), ids=lambda p: os.path.basename(os.path.dirname(p)) + '/' + os.path.basename(p)[:-5])
 def test_training_step_matches_reference(monkeypatch, path):
     from oracle import ref_import
     from bihome_b200 import engine
@@ -56,6 +57,9 @@ def test_training_step_matches_reference(monkeypatch, path):
     t = gpu_pairs.transform_args(cfg['DATA']['TRANSFORMS'])
     data['target'] = data['delta'] if t['target_gen'] == '4_points' else \
         gpu_pairs.perspective_field_target(data['corners'], data['delta'], P)
+    if 'image_1' in t['image_keys']:                    # s-coco/nguyen-orig: PhotometricHead warps the whole first image
+        lo = torch.rand(B, 1, 31, 41, generator=torch.Generator().manual_seed(5))
+        data['image_1'] = torch.nn.functional.interpolate(lo, size=(240, 320), mode='bicubic', align_corners=True)
     ref.train()
     ours.train()
 

@@ -97,3 +97,24 @@ def test_train_entry_point_runs_and_resumes(tmp_path):
     ev = load_entry('eval')
     mace = ev.main(CONFIG, os.path.join(log_dir, 'model_000005.pth'), batch_size=8, samples=32)
     assert np.isfinite(mace)
+
+
+def test_config5_mace_subsample_both_field_heads(tmp_path, monkeypatch):
+    """BASELINE.json configs[4] on a 500-pair sub-sample (the 10 000-pair run is tools/mace10k.py under tools/gpu_round.sh,
+    its record is profiles/r02_mace10k.json): unmodified random-init weights -- no hand-scaled layer --, reference path =
+    plain ATen backbone + float64 oracle head on the GPU and on the host cores, B200 path = eval.py's evaluate() with the ATen
+    AND the fused (K6) field head; every per-batch MACE and the mean within 0.01 px (north_star)."""
+    import json
+    import subprocess
+    import sys
+    monkeypatch.delenv('BH_FIELD_HEAD', raising=False)
+    out = os.path.join(str(tmp_path), 'mace.json')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'mace10k.py'), '--pairs', '500', '--batch', '250', '--cpu-ref', '250',
+                        '--out', out], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.load(open(out))
+    assert res['within_tolerance'] and res['pairs'] == 500
+    for side in ('aten', 'fused'):
+        assert res['b200_path'][side]['max_abs_batch_diff_vs_reference'] <= 0.01
+        assert res['b200_path'][side]['mace'] > 1.0          # not vacuous: a random-init model is far from the ground truth
+    assert res['reference_cpu_backbone']['max_abs_batch_diff_vs_gpu_reference'] <= 0.01

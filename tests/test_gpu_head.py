@@ -103,6 +103,34 @@ def test_pairgen_vs_oracle(max_delta):
     assert p2.data_ptr() == p1.data_ptr() + p1.numel() * 4
 
 
+@pytest.mark.parametrize('max_delta', [32, 0])
+def test_pairgen_image_1_vs_oracle(max_delta):
+    """the whole first image as the reference's batch carries it ('image_1' after DictToGrayscale / DictStandardize /
+    DictToTensor, the tensor PhotometricHead warps in s-coco/nguyen-orig), and the loader's batch for such a config"""
+    import bihome_b200.functional as F
+    from bihome_b200.data import gpu_pairs
+    from oracle import pairgen
+    n_img, B = 3, 5
+    images = np.stack([pairgen.synthetic_image(i) for i in range(n_img)])
+    rs = np.random.RandomState(77 + max_delta)
+    qs = [pairgen.draw_params(rs, 240, 320, 32, 128, max_delta) for _ in range(B)]
+    idx = [b % n_img for b in range(B)]
+    im1 = F.pairgen_image(torch.from_numpy(images).cuda(), torch.tensor(idx, dtype=torch.int32).cuda(),
+                          torch.from_numpy(pairgen.pack_params(qs)).cuda())
+    assert im1.shape == (B, 1, 240, 320)
+    for b in range(B):
+        ref = pairgen.to_network_input(pairgen.apply_photometric(images[idx[b]], qs[b]['photo_1']))
+        assert np.abs(im1[b].cpu().numpy() - ref).max() < 2e-4, b
+        assert (im1[b].cpu().numpy() == ref).mean() > 0.9
+    # patch_1 is the crop of image_1 at the batch's corners, bit for bit (same chain, same pixels)
+    loader = gpu_pairs.GpuPairLoader(torch.from_numpy(images).cuda(), 4, 8, max_delta=float(max_delta), image_keys=('image_1',))
+    batch = loader.next_batch()
+    c = batch['corners'].long().cpu()
+    for b in range(4):
+        x0, y0 = int(c[b, 0, 0]), int(c[b, 0, 1])
+        assert torch.equal(batch['image_1'][b, :, y0:y0 + 128, x0:x0 + 128], batch['patch_1'][b])
+
+
 def test_pairgen_golden_reference_pipeline(golden):
     """explicit parameters replayed from the seeded RandomState the reference transforms consumed"""
     import bihome_b200.functional as F

@@ -149,12 +149,15 @@ def _kernel_cells(H32, Ho, Wo):
     return torch.from_numpy(np.floor(u)), torch.from_numpy(np.floor(v))
 
 
-@pytest.fixture(params=['tile', 'ring'])
+@pytest.fixture(params=['tile', 'tile4', 'ring'])
 def warp_path(request, F):
-    """both NCHW implementations behind bh_warp_fwd / bh_warp_bwd: the tile kernels (default) and the persistent ring"""
+    """the NCHW implementations behind bh_warp_fwd / bh_warp_bwd: the tile kernels (default: two warps per tile; 'tile4':
+    the four-warp build) and the persistent ring kernels"""
     F.tune('warp_path', 1 if request.param == 'ring' else 0)
+    F.tune('warp_variant', 1 if request.param == 'tile4' else 0)
     yield request.param
     F.tune('warp_path', 0)
+    F.tune('warp_variant', 0)
 
 
 @pytest.mark.parametrize('B,C,Hs,Ws,Ho,Wo,nhwc', WARP_SHAPES)

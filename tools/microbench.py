@@ -226,10 +226,14 @@ def main():
     if a.warp_only:
         for B, P in ((256, 128), (1024, 128), (4096, 128), (256, 256), (64, 512)):
             bench_copy(B, P, t)
-            for path, tag in ((0, ' [tile]'), (1, ' [ring]')):
-                F.tune('warp_path', path)
-                for scale in (0.02, 0.25):
+            for variant in ((0, 1) if P == 128 and B != 1024 else (0,)):
+                F.tune('warp_variant', variant)
+                tag = ' [tile%s]' % (', 4 warps x 8 rows' if variant & 1 else ', 2 warps x 16 rows')
+                for scale in ((0.02, 0.25) if variant == 0 else (0.02,)):
                     bench_image_warp(B, P, t, scale, tag)
+            F.tune('warp_variant', 0)
+            F.tune('warp_path', 1)
+            bench_image_warp(B, P, t, 0.02, ' [ring]')
             F.tune('warp_path', 0)
         return
     print(json.dumps({'peak_GBps_measured': PEAK, 'timing': 'cuda events, L2 flushed (256 MB written, then 256 MB read: clean lines) before every launch, mean of %d' % a.iters}))
