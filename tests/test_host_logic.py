@@ -79,9 +79,13 @@ def test_hot_path_refuses_cpu_tensors():
 def test_transform_args_from_yaml():
     from bihome_b200.data import gpu_pairs
     t = gpu_pairs.transform_args(cfg('pds-coco/zeng-bihome-lr-1e-3.yaml')['DATA']['TRANSFORMS'])
-    assert t == {'rho': 32, 'patch_size': 128, 'max_delta': 32.0, 'mean': 0.443, 'std': 0.129, 'target_gen': '4_points'}
+    assert t == {'rho': 32, 'patch_size': 128, 'max_delta': 32.0, 'mean': 0.443, 'std': 0.129, 'target_gen': '4_points',
+                 'image_keys': ()}
     t = gpu_pairs.transform_args(cfg('s-coco/detone-bihome-lr-5e-3.yaml')['DATA']['TRANSFORMS'])
     assert t['max_delta'] == 0.0
+    # the PhotometricHead config reads the whole first image besides the patches
+    nguyen = [{'HomographyNetPrep': [32, 128, [], 0]}, {'DictToTensor': [['image_1', 'patch_1', 'patch_2']]}]
+    assert gpu_pairs.transform_args(nguyen)['image_keys'] == ('image_1',)
     zeng_orig = [{'HomographyNetPrep': [32, 128, ['image_1', 'image_2'], 32, 'all_points']},
                  {'DictStandardize': [[0.443], [0.129], ['patch_1', 'patch_2']]}]
     assert gpu_pairs.transform_args(zeng_orig)['target_gen'] == 'all_points'
