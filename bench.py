@@ -80,6 +80,16 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def workload_config(batch, world, pool):
+    """the `config` object of the JSON line -- the same for both arms (the reference arm runs the same workload on the
+    host cores; what differs is said in its cpu_baseline.sample)"""
+    return {'workload': 'pds-coco zeng-bihome-lr-1e-3 training step (Zeng ResNet34 perspective-field backbone + biHomE '
+                        'loss, ResNet-34 stem extractor), 128x128 patches, B=%d per GPU, fp32 (cuDNN TF32 convs = torch default), '
+                        'random-init weights, synthetic uint8 image pool (%d x 240x320) resident in HBM' % (batch, pool),
+            'global_batch': batch * world, 'parallelism': 'dp%d' % world,
+            'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'}
+
+
 def cpu_oracle_run(steps, warmup, batch, threads):
     """the reference's CPU path for the same config: torch backbone on CPU + oracle head (oracle/ref_train.py)"""
     from bihome_b200 import engine
@@ -119,15 +129,26 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 8
+    # the same B = 256 step as the GPU arm (BatchNorm statistics and the per-step overheads are those of the real workload);
+    # a B = 256 step of the Zeng backbone keeps ~35 GB of activations on the host, so a box with less RAM runs B = 64 steps
+    batch = args.ref_batch
+    if batch is None:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:  # noqa: BLE001
+            avail = 0
+        batch = args.batch if avail >= 56e9 else 64
     value, spp = cpu_oracle_run(args.steps, args.warmup, batch, threads)
+    sample = ('%d steps of B=%d after %d warm-up (%.1f s/step): torch CPU backbone (plain ATen modules, NCHW) + the oracle\'s '
+              'kornia-0.5.0 head and its autograd, Adam, %d host threads' % (args.steps, batch, args.warmup, spp, threads))
+    if batch != args.batch:
+        sample += '; bounded sample: B=%d steps of the B=%d workload (host RAM)' % (batch, args.batch)
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': spp * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'pds-coco zeng-bihome-lr-1e-3 training step, 128x128 patches (reference CPU path: '
-                                   'torch CPU backbone + oracle kornia-0.5.0 head), B=%d per step' % batch},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': '%d steps of B=%d (bounded sample of the B=256 workload)' % (args.steps, batch)},
+            'config': workload_config(args.batch, max(args.gpus, 1), args.pool),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -251,6 +272,14 @@ def run_ours(args):
             gbs = per_pair * B / (kernels[name]['avg_ms'] * 1e-3) / 1e9
             kernels[name].update({'algorithmic_GBps': gbs, 'frac_of_hbm_peak': gbs / peak})
 
+    # BASELINE.json's second metric, "warp+loss HBM GB/s": the three bandwidth kernels of the path together
+    wl = [(n, kernels[n]['avg_ms'] * kernels[n]['launches'] / args.steps) for n in ('bh_warp_fwd', 'bh_warp_bwd', 'bh_bihome_fwd_bwd') if n in kernels]
+    wl_ms = sum(ms_ for _, ms_ in wl)
+    wl_bytes = (270336 + 270408 + LOSS_BYTES_PER_PAIR) * B
+    warp_loss = {'kernels': [n for n, _ in wl], 'ms_per_step': wl_ms, 'algorithmic_bytes_per_step': wl_bytes,
+                 'achieved': wl_bytes / (wl_ms * 1e-3) / 1e9 if wl_ms > 0 else None, 'peak': peak, 'unit': 'GB/s',
+                 'frac': (wl_bytes / (wl_ms * 1e-3) / 1e9 / peak) if wl_ms > 0 else None}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -261,15 +290,11 @@ def run_ours(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': 'pds-coco zeng-bihome-lr-1e-3 training step (Zeng ResNet34 perspective-field backbone + biHomE '
-                                   'loss, ResNet-34 stem extractor), 128x128 patches, B=%d per GPU, fp32 (cuDNN TF32 convs = torch default), '
-                                   'random-init weights, synthetic uint8 image pool (%d x 240x320) resident in HBM' % (B, args.pool),
-                       'global_batch': B * world, 'parallelism': 'dp%d' % world, 'channels_last': bool(args.channels_last),
-                       'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten',
-                       'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'},
+            'config': workload_config(B, world, args.pool),
+            'layout': {'channels_last': bool(args.channels_last), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
-            'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'clocks': clk,
+            'gpu_launches': launches, 'roofline': roofline, 'warp_loss_roofline': warp_loss, 'cpu_baseline': cpu_baseline, 'clocks': clk,
             'kernels': kernels, 'final_loss': final_loss, 'field_head_self_test': autotune.last_verdict(dev)}
     print(json.dumps(line))
     if world > 1:
@@ -293,6 +318,7 @@ def main():
     ap.add_argument('--field-head', default=None, choices=['aten', 'fused'],
                     help="Zeng backbone's last stage: 'aten' = the four torch modules (default), 'fused' = K6 (csrc/fieldhead.cu); "
                          "unset = BH_FIELD_HEAD, else the device's self-test decides (bihome_b200/autotune.py)")
+    ap.add_argument('--ref-batch', type=int, default=None, help='--impl reference: image pairs per CPU step (default: --batch, 64 on a box with < 56 GB of free RAM)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer phase (profiling runs)')
     ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')

@@ -21,6 +21,8 @@ SIGNATURES = {
     'bh_warp_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     'bh_bihome_fwd_bwd': (_i, [_vp] * 10 + [_f] + [_vp] * 10 + [_i, _i, _i, _i, _i, _vp]),
     'bh_bihome_rescale': (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
+    'bh_triplet_fwd_bwd': (_i, [_vp] * 10 + [_i, _i, _i, _i] + [_f] * 5 + [_vp] * 12 + [_i, _i, _i, _i, _i, _vp]),
+    'bh_triplet_rescale': (_i, [_vp] * 11 + [_i, _i, _i, _i, _vp]),
     'bh_dltn_fwd': (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
     'bh_dltn_bwd': (_i, [_vp] * 9 + [_i, _i, _i, _i, _vp]),
     'bh_pairgen_draw': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _vp]),

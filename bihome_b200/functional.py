@@ -7,6 +7,7 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   warp(src, H, out_h, out_w, pool=None)                    K2   warp_image(inverse=True)   (src/data/utils.py:54-59)
   coverage_mask(H, src_hw, out_hw, pool)                   K2   warp(ones) + AvgPool2d     (PerceptualHead.py:380-382,447-459)
   bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu)    K3   double-line biHomE loss    (PerceptualHead.py:559-561,609-665)
+  triplet_loss(f1, f2, f1w, f2w, a1, b2, a2, b1, ...)      K3g  every other loss variant   (PerceptualHead.py:465-665, TripletHead.py:78-153)
   dltn(p1, p2, choice) / dltn_field(field, choice, four)   K4   find_homography_dlt        (ransac_utils.py:58-72, PerceptualHead.py:164-178)
   pairgen_draw(...) / pairgen_apply(...)                   K5   HomographyNetPrep pipeline (src/data/transforms.py:456-576)
   mace(delta_gt, delta_hat)                                     train.py:401-404
@@ -283,6 +284,102 @@ def bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu, m1=None, m2=None):
     Returns (loss_b [B], parts [B,5] = ln1, ln2, den1 (unclamped), den2, ln3); the reference's scalar is loss_b.sum().
     """
     return _BihomeLoss.apply(f1, f2, f1w, f2w, m1, m2, m1w, m2w, H12, H21, float(mu))
+
+
+# ------------------------------------------------------------------------------------------------
+# K3g
+# ------------------------------------------------------------------------------------------------
+_DISTANCES = {'l1': 0, 'l2': 1, 'cosine': 2}
+_HINGES = {None: 0, 'channel': 1, 'pixel': 2}
+
+
+class _TripletLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, f1w, f2w, a1, b2, a2, b1, H12, H21, cfg):
+        ctx.set_materialize_grads(False)
+        lines, distance, hinge, margins, mask_crd, mu, scale = cfg
+        two = lines == 2
+        feats = [f1, f2, f1w] + ([f2w] if two else [])
+        for n, t in zip(('f1', 'f2', 'f1w', 'f2w'), feats):
+            _need_cuda_f32(n, t)
+        _need_cuda_f32('a1', a1)
+        nhwc = all(_is_nhwc(t) for t in feats)
+        if not nhwc:
+            feats = [t.contiguous() for t in feats]
+        f1, f2, f1w = feats[:3]
+        f2w = feats[3] if two else None
+        B, C, h, w = f1w.shape
+        ctx.mask_shapes = tuple(None if t is None else tuple(t.shape) for t in (a1, b2, a2, b1))
+        dense = lambda t: None if t is None else t.reshape(B, h, w).contiguous()
+        a1, b2, a2, b1 = dense(a1), dense(b2), dense(a2) if two else None, dense(b1) if two else None
+        dev = f1w.device
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        parts = torch.empty(B, 5, device=dev, dtype=torch.float32)
+        g_f1w = torch.empty_like(f1w)
+        g_f2w = torch.empty_like(f2w) if two else None
+        want_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_f1 = torch.empty_like(f1) if want_in else None
+        g_f2 = torch.empty_like(f2) if want_in else None
+        g_a1 = torch.empty_like(a1)
+        g_a2 = torch.empty_like(a2) if two else None
+        g_b2 = torch.empty_like(b2) if (b2 is not None and ctx.needs_input_grad[5]) else None
+        g_b1 = torch.empty_like(b1) if (b1 is not None and ctx.needs_input_grad[7]) else None
+        if two:
+            H12c, H21c = H12.contiguous().view(B, 9), H21.contiguous().view(B, 9)
+            gH12 = torch.empty(B, 9, device=dev, dtype=torch.float32)
+            gH21 = torch.empty(B, 9, device=dev, dtype=torch.float32)
+        else:
+            H12c = H21c = gH12 = gH21 = None
+        with torch.cuda.device(dev), _timed('bh_triplet_fwd_bwd'):
+            cabi.check(cabi.lib().bh_triplet_fwd_bwd(
+                _ptr(f1), _ptr(f2), _ptr(f1w), _ptr(f2w), _ptr(a1), _ptr(b2), _ptr(a2), _ptr(b1), _ptr(H12c), _ptr(H21c),
+                lines, _DISTANCES[distance], _HINGES[hinge], int(bool(mask_crd)), float(margins[0]), float(margins[1]),
+                float(scale[0]), float(scale[1]), float(mu), _ptr(loss), _ptr(parts), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1),
+                _ptr(g_f2), _ptr(g_a1), _ptr(g_b2), _ptr(g_a2), _ptr(g_b1), _ptr(gH12), _ptr(gH21), B, C, h, w, int(nhwc),
+                _stream()), 'bh_triplet_fwd_bwd')
+        ctx.grads = (g_f1w, g_f2w, g_f1, g_f2, g_a1, g_b2, g_a2, g_b1, gH12, gH21)
+        ctx.dims = (B, C, h, w)
+        ctx.mark_non_differentiable(parts)
+        return loss, parts
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        if g_loss is None:
+            return (None,) * 11
+        if ctx.grads is None:
+            raise RuntimeError('triplet_loss: the fused loss stores its gradients once; backward twice is not supported')
+        g_f1w, g_f2w, g_f1, g_f2, g_a1, g_b2, g_a2, g_b1, gH12, gH21 = ctx.grads
+        ctx.grads = None
+        B, C, h, w = ctx.dims
+        g_loss = g_loss.contiguous().float()
+        with torch.cuda.device(g_f1w.device), _timed('bh_triplet_rescale'):
+            cabi.check(cabi.lib().bh_triplet_rescale(_ptr(g_loss), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_a1),
+                                                     _ptr(g_b2), _ptr(g_a2), _ptr(g_b1), _ptr(gH12), _ptr(gH21), B, C, h, w, _stream()),
+                       'bh_triplet_rescale')
+        shaped = lambda g, like: None if g is None else g.view(like)
+        ms = ctx.mask_shapes
+        return (g_f1, g_f2, g_f1w, g_f2w, shaped(g_a1, ms[0]), shaped(g_b2, ms[1]), shaped(g_a2, ms[2]), shaped(g_b1, ms[3]),
+                None if gH12 is None else gH12.view(B, 3, 3), None if gH21 is None else gH21.view(B, 3, 3), None)
+
+
+def triplet_loss(f1, f2, f1w, f2w, a1, b2, a2=None, b1=None, H12=None, H21=None, lines=2, distance='l1', hinge=None, margin=0.0,
+                 mask_crd=False, mu=0.0, scale=(1.0, 1.0)):
+    """Per-sample masked triplet loss in the reference's other variants (one-/double-line; l1 / l2 / cosine; margin 'inf'
+    (hinge None), channel-aware ('channel') or channel-agnostic / one-line ('pixel') numeric margin; MASK_CRD weights).
+
+    features [B,C,h,w]; masks [B,h,w] or [B,1,h,w] at the feature resolution (a = warped mask of the line's source patch,
+    b = mask of its target patch, None == ones); ``margin`` a number or a pair (line 1, line 2); ``scale`` multiplies the
+    two lines.  Returns (loss_b [B], parts [B,5] = ln1, ln2, den1 (unclamped), den2, ln3); gradients flow to all four
+    features, all four masks and both homographies."""
+    if distance not in _DISTANCES:
+        raise ValueError('Do not know this distance metric: %r' % (distance,))
+    if hinge not in _HINGES:
+        raise ValueError('hinge must be None, \'channel\' or \'pixel\', got %r' % (hinge,))
+    if hinge == 'channel' and distance != 'l1':
+        raise ValueError('a per-channel margin needs per-channel distances (l1)')
+    margins = tuple(margin) if isinstance(margin, (tuple, list)) else (margin, margin)
+    cfg = (int(lines), distance, hinge, margins, bool(mask_crd), float(mu), (float(scale[0]), float(scale[1])))
+    return _TripletLoss.apply(f1, f2, f1w, f2w, a1, b2, a2, b1, H12, H21, cfg)
 
 
 # ------------------------------------------------------------------------------------------------

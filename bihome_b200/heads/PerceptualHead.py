@@ -9,8 +9,8 @@ Hot path of the shipped ``*-bihome-*`` configs (TRIPLET_LOSS 'double-line', TRIP
 Both directions are batched through K1/K2 in one launch each (2B samples), the coverage masks never exist at
 full resolution, and the loss kernel reads every feature once.  Zeng configs (PF_KEYS) get their delta_hat from
 K4 (dltn_field) after the reference's index-proportional multinomial draw.  Everything else the reference's
-head offers (one-line, numeric margins, l2/cosine, 'dual', MASK_CRD, user masks, up-sampling strategies,
-multihead loss) is kept on the same K1/K2 warps with the small loss algebra in torch ops.
+head offers (one-line, numeric margins, l2/cosine, 'dual', MASK_CRD, user masks, up-sampling strategies) runs on the same
+K1/K2 warps with the loss algebra and its gradients in K3g (F.triplet_loss); the multihead loss returns features.
 """
 import warnings
 
@@ -298,100 +298,81 @@ class Model(nn.Module):
         self.last_parts = parts
         return loss_b.sum(), dict(f1=f1, f2=f2, f1w=f1w, h1=H[:B], parts=parts)
 
+    def _loss_variant(self, double):
+        """(distance, hinge, margin) of F.triplet_loss for this head's TRIPLET_* settings (reference :465-538, :555-665)"""
+        distance = self.triplet_distance
+        if not double:
+            # one-line: max(l1 - l3 + margin, 0) on channel-aggregated distances (:512)
+            assert distance in ('l1', 'cosine'), 'Do not know this distance metric'
+            return distance, 'pixel', float(self.triplet_margin)
+        assert distance in ('l1', 'l2', 'cosine'), 'Do not know this distance metric'
+        if isinstance(self.triplet_margin, str):
+            return distance, None, 0.0
+        assert self.triplet_channel_aggregation in ('channel-aware', 'channel-agnostic'), 'Do not know this aggregation technique'
+        if self.triplet_channel_aggregation == 'channel-aware' and distance == 'l1':
+            return distance, 'channel', float(self.triplet_margin)
+        # channel-agnostic numeric margin (and the per-pixel distances, which have no channels left to be aware of): the
+        # reference's branch is shape-inconsistent (:627-628,647-649); this is its evident intent, the margin applied to
+        # the channel-aggregated distance
+        return distance, 'pixel', float(self.triplet_margin)
+
     def _triplet_generic(self, data, patch_1, patch_2, d12, d21, scores):
-        """Every other variant of the reference's triplet_resnet_loss (:320-714): K1/K2 warps + torch loss algebra."""
+        """Every other variant of the reference's triplet_resnet_loss (:320-714): both directions through K1 / K2 in one
+        launch each, the loss algebra and its gradients in K3g (F.triplet_loss)."""
         B, P = patch_1.shape[0], patch_1.shape[-1]
         double = 'double-line' in self.triplet_version
-        if len(self.mask_keys):
+        user_masks = len(self.mask_keys) > 0
+        if user_masks:
             m1 = data[self.mask_keys[0]].reshape(-1, 1, P, P)
             m2 = data[self.mask_keys[1]].reshape(-1, 1, P, P)
             if m1.shape[0] != B:
                 m1 = m1.repeat_interleave(B // m1.shape[0], dim=0)
                 m2 = m2.repeat_interleave(B // m2.shape[0], dim=0)
-        else:
-            m1, m2 = torch.ones_like(patch_1), torch.ones_like(patch_2)
         f1 = self._features(patch_1)
         f2 = self._features(patch_2)
-        p1w, h1 = self._warp(patch_1, d12)
-        f1w = self._features(p1w)
-        m1w, _ = self._warp(m1, d12)
-        if double:
-            p2w, h2 = self._warp(patch_2, d21)
-            f2w = self._features(p2w)
-            m2w, _ = self._warp(m2, d21)
-        loss_dual = None
-        if 'dual' in self.triplet_version:
-            fe = self.backbone.feature_extractor
-            g1, g2, g1w = fe(patch_1), fe(patch_2), fe(p1w)
-            l1d = (g1w - g2).abs().sum(1)
-            l3d = (g1 - g2).abs().sum(1)
-            a, bm = m1w.squeeze(1), m2.squeeze(1)
-            den = (a * bm).sum(-1).sum(-1)
-            loss_dual = ((a * bm * (l1d - l3d)).sum(-1).sum(-1) / torch.max(den, torch.ones_like(den))).sum()
-            if double:
-                l2d = (fe(p2w) - g1).abs().sum(1)
-                a2, b1 = m2w.squeeze(1), m1.squeeze(1)
-                den2 = (a2 * b1).sum(-1).sum(-1)
-                loss_dual = loss_dual + ((a2 * b1 * (l2d - l3d)).sum(-1).sum(-1) / torch.max(den2, torch.ones_like(den2))).sum()
-        k = m1.shape[-1] // f1w.shape[-2]
-        pool = lambda t: nn.functional.avg_pool2d(t, k).squeeze(1)
-        a1, b2 = pool(m1w), pool(m2)
-        if double:
-            b1, a2 = pool(m1), pool(m2w)
-        aux = dict(f1=f1, f2=f2, f1w=f1w, h1=h1, parts=None)
-        clamp1 = lambda t: torch.max(t, torch.ones_like(t))
-        if 'one-line' in self.triplet_version:
-            if getattr(self.auxiliary_resnet, 'with_projection_head', None) is not None:
-                f1w = f1w / f1w.norm(p=2, dim=1, keepdim=True)
-                f2 = f2 / f2.norm(p=2, dim=1, keepdim=True)
-                f1 = f1 / f1.norm(p=2, dim=1, keepdim=True)
-            if self.triplet_distance == 'l1':
-                l1, l3 = (f1w - f2).abs().sum(1), (f1 - f2).abs().sum(1)
-            elif self.triplet_distance == 'cosine':
-                l1 = 1 - torch.cosine_similarity(f1w, f2, dim=1)
-                l3 = 1 - torch.cosine_similarity(f1, f2, dim=1)
-            else:
-                assert False, 'Do not know this distance metric'
-            loss_mat = torch.clamp(l1 - l3 + self.triplet_margin, min=0)
-            if scores is not None:
-                loss_mat = loss_mat * scores.reshape(B, 1, 1)
-            if not self.change_detection_mask:
-                den = (a1 * b2).sum(-1).sum(-1)
-                loss = (a1 * b2 * loss_mat).sum(-1).sum(-1) / clamp1(den)
-            else:
-                den = a1.sum(-1).sum(-1)
-                loss = (a1 * loss_mat).sum(-1).sum(-1) / clamp1(den)
-            loss = loss.sum()
+        k = P // f1.shape[-2]
+        H = F.dlt4(torch.cat([d12, d21], dim=0) if double else d12, size=(patch_1.shape[-2], patch_1.shape[-1]))
+        src = _stack(patch_1, patch_2) if double else patch_1
+        if user_masks:
+            warped = F.warp(src, H, P, P)
+            mw_full = F.warp(_stack(m1, m2) if double else m1, H, P, P).squeeze(1)
+            mw = nn.functional.avg_pool2d(mw_full.unsqueeze(1), k).squeeze(1)
+            m1p = nn.functional.avg_pool2d(m1, k).squeeze(1)
+            m2p = nn.functional.avg_pool2d(m2, k).squeeze(1)
         else:
-            if self.triplet_distance == 'l1':
-                l1, l2, l3 = (f1w - f2).abs(), (f2w - f1).abs(), (f1 - f2).abs()
-            elif self.triplet_distance == 'l2':
-                l1, l2, l3 = ((f1w - f2) ** 2).mean(1), ((f2w - f1) ** 2).mean(1), ((f1 - f2) ** 2).mean(1)
-            elif self.triplet_distance == 'cosine':
-                l1 = 1 - torch.cosine_similarity(f1w, f2, dim=1)
-                l2 = 1 - torch.cosine_similarity(f2w, f1, dim=1)
-                l3 = 1 - torch.cosine_similarity(f1, f2, dim=1)
+            warped, mw = F.warp(src, H, P, P, pool=k)
+            m1p = m2p = None
+        h1 = H[:B]
+        h2 = H[B:] if double else None
+        f1w = self._features(warped[:B])
+        f2w = self._features(warped[B:]) if double else None
+        aux = dict(f1=f1, f2=f2, f1w=f1w, h1=h1, parts=None)
+        n1, n2, n1w = f1, f2, f1w
+        if not double and getattr(self.auxiliary_resnet, 'with_projection_head', None) is not None:
+            n1w = f1w / f1w.norm(p=2, dim=1, keepdim=True)
+            n2 = f2 / f2.norm(p=2, dim=1, keepdim=True)
+            n1 = f1 / f1.norm(p=2, dim=1, keepdim=True)
+        distance, hinge, margin = self._loss_variant(double)
+        loss_b, parts = F.triplet_loss(n1, n2, n1w, f2w, mw[:B], m2p, mw[B:] if double else None, m1p, h1, h2,
+                                       lines=2 if double else 1, distance=distance, hinge=hinge, margin=margin,
+                                       mask_crd=bool(self.change_detection_mask) and not double,
+                                       mu=self.triplet_mu if double else 0.0)
+        if scores is not None:
+            loss_b = loss_b * scores.reshape(B)
+        loss = loss_b.sum()
+        aux['parts'] = parts
+        if 'dual' in self.triplet_version:
+            # the content-aware backbone's own full-resolution feature extractor adds a second triplet term (:407-441)
+            fe = self.backbone.feature_extractor
+            g1, g2, g1w = fe(patch_1), fe(patch_2), fe(warped[:B])
+            g2w = fe(warped[B:]) if double else None
+            if user_masks:
+                a_full, m1f, m2f = mw_full, m1.squeeze(1), m2.squeeze(1)
             else:
-                assert False, 'Do not know this distance metric'
-
-            def line(la, lb):
-                if isinstance(self.triplet_margin, str):
-                    return (la - lb).sum(1) if la.dim() == 4 else la - lb
-                if self.triplet_channel_aggregation == 'channel-aware':
-                    return torch.clamp(la - lb + self.triplet_margin, min=0).sum(1)
-                # channel-agnostic numeric margin: the reference's branch is shape-inconsistent (:627-628,647-649);
-                # this is its evident intent, margin applied to the channel-summed distance
-                return torch.clamp(la.sum(1) - lb.sum(1) + self.triplet_margin, min=0)
-            den1 = (a1 * b2).sum(-1).sum(-1)
-            ln1 = ((a1 * b2 * line(l1, l3)).sum(-1).sum(-1) / clamp1(den1)).sum()
-            den2 = (a2 * b1).sum(-1).sum(-1)
-            ln2 = ((a2 * b1 * line(l2, l3)).sum(-1).sum(-1) / clamp1(den2)).sum()
-            eye = torch.eye(3, dtype=h1.dtype, device=h1.device).unsqueeze(0)
-            ln3 = ((torch.matmul(h1, h2) - eye) ** 2).sum()
-            loss = ln1 + ln2 + self.triplet_mu * ln3
-            aux['dens'] = (den1, den2)
-        if loss_dual is not None:
-            loss = loss + loss_dual
+                a_full, m1f, m2f = F.coverage_mask(H, (P, P), (P, P), 1), None, None
+            dual_b, _ = F.triplet_loss(g1, g2, g1w, g2w, a_full[:B], m2f, a_full[B:] if double else None, m1f, h1, h2,
+                                       lines=2 if double else 1, distance='l1', hinge=None, mu=0.0)
+            loss = loss + dual_b.sum()
         return loss, aux
 
     def _log(self, data, aux):

@@ -5,7 +5,8 @@ and ``predict_homography`` as the reference.
 
 On the B200 path both directions go through K1 (4-point DLT) and K2 (warp) in one launch each; when the backbone's
 masks are the constant ones of ``FIX_MASK`` the warped masks come out of K2's analytic coverage computation instead
-of two more full warps.  The margin algebra on the [B,1,P,P] maps is a handful of torch element-wise ops.
+of two more full warps.  The margin algebra on the [B,1,P,P] maps, ln3 and every gradient come out of K3g
+(``F.triplet_loss``) in one call.
 
 Reference quirk kept on purpose: with a numeric margin and 'channel-agnostic' aggregation the
 reference clamps ``[B,H,W]`` against ``zeros_like`` of a ``[B,1,H,W]`` tensor (:91-92,134-135); the broadcast makes a
@@ -48,24 +49,16 @@ class Model(torch.nn.Module):
         predictor = getattr(self.backbone, 'mask_predictor', None)
         return predictor is not None and bool(getattr(predictor, 'fix_mask', False))
 
-    def _line(self, la, lb):
-        """per-pixel loss map [B,H,W] from two per-channel distance maps [B,C,H,W] (reference :79-95)"""
+    def _loss_variant(self, b, c):
+        """(hinge, margin, scale) of F.triplet_loss for TRIPLET_MARGIN / TRIPLET_AGGREGATION (reference :79-95)"""
         if isinstance(self.triplet_margin, str):
-            if self.triplet_channel_aggregation == 'channel-aware':
-                return (la - lb).sum(1), 1
-            return la.sum(1) - lb.sum(1), 1
+            return None, 0.0, 1.0
         if self.triplet_channel_aggregation == 'channel-aware':
-            return torch.clamp(la - lb + self.triplet_margin, min=0).sum(1), 1
-        b, c = la.shape[0], la.shape[1]
+            return 'channel', float(self.triplet_margin), 1.0
         if c != 1 and b != 1:
             raise RuntimeError('TripletHead: a numeric margin with channel-agnostic aggregation is only defined for '
                                'one-channel features (the reference broadcast fails for B = %d, C = %d)' % (b, c))
-        return torch.clamp(la.sum(1) - lb.sum(1) + self.triplet_margin, min=0), (b if c == 1 else c)
-
-    @staticmethod
-    def _masked_mean(ma, mb, loss_mat):
-        den = (ma * mb).sum(-1).sum(-1)
-        return ((ma * mb * loss_mat).sum(-1).sum(-1) / torch.max(den, torch.ones_like(den))).sum()
+        return 'pixel', float(self.triplet_margin), float(b if c == 1 else c)
 
     def forward(self, data):
         e1, e2 = self.patch_keys
@@ -94,41 +87,31 @@ class Model(torch.nn.Module):
             warped = F.warp(src, H, out_h, out_w)
             mw = F.warp(masks, H, out_h, out_w).squeeze(1)
         h1 = H[:B]
+        h2 = H[B:] if double else None
         f1w = self.backbone.feature_extractor(warped[:B])
-        m1w = mw[:B]
-        m1s, m2s = m1.squeeze(1), m2.squeeze(1)
-
-        l1 = (f1w - f2).abs()
-        l3 = (f1 - f2).abs()
-        mat, scale = self._line(l1, l3)
-        ln1 = self._masked_mean(m1w, m2s, mat) * scale
-        loss = ln1
-        if double:
-            h2 = H[B:]
-            f2w = self.backbone.feature_extractor(warped[B:])
-            m2w = mw[B:]
-            l2 = (f2w - f1).abs()
-            mat, scale = self._line(l2, l3)
-            ln2 = self._masked_mean(m2w, m1s, mat) * scale
-            eye = torch.eye(3, dtype=h1.dtype, device=h1.device).unsqueeze(0)
-            ln3 = ((torch.bmm(h1, h2) - eye) ** 2).sum()
-            loss = ln1 + ln2 + self.mu * ln3
+        f2w = self.backbone.feature_extractor(warped[B:]) if double else None
+        hinge, margin, scale = self._loss_variant(B, f1.shape[1])
+        # both lines, ln3 and every gradient (features, masks, homographies) in one K3g call (reference :78-153)
+        loss_b, parts = F.triplet_loss(f1, f2, f1w, f2w, mw[:B], m2.squeeze(1), mw[B:] if double else None,
+                                       m1.squeeze(1) if double else None, h1, h2, lines=2 if double else 1, distance='l1',
+                                       hinge=hinge, margin=margin, mu=self.mu if double else 0.0, scale=(scale, scale))
+        loss = loss_b.sum()
 
         if 'summary_writer' in data:
             step, sw = data['summary_writer_step'], data['summary_writer']
             sw.add_scalars('feature_space', {'patch_2_f': f2.mean().item()}, step)
             sw.add_scalars('feature_space', {'patch_1_f_prime': f1w.mean().item()}, step)
             sw.add_scalars('feature_space', {'patch_1_f': f1.mean().item()}, step)
-            sw.add_scalars('loss_comp', {'l1': l1.mean().item()}, step)
-            sw.add_scalars('loss_comp', {'l3': l3.mean().item()}, step)
+            sw.add_scalars('loss_comp', {'l1': (f2 - f1w).abs().mean().item()}, step)
+            sw.add_scalars('loss_comp', {'l3': (f1 - f2).abs().mean().item()}, step)
             eye = torch.eye(3, dtype=h1.dtype, device=h1.device).unsqueeze(0)
             sw.add_scalars('h', {'h1': ((h1 - eye) ** 2).sum().item()}, step)
             if double:
                 sw.add_scalars('feature_space', {'patch_2_f_prime': f2w.mean().item()}, step)
-                sw.add_scalars('loss_comp', {'l2': l2.mean().item()}, step)
-                sw.add_scalars('loss_comp', {'ln1': ln1.item()}, step)
-                sw.add_scalars('loss_comp', {'ln2': ln2.item()}, step)
-                sw.add_scalars('loss_comp', {'ln3': self.mu * ln3.item()}, step)
+                sw.add_scalars('loss_comp', {'l2': (f1 - f2w).abs().mean().item()}, step)
+                sw.add_scalars('loss_comp', {'ln1': parts[:, 0].sum().item()}, step)
+                sw.add_scalars('loss_comp', {'ln2': parts[:, 1].sum().item()}, step)
+                sw.add_scalars('loss_comp', {'ln3': self.mu * parts[:, 4].sum().item()}, step)
                 sw.add_scalars('h', {'h2': ((h2 - eye) ** 2).sum().item()}, step)
 
         delta_gt = data['delta'] if 'delta' in data else None

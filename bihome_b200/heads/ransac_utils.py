@@ -8,12 +8,38 @@ Mirror of the reference's ``src/heads/ransac_utils.py`` (DSACSoftmax :26-160): s
                 yields the same correspondences;
   * solve     : N-point normalised DLT (kornia.find_homography_dlt, reference :72) on the K4 kernel
                 (bihome_b200.functional.dltn), gather fused;
-  * scoring   : 'repr_error' softmax (:97-100,126).  With one hypothesis the softmax is identically 1 and the
-                16384-point reprojection pass is skipped (bit-identical output).
+  * scoring   : 'repr_error' / 'inliers_ratio' / 'soft_inliers_ratio' / 'score_cnn' softmax (:97-126).  With one
+                hypothesis the softmax is identically 1 and the 16384-point reprojection pass is skipped (bit-identical
+                output).
 """
+import math
+
 import torch
+import torch.nn as nn
+import torchvision.models as models
 
 from .. import functional as F
+
+
+class ScoreCNN(nn.Module):
+    """ResNet-18 with a 2-channel stem and one output: scores a hypothesis from the [2, sqrt(N), sqrt(N)] image of its
+    signed reprojection errors (reference ransac_utils.py:10-23; same attribute names, so checkpoints interchange)."""
+
+    def __init__(self, pretrained):
+        super().__init__()
+        weights = None
+        if pretrained:
+            try:
+                self.resnet18 = models.resnet18(weights='DEFAULT', progress=True)
+            except Exception:  # noqa: BLE001 -- no network / no cached checkpoint
+                self.resnet18 = models.resnet18(weights=weights)
+        else:
+            self.resnet18 = models.resnet18(weights=weights)
+        self.resnet18.conv1 = nn.Conv2d(2, 64, kernel_size=(7, 7), stride=(2, 2), padding=(3, 3), bias=False)
+        self.resnet18.fc = nn.Linear(512, 1, bias=True)
+
+    def forward(self, x):
+        return self.resnet18(x)
 
 
 def sample_choice(n_points, count, device):
@@ -43,7 +69,7 @@ class DSACSoftmax(torch.nn.Module):
             self.scoring_distance_beta = kwargs['SCORING_DISTANCE_BETA']
             self.scoring_distance_threshold = kwargs['SCORING_DISTANCE_THRESHOLD']
         if self.scoring_method == 'score_cnn':
-            raise NotImplementedError('score_cnn scoring is unused by every shipped config and not provided')
+            self.score_cnn = ScoreCNN(kwargs['SCORE_CNN_PRETRAINED'])
 
     def sample_hypotheses(self, points1, points2, points_per_hypothesis, hypothesis_no, choice=None):
         B, N = points1.shape[0], points1.shape[1]
@@ -71,6 +97,10 @@ class DSACSoftmax(torch.nn.Module):
         elif self.scoring_method == 'soft_inliers_ratio':
             err = torch.norm(proj - p2, dim=-1)
             scores = torch.sigmoid(self.scoring_distance_beta * (err - self.scoring_distance_threshold)).sum(-1)
+        elif self.scoring_method == 'score_cnn':
+            # the signed reprojection errors of all N = side^2 points as a 2-channel image (reference :113-121)
+            side = int(math.sqrt(p1.shape[1]))
+            scores = self.score_cnn((proj - p2).permute(0, 2, 1).reshape(B * n, 2, side, side))
         else:
             assert False, 'I do not know this scoring method'
         return torch.softmax(-scores.reshape(B, n), dim=-1)

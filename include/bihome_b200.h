@@ -112,6 +112,38 @@ int bh_bihome_rescale(const float* gscale, float* g_f1w, float* g_f2w, float* g_
                       float* g_m2w, float* gH12, float* gH21, int B, int C, int h, int w, bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K3g  the masked triplet loss in every other variant of the reference, fused forward + backward
+ *
+ * replaces: src/heads/PerceptualHead.py:465-538 (one-line: l1 / cosine, numeric margin, MASK_CRD weights),
+ *           :555-665 (double-line: l1 / l2 / cosine distances, margin 'inf' or numeric, channel-aware or
+ *           channel-agnostic aggregation, mu * ||H12 H21 - I||^2), src/heads/TripletHead.py:78-153 (the same algebra on
+ *           one-channel full-resolution maps with learned masks -- the shipped zhang-orig loss) and the ~40 element-wise
+ *           ATen kernels (+ as many in autograd) behind each.
+ *
+ *   line 1: x = f1w, y = f2, W = a1*b2 (mask_crd: a1);  line 2 (lines == 2): x = f2w, y = f1, W = a2*b1
+ *   distance 0: l1, per channel |x - y|;  1: l2, channel mean of (x - y)^2;  2: 1 - cosine_similarity (eps 1e-8)
+ *   hinge 0: g = sum_c (d(x,y) - d(f1,f2))                           (TRIPLET_MARGIN 'inf')
+ *         1: g = sum_c max(|x-y| - |f1-f2| + margin, 0)              (numeric margin, channel-aware; distance 0 only)
+ *         2: g = max(d(x,y) - d(f1,f2) + margin, 0) on channel-aggregated distances (one-line; channel-agnostic)
+ *   ln = scale * sum_hw W g / max(sum_hw W, 1);   loss_b = ln1 [+ ln2 + mu * ||H12 H21 - I||_F^2]
+ *
+ * features [B,C,h,w] (channels_last = 0) or [B,h,w,C] (= 1); masks [B,h,w] at the feature resolution, b2 / b1 NULL ==
+ * ones; lines == 1 ignores f2w, a2, b1, H12, H21 and their gradients (may be NULL).
+ * outputs: loss [B]; parts [B,5] = {ln1, ln2, S1, S2, ln3}; g_f1w, g_f2w (feature layout); g_f1, g_f2 optional (both or
+ * none); g_a1, g_a2 [B,h,w] required (scratch between the launches, final on return); g_b2, g_b1 optional; gH12, gH21.
+ * Three stream-ordered launches (mask sums, streaming pass, per-sample finish).  bh_triplet_rescale multiplies every
+ * non-NULL gradient of sample b by gscale[b] (no-op launch for 1).
+ * ------------------------------------------------------------------------------------------- */
+int bh_triplet_fwd_bwd(const float* f1, const float* f2, const float* f1w, const float* f2w, const float* a1, const float* b2,
+                       const float* a2, const float* b1, const float* H12, const float* H21, int lines, int distance,
+                       int hinge, int mask_crd, float margin1, float margin2, float scale1, float scale2, float mu,
+                       float* loss, float* parts, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2, float* g_a1,
+                       float* g_b2, float* g_a2, float* g_b1, float* gH12, float* gH21, int B, int C, int h, int w,
+                       int channels_last, bh_stream_t stream);
+int bh_triplet_rescale(const float* gscale, float* g_f1w, float* g_f2w, float* g_f1, float* g_f2, float* g_a1, float* g_b2,
+                       float* g_a2, float* g_b1, float* gH12, float* gH21, int B, int C, int h, int w, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K4  N-point normalised DLT (Zeng / DSAC branch), one warp per hypothesis
  *
  * replaces: src/heads/ransac_utils.py:58-72 (gather + kornia.find_homography_dlt: normalize_points,

@@ -9,6 +9,11 @@ Follows, function by function (paths relative to /root/reference):
   bihome_double_line         src/heads/PerceptualHead.py:447-459 (mask pooling), 559-561 (l1 distances),
                              609-665 (ln1, ln2, ln3, loss; margin 'inf', channel-agnostic)
   head_double_line           src/heads/PerceptualHead.py:320-402 (+ the loss above): the whole biHomE head
+  triplet_general            src/heads/PerceptualHead.py:465-538 (one-line: l1 / cosine, numeric margin, MASK_CRD),
+                             :555-665 (double-line: l1 / l2 / cosine, 'inf' or numeric margin, channel-aware /
+                             channel-agnostic) and src/heads/TripletHead.py:78-153 (the same algebra on the content-aware
+                             backbone's full-resolution maps) -- every variant of the masked triplet loss beside the
+                             north-star one, on already pooled masks
   field_to_points            src/heads/PerceptualHead.py:125-146   (forward_map_field)
   dsac_hypotheses            src/heads/ransac_utils.py:48-74       (__sample_hypotheses)
   dsac_scores                src/heads/ransac_utils.py:76-128      ('repr_error' mode)
@@ -85,6 +90,53 @@ def bihome_double_line(f1, f2, f1w, f2w, m1, m2, m1w, m2w, H12, H21, mu):
                       m1w_pooled=a1, m2w_pooled=a2)
 
 
+def triplet_general(f1, f2, f1w, f2w, a1, b2, a2, b1, H12, H21, lines, distance, hinge, margin, mask_crd=False, mu=0.0,
+                    scale=(1.0, 1.0)):
+    """The masked triplet loss of the reference in all its well-defined variants, per sample.
+
+    features [B,C,h,w]; masks [B,h,w] at the feature resolution (a = warped mask of the line's source patch, b = mask of
+    its target patch; b None == ones); ``lines`` 1 (one-line, PerceptualHead.py:465-538; TripletHead 'oneline') or 2;
+    ``distance`` 'l1' | 'l2' | 'cosine' (:559-603); ``hinge`` None (margin 'inf': the signed difference, :614-620),
+    'channel' (channel-aware numeric margin: max(. + margin, 0) per channel, then the channel sum, :622-623) or 'pixel'
+    (max(. + margin, 0) of the channel-aggregated distances, :512 and :625-626); ``mask_crd`` weighs with a alone
+    (:533-537).  ``scale`` multiplies the two lines (the B-fold broadcast of TripletHead.py:91-92 for one-channel
+    features).  Returns (loss_b [B], dict(ln1, ln2, den1, den2, ln3))."""
+    def dist(x, y):
+        if distance == 'l1':
+            return (x - y).abs()                                            # per channel
+        if distance == 'l2':
+            return ((x - y) ** 2).mean(1)                                   # per pixel
+        return 1 - torch.cosine_similarity(x, y, dim=1)                     # per pixel
+
+    def line(la, lb, m):
+        per_channel = la.dim() == 4
+        if hinge is None:
+            return (la - lb).sum(1) if per_channel else la - lb
+        if hinge == 'channel':
+            assert per_channel, 'a per-channel margin needs per-channel distances (l1)'
+            return torch.clamp(la - lb + m, min=0).sum(1)
+        if per_channel:
+            la, lb = la.sum(1), lb.sum(1)
+        return torch.clamp(la - lb + m, min=0)
+
+    def masked(a, b, mat):
+        w = a if (mask_crd or b is None) else a * b
+        den = w.sum(-1).sum(-1)
+        return (w * mat).sum(-1).sum(-1) / torch.max(den, torch.ones_like(den)), den
+
+    l3 = dist(f1, f2)
+    ln1, den1 = masked(a1, b2, line(dist(f1w, f2), l3, margin))
+    ln1 = ln1 * scale[0]
+    zero = torch.zeros_like(ln1)
+    if lines == 1:
+        return ln1, dict(ln1=ln1, ln2=zero, den1=den1, den2=zero, ln3=zero)
+    ln2, den2 = masked(a2, b1, line(dist(f2w, f1), l3, margin))
+    ln2 = ln2 * scale[1]
+    eye = torch.eye(3, dtype=H12.dtype, device=H12.device).unsqueeze(0)
+    ln3 = ((torch.matmul(H12, H21) - eye) ** 2).sum(-1).sum(-1)
+    return ln1 + ln2 + mu * ln3, dict(ln1=ln1, ln2=ln2, den1=den1, den2=den2, ln3=ln3)
+
+
 def head_double_line(patch_1, patch_2, delta_12, delta_21, extractor, mu, mask_1=None, mask_2=None):
     """The whole biHomE head for given 4-point offsets (DeTone/Zhang configs and the tail of Zeng)."""
     m1 = torch.ones_like(patch_1) if mask_1 is None else mask_1
@@ -106,9 +158,9 @@ def field_to_points(pf):
     """pf [B,2,P,Q] -> (coords [B,PQ,2] as (x,y), coords + field, four_points [4,2])."""
     B, _, P, Q = pf.shape
     yy, xx = np.mgrid[0:P, 0:Q]
-    coords = torch.from_numpy(np.stack((xx.reshape(-1), yy.reshape(-1)), axis=-1)).to(pf.dtype)
+    coords = torch.from_numpy(np.stack((xx.reshape(-1), yy.reshape(-1)), axis=-1)).to(pf.dtype).to(pf.device)
     coords = coords.unsqueeze(0).repeat(B, 1, 1)
-    four = torch.tensor([[0, 0], [Q, 0], [Q, P], [0, P]], dtype=pf.dtype)
+    four = torch.tensor([[0, 0], [Q, 0], [Q, P], [0, P]], dtype=pf.dtype, device=pf.device)
     return coords, coords + pf.reshape(B, 2, -1).permute(0, 2, 1), four
 
 
@@ -122,7 +174,7 @@ def dsac_hypotheses(points1, points2, points_per_hypothesis, hypothesis_no, choi
     B = points1.shape[0]
     if choice is None:
         choice = multinomial_choice(points1.shape[1], B * points_per_hypothesis * hypothesis_no)
-    idx = choice.reshape(B, -1, 1).repeat(1, 1, 2)
+    idx = choice.to(points1.device).reshape(B, -1, 1).repeat(1, 1, 2)
     s1 = torch.gather(points1, 1, idx).reshape(B * hypothesis_no, points_per_hypothesis, 2)
     s2 = torch.gather(points2, 1, idx).reshape(B * hypothesis_no, points_per_hypothesis, 2)
     return K.find_homography_dlt(s1, s2).reshape(B, hypothesis_no, 3, 3)

@@ -43,6 +43,16 @@ def bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, mu, m1=None, m2=None):
     return loss_b, parts
 
 
+def triplet_loss(f1, f2, f1w, f2w, a1, b2, a2=None, b1=None, H12=None, H21=None, lines=2, distance='l1', hinge=None, margin=0.0,
+                 mask_crd=False, mu=0.0, scale=(1.0, 1.0)):
+    assert not isinstance(margin, (tuple, list))
+    sq = lambda t: None if t is None else t.reshape(t.shape[0], t.shape[-2], t.shape[-1])
+    loss_b, p = R.triplet_general(f1, f2, f1w, f2w, sq(a1), sq(b2), sq(a2), sq(b1), H12, H21, lines, distance, hinge, margin,
+                                  mask_crd=mask_crd, mu=mu, scale=scale)
+    parts = torch.stack([p['ln1'], p['ln2'], p['den1'], p['den2'], p['ln3']], dim=1).detach()
+    return loss_b, parts
+
+
 def dltn(points1, points2, choice=None):
     from oracle import kornia050 as K
     if choice is not None:
@@ -96,7 +106,7 @@ def fh_affine(x, a, M, gx):
 
 def install(monkeypatch):
     import bihome_b200.functional as F
-    for name, fn in (('dlt4', dlt4), ('warp', warp), ('coverage_mask', coverage_mask), ('bihome_loss', bihome_loss),
+    for name, fn in (('dlt4', dlt4), ('warp', warp), ('coverage_mask', coverage_mask), ('bihome_loss', bihome_loss), ('triplet_loss', triplet_loss),
                      ('dltn', dltn), ('dltn_field', dltn_field), ('mace', mace), ('_fh_moments', fh_moments), ('_fh_fwd', fh_fwd),
                      ('_fh_bwd', fh_bwd), ('_fh_affine', fh_affine)):
         monkeypatch.setattr(F, name, fn)

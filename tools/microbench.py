@@ -134,6 +134,52 @@ def bench_loss(B, P, C, t, nhwc):
            t(lambda: F.bihome_loss(f1, f2, f1w, f2w, m1w, m2w, H12, H21, 0.01)), nbytes)
 
 
+def _torch_triplet(f1, f2, f1w, f2w, a1, a2, h12, h21, hinge, margin, mu):
+    """the ATen op chain K3g replaces (the reference's algebra, PerceptualHead.py:555-665, l1 distances) incl. autograd"""
+    l1, l2, l3 = (f1w - f2).abs(), (f2w - f1).abs(), (f1 - f2).abs()
+
+    def line(la, lb):
+        if hinge is None:
+            return la.sum(1) - lb.sum(1)
+        if hinge == 'channel':
+            return torch.clamp(la - lb + margin, min=0).sum(1)
+        return torch.clamp(la.sum(1) - lb.sum(1) + margin, min=0)
+    d1, d2 = a1.sum(-1).sum(-1), a2.sum(-1).sum(-1)
+    ln1 = ((a1 * line(l1, l3)).sum(-1).sum(-1) / torch.max(d1, torch.ones_like(d1))).sum()
+    ln2 = ((a2 * line(l2, l3)).sum(-1).sum(-1) / torch.max(d2, torch.ones_like(d2))).sum()
+    eye = torch.eye(3, device=h12.device).unsqueeze(0)
+    return ln1 + ln2 + mu * ((torch.matmul(h12, h21) - eye) ** 2).sum()
+
+
+def bench_triplet(B, C, h, nhwc, t):
+    """K3g (bh_triplet_fwd_bwd: three launches) against the torch element-wise ops + autograd it replaces, forward +
+    backward to the warped features, masks and homographies (the extractor is frozen: no gradient for f1 / f2)"""
+    mk = lambda: (torch.rand(B, C, h, h, device='cuda').contiguous(memory_format=torch.channels_last) if nhwc and C > 1
+                  else torch.rand(B, C, h, h, device='cuda'))
+    f1, f2 = mk(), mk()
+    f1w, f2w = mk().requires_grad_(True), mk().requires_grad_(True)
+    a1, a2 = torch.rand(B, h, h, device='cuda', requires_grad=True), torch.rand(B, h, h, device='cuda', requires_grad=True)
+    H12 = (torch.eye(3, device='cuda').repeat(B, 1, 1) + 0.01 * torch.randn(B, 3, 3, device='cuda')).requires_grad_(True)
+    H21 = torch.linalg.inv(H12.detach()).requires_grad_(True)
+    leaves = [f1w, f2w, a1, a2, H12, H21]
+    shape = {'B': B, 'C': C, 'h': h, 'layout': 'nhwc' if nhwc and C > 1 else 'nchw'}
+    for hinge, margin in ((None, 0.0), ('channel', 0.05), ('pixel', 1.0)):
+        nbytes = ((4 + 2) * C * h * h * 4 + 4 * h * h * 4) * B
+        if hinge == 'pixel' and not (nhwc and C > 1):
+            nbytes += 4 * C * h * h * 4 * B      # the planar kernel walks the channels twice (second walk out of L2)
+
+        def fused():
+            loss_b, _ = F.triplet_loss(f1, f2, f1w, f2w, a1, None, a2, None, H12, H21, lines=2, distance='l1', hinge=hinge,
+                                       margin=margin, mu=0.01)
+            torch.autograd.grad(loss_b.sum(), leaves)
+
+        def aten():
+            torch.autograd.grad(_torch_triplet(f1, f2, f1w, f2w, a1, a2, H12, H21, hinge, margin, 0.01), leaves)
+        name = 'hinge=%s' % hinge
+        report('triplet fwd+bwd K3g (%s)' % name, shape, t(fused), nbytes)
+        report('triplet fwd+bwd ATen ops (%s)' % name, shape, t(aten), nbytes)
+
+
 def bench_small(B, P, t):
     H, d = rand_h(B, P)
     d = d.requires_grad_(True)
@@ -187,6 +233,7 @@ def main():
     ap.add_argument('--warp-only', action='store_true', help='time only the 1-channel image warp (forward + backward)')
     ap.add_argument('--dirty', action='store_true', help='flush by memset only (leaves the L2 full of dirty lines: adds their write-back to every timing)')
     ap.add_argument('--loss-cl', action='store_true', help='time the fused loss for every cluster size (BH_LOSS_CL knob)')
+    ap.add_argument('--triplet', action='store_true', help='time K3g (the other loss variants) against the ATen op chain it replaces')
     ap.add_argument('--field-head', action='store_true', help='time K6 (the Zeng field head) against the ATen modules')
     a = ap.parse_args()
     torch.manual_seed(0)
@@ -201,9 +248,15 @@ def main():
         F.mace(torch.randn(256, 4, 2, device='cuda'), torch.randn(256, 4, 2, device='cuda'))
         F.coverage_mask(rand_h(256, 128)[0].detach(), (128, 128), (128, 128), pool=8)      # the stand-alone analytic mask kernel
         bench_field_head(64, 128, t)
+        bench_triplet(256, 64, 32, True, t)
+        bench_triplet(64, 1, 128, False, t)
         torch.cuda.synchronize()
         return
     t = Timer(a.iters, dirty=a.dirty)
+    if a.triplet:
+        for B, C, h, nhwc in ((256, 64, 32, True), (256, 64, 32, False), (64, 1, 128, False), (1024, 64, 32, True)):
+            bench_triplet(B, C, h, nhwc, t)
+        return
     if a.field_head:
         for B in (64, 256):
             bench_field_head(B, 128, t)
