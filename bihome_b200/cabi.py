@@ -33,8 +33,8 @@ SIGNATURES = {
     'bh_fieldhead_supported': (_i, [_i, _i]),
     'bh_fieldhead_grid': (_i, [_i, ctypes.c_longlong]),
     'bh_fieldhead_moments': (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp]),
-    'bh_fieldhead_fwd': (_i, [_vp] * 6 + [_i, _i, _i, _i, _vp]),
-    'bh_fieldhead_bwd': (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
+    'bh_fieldhead_fwd': (_i, [_vp] * 6 + [_i, _i, _i, _i, _i, _vp]),
+    'bh_fieldhead_bwd': (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _vp]),
     'bh_fieldhead_affine': (_i, [_vp] * 4 + [ctypes.c_longlong, _i, _i, _vp]),
 }
 

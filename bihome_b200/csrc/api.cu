@@ -41,8 +41,8 @@ extern "C" const char* bh_strerror(int code) {
 
 extern "C" int bh_tune_set(const char* key, int value) {
     if (!key) return BH_E_NULL;
-    static const char* const names[] = {"warp_path", "loss_variant", "loss_cluster", "warp_variant"};
-    for (int k = 0; k < 4; ++k)
+    static const char* const names[] = {"warp_path", "loss_variant", "loss_cluster", "warp_variant", "fieldhead_variant"};
+    for (int k = 0; k < 5; ++k)
         if (strcmp(key, names[k]) == 0) {
             bh::g_tune[k] = value;
             return BH_OK;

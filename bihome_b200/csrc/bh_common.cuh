@@ -34,7 +34,7 @@ inline int num_sms() {
 
 // Tuning switches of tools/microbench.py (bh_tune_set, include/bihome_b200.h): process-global, never touched by the product
 // path -- every entry point picks its kernel from its arguments alone while these hold their default 0.
-enum TuneKey { kTuneWarpPath = 0, kTuneLossVariant = 1, kTuneLossCluster = 2, kTuneWarpVariant = 3, kTuneCount = 8 };
+enum TuneKey { kTuneWarpPath = 0, kTuneLossVariant = 1, kTuneLossCluster = 2, kTuneWarpVariant = 3, kTuneFieldheadVariant = 4, kTuneCount = 8 };
 extern int g_tune[kTuneCount];
 
 // Every kernel launch in the library goes through BH_LAUNCH_CHECK so the launch counter that

@@ -301,6 +301,14 @@ __global__ void __launch_bounds__(256) affine_acc_kernel(const float* __restrict
 }
 
 #ifndef BH_HOST_EMULATION
+// the tensor-core kernels of the same entry points (fieldhead_mma.cu)
+bool fieldhead_mma_ok(int HW, int cin, int hid);
+int launch_fieldhead_fwd_mma(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* out, long long n_pix,
+                             int HW, int tf32, cudaStream_t stream);
+int launch_fieldhead_bwd_mma(const float* x, const float* W1, const float* b1, const float* W2, const float* gOut, float* gx, float* partials,
+                             long long n_pix, int HW, int tf32, cudaStream_t stream);
+inline bool use_mma(int HW, int cin, int hid) { return g_tune[kTuneFieldheadVariant] != 1 && fieldhead_mma_ok(HW, cin, hid); }
+
 inline int fh_grid(long long n_items, int per_sm) {
     const long long cap = static_cast<long long>(kNumSMs) * per_sm;
     return static_cast<int>(n_items < 1 ? 1 : (n_items < cap ? n_items : cap));
@@ -318,7 +326,7 @@ extern "C" int bh_fieldhead_grid(int what, long long n_pix) {
     using namespace bh;
     if (n_pix <= 0) return 0;
     if (what == 0) return fh_grid((n_pix + kMomTile - 1) / kMomTile, 7);   // moments: 7 x 288 threads per SM
-    return fh_grid((n_pix + kFhTile - 1) / kFhTile, 5);                    // backward: 37 KB of shared memory per CTA
+    return fh_grid((n_pix + kFhTile - 1) / kFhTile, 3);                    // backward (either kernel): 32-pixel tiles, 3 CTAs per SM
 }
 
 extern "C" int bh_fieldhead_moments(const float* x, double* partials, long long n_pix, int cin, bh_stream_t stream) {
@@ -332,26 +340,29 @@ extern "C" int bh_fieldhead_moments(const float* x, double* partials, long long 
 }
 
 extern "C" int bh_fieldhead_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* out,
-                                int B, int HW, int cin, int hid, bh_stream_t stream) {
+                                int B, int HW, int cin, int hid, int tf32, bh_stream_t stream) {
     using namespace bh;
     if (!x || !W1 || !b1 || !W2 || !b2 || !out) return BH_E_NULL;
     if (B <= 0 || HW <= 0) return BH_E_SHAPE;
     if (!bh_fieldhead_supported(cin, hid)) return BH_E_UNSUPPORTED;
     if (!aligned16(x)) return BH_E_ALIGN;
     const long long n_pix = static_cast<long long>(B) * HW;
+    if (use_mma(HW, cin, hid)) return launch_fieldhead_fwd_mma(x, W1, b1, W2, b2, out, n_pix, HW, tf32, reinterpret_cast<cudaStream_t>(stream));
     fieldhead_fwd_kernel<16, 128><<<fh_grid((n_pix + 255) / 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, W1, b1, W2, b2, out, n_pix, HW);
     return launch_status();
 }
 
 extern "C" int bh_fieldhead_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* gOut, float* gx,
-                                float* partials, int B, int HW, int cin, int hid, bh_stream_t stream) {
+                                float* partials, int B, int HW, int cin, int hid, int tf32, bh_stream_t stream) {
     using namespace bh;
     if (!x || !W1 || !b1 || !W2 || !gOut || !gx || !partials) return BH_E_NULL;
     if (B <= 0 || HW <= 0) return BH_E_SHAPE;
     if (!bh_fieldhead_supported(cin, hid)) return BH_E_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(gx)) return BH_E_ALIGN;
     const long long n_pix = static_cast<long long>(B) * HW;
+    if (use_mma(HW, cin, hid))
+        return launch_fieldhead_bwd_mma(x, W1, b1, W2, gOut, gx, partials, n_pix, HW, tf32, reinterpret_cast<cudaStream_t>(stream));
     fieldhead_bwd_kernel<16, 128><<<bh_fieldhead_grid(1, n_pix), kFhThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, W1, b1, W2, gOut, gx, partials, n_pix, HW);
     return launch_status();

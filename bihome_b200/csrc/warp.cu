@@ -1577,15 +1577,34 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// one 128-bit reduction (SASS REDG.E.ADD.F32x4) instead of four scalar atomics
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 scale4(const float4& g, float w) { return make_float4(g.x * w, g.y * w, g.z * w, g.w * w); }
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 shfl_up4(const float4& v, int d) {
+    return make_float4(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d), __shfl_up_sync(0xffffffffu, v.z, d),
+                       __shfl_up_sync(0xffffffffu, v.w, d));
+}
+
 // Backward, generic layouts.  grid = (chunks, B); every block reduces its pixel chunk to 9 partial sums
-// (partials[b][chunk][9]); warp_bwd_finish_kernel adds them in order.  Optional image gradient by red.add.
+// (partials[b][chunk][9]); warp_bwd_finish_kernel adds them in order.
+// Optional image gradient (gSrc, accumulated): WARP-AGGREGATED reductions.  The lanes of a warp walk neighbouring output
+// pixels of a row (`agg` lanes apart: 1 in the planar layouts, C/4 in channels-last), and at scales near one the right-hand
+// taps of a pixel are the left-hand taps of its neighbour: the neighbour's two right-hand contributions arrive by shuffle
+// and are added in registers, so a pixel issues two reductions instead of four (the warp's first pixel: four); in
+// channels-last each of them is one 128-bit red.global.add.v4.f32 for four channels.  The merge is keyed on the tap
+// addresses being EQUAL, nothing else, so it is exact whatever the homography does.
 template <bool kVec4>
 __global__ void __launch_bounds__(256)
     warp_bwd_generic_kernel(const float* __restrict__ src, const float* __restrict__ H, const float* __restrict__ gOut,
                             const float* __restrict__ gMaskPooled, float* __restrict__ partials, float* __restrict__ gSrc,
                             int C, int Hs, int Ws, int Ho, int Wo, int pool, Layout ls, Layout lo) {
     __shared__ float red[9 * 8];
+    constexpr unsigned kFull = 0xffffffffu;
     const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const Hmat hm = load_h(H, b);
     float acc[9];
 #pragma unroll
@@ -1594,16 +1613,29 @@ __global__ void __launch_bounds__(256)
     // kVec4 (channels-last): a group of cq threads shares a pixel and splits the channels 4 by 4
     const int cq = kVec4 ? (C >> 2) : 1;
     const long long nwork = static_cast<long long>(npix) * cq;
-    for (long long wi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; wi < nwork;
-         wi += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // lanes `agg` apart hold the same channels of x-neighbouring pixels (0: no such lane inside the warp)
+    const int agg = (gSrc != nullptr && gOut != nullptr && cq < 32 && (cq & (cq - 1)) == 0) ? cq : 0;
+    // warp-uniform trip count: the shuffles below need every lane of the warp
+    for (long long w0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x - lane; w0 < nwork;
+         w0 += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const bool live = w0 + lane < nwork;
+        const long long wi = live ? w0 + lane : nwork - 1;
         const int q = kVec4 ? static_cast<int>(wi % cq) : 0;
         const int r = static_cast<int>(wi / cq);
         const int y = r / Wo, x = r - y * Wo;
         float u, v, rw;
         project(hm, static_cast<float>(x), static_cast<float>(y), u, v, rw);
         const Taps t = make_taps(u, v, Ws, Hs);
+        // does this lane take over the right-hand taps of the lane `agg` below it / were its own taken by the lane above?
+        bool absorb = false, absorbed = false;
+        if (agg > 0) {
+            const int px0 = __shfl_up_sync(kFull, t.x0, agg), py0 = __shfl_up_sync(kFull, t.y0, agg);
+            const int plive = __shfl_up_sync(kFull, static_cast<int>(live), agg);
+            absorb = lane >= agg && live && plive != 0 && px0 + 1 == t.x0 && py0 == t.y0;
+            absorbed = __shfl_down_sync(kFull, static_cast<int>(absorb), agg) != 0 && lane + agg < 32;
+        }
         float gu = 0.0f, gv = 0.0f;
-        if (gMaskPooled != nullptr && q == 0) {
+        if (gMaskPooled != nullptr && q == 0 && live) {
             float du, dv;
             cover_grad(t, du, dv);
             const float gm = __ldg(gMaskPooled + (static_cast<long long>(b) * (Ho / pool) + y / pool) * (Wo / pool) + x / pool) /
@@ -1615,49 +1647,71 @@ __global__ void __launch_bounds__(256)
             const float* sp = src + b * ls.sb;
             const float* gp = gOut + b * lo.sb + static_cast<long long>(y) * lo.sy + static_cast<long long>(x) * lo.sx;
             float* gs = gSrc ? gSrc + b * ls.sb : nullptr;
+            const float w00 = t.wx0 * t.wy0, w10 = t.wx1 * t.wy0, w01 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
             if (kVec4) {
                 const long long o = (static_cast<long long>(t.y0) * Ws + t.x0) * C + q * 4;
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gp + q * 4));
-                const float4 nw = ld4_or_zero(sp + o, t.inx0 && t.iny0);
-                const float4 ne = ld4_or_zero(sp + o + C, t.inx1 && t.iny0);
-                const float4 sw = ld4_or_zero(sp + o + static_cast<long long>(Ws) * C, t.inx0 && t.iny1);
-                const float4 se = ld4_or_zero(sp + o + static_cast<long long>(Ws) * C + C, t.inx1 && t.iny1);
-                float du, dv;
-                blend_grad(t, nw.x, ne.x, sw.x, se.x, du, dv); gu = fmaf(g.x, du, gu); gv = fmaf(g.x, dv, gv);
-                blend_grad(t, nw.y, ne.y, sw.y, se.y, du, dv); gu = fmaf(g.y, du, gu); gv = fmaf(g.y, dv, gv);
-                blend_grad(t, nw.z, ne.z, sw.z, se.z, du, dv); gu = fmaf(g.z, du, gu); gv = fmaf(g.z, dv, gv);
-                blend_grad(t, nw.w, ne.w, sw.w, se.w, du, dv); gu = fmaf(g.w, du, gu); gv = fmaf(g.w, dv, gv);
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    g = __ldg(reinterpret_cast<const float4*>(gp + q * 4));
+                    const float4 nw = ld4_or_zero(sp + o, t.inx0 && t.iny0);
+                    const float4 ne = ld4_or_zero(sp + o + C, t.inx1 && t.iny0);
+                    const float4 sw = ld4_or_zero(sp + o + static_cast<long long>(Ws) * C, t.inx0 && t.iny1);
+                    const float4 se = ld4_or_zero(sp + o + static_cast<long long>(Ws) * C + C, t.inx1 && t.iny1);
+                    float du, dv;
+                    blend_grad(t, nw.x, ne.x, sw.x, se.x, du, dv); gu = fmaf(g.x, du, gu); gv = fmaf(g.x, dv, gv);
+                    blend_grad(t, nw.y, ne.y, sw.y, se.y, du, dv); gu = fmaf(g.y, du, gu); gv = fmaf(g.y, dv, gv);
+                    blend_grad(t, nw.z, ne.z, sw.z, se.z, du, dv); gu = fmaf(g.z, du, gu); gv = fmaf(g.z, dv, gv);
+                    blend_grad(t, nw.w, ne.w, sw.w, se.w, du, dv); gu = fmaf(g.w, du, gu); gv = fmaf(g.w, dv, gv);
+                }
                 if (gs) {
-                    const float w00 = t.wx0 * t.wy0, w10 = t.wx1 * t.wy0, w01 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
-                    const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (t.inx0 && t.iny0) atomicAdd(gs + o + k, gg[k] * w00);
-                        if (t.inx1 && t.iny0) atomicAdd(gs + o + C + k, gg[k] * w10);
-                        if (t.inx0 && t.iny1) atomicAdd(gs + o + static_cast<long long>(Ws) * C + k, gg[k] * w01);
-                        if (t.inx1 && t.iny1) atomicAdd(gs + o + static_cast<long long>(Ws) * C + C + k, gg[k] * w11);
+                    float4 c_nw = scale4(g, w00), c_sw = scale4(g, w01);
+                    const float4 c_ne = scale4(g, w10), c_se = scale4(g, w11);
+                    if (agg > 0) {
+                        const float4 r_ne = shfl_up4(c_ne, agg), r_se = shfl_up4(c_se, agg);
+                        if (absorb) { c_nw = add4(c_nw, r_ne); c_sw = add4(c_sw, r_se); }
+                    }
+                    if (live) {
+                        if (t.inx0 && t.iny0) red_add_v4(gs + o, c_nw);
+                        if (t.inx0 && t.iny1) red_add_v4(gs + o + static_cast<long long>(Ws) * C, c_sw);
+                        if (!absorbed) {
+                            if (t.inx1 && t.iny0) red_add_v4(gs + o + C, c_ne);
+                            if (t.inx1 && t.iny1) red_add_v4(gs + o + static_cast<long long>(Ws) * C + C, c_se);
+                        }
                     }
                 }
             } else {
                 for (int c = 0; c < C; ++c) {
-                    const float g = __ldg(gp + static_cast<long long>(c) * lo.sc);
-                    float nw, ne, sw, se, du, dv;
-                    gather4(sp + static_cast<long long>(c) * ls.sc, t, ls.sy, ls.sx, nw, ne, sw, se);
-                    blend_grad(t, nw, ne, sw, se, du, dv);
-                    gu = fmaf(g, du, gu);
-                    gv = fmaf(g, dv, gv);
+                    float g = 0.0f;
+                    if (live) {
+                        g = __ldg(gp + static_cast<long long>(c) * lo.sc);
+                        float nw, ne, sw, se, du, dv;
+                        gather4(sp + static_cast<long long>(c) * ls.sc, t, ls.sy, ls.sx, nw, ne, sw, se);
+                        blend_grad(t, nw, ne, sw, se, du, dv);
+                        gu = fmaf(g, du, gu);
+                        gv = fmaf(g, dv, gv);
+                    }
                     if (gs) {
-                        float* gc = gs + static_cast<long long>(c) * ls.sc + static_cast<long long>(t.y0) * ls.sy +
-                                    static_cast<long long>(t.x0) * ls.sx;
-                        if (t.inx0 && t.iny0) atomicAdd(gc, g * t.wx0 * t.wy0);
-                        if (t.inx1 && t.iny0) atomicAdd(gc + ls.sx, g * t.wx1 * t.wy0);
-                        if (t.inx0 && t.iny1) atomicAdd(gc + ls.sy, g * t.wx0 * t.wy1);
-                        if (t.inx1 && t.iny1) atomicAdd(gc + ls.sy + ls.sx, g * t.wx1 * t.wy1);
+                        float c_nw = g * w00, c_sw = g * w01;
+                        const float c_ne = g * w10, c_se = g * w11;
+                        if (agg > 0) {
+                            const float r_ne = __shfl_up_sync(kFull, c_ne, agg), r_se = __shfl_up_sync(kFull, c_se, agg);
+                            if (absorb) { c_nw += r_ne; c_sw += r_se; }
+                        }
+                        if (live) {
+                            float* gc = gs + static_cast<long long>(c) * ls.sc + static_cast<long long>(t.y0) * ls.sy +
+                                        static_cast<long long>(t.x0) * ls.sx;
+                            if (t.inx0 && t.iny0) atomicAdd(gc, c_nw);
+                            if (t.inx0 && t.iny1) atomicAdd(gc + ls.sy, c_sw);
+                            if (!absorbed) {
+                                if (t.inx1 && t.iny0) atomicAdd(gc + ls.sx, c_ne);
+                                if (t.inx1 && t.iny1) atomicAdd(gc + ls.sy + ls.sx, c_se);
+                            }
+                        }
                     }
                 }
             }
         }
-        accum_gh(acc, gu, gv, u, v, rw, static_cast<float>(x), static_cast<float>(y));
+        if (live) accum_gh(acc, gu, gv, u, v, rw, static_cast<float>(x), static_cast<float>(y));
     }
     block_sum<9>(acc, red);
     store9(acc, partials + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * 9);

@@ -64,3 +64,60 @@ def train_step(model, data, optimizer, scheduler=None, gradient_clip=-1):
     if scheduler is not None:
         scheduler.step()
     return loss, delta_gt, delta_hat
+
+
+class GraphedStep:
+    """Forward + backward of ``nn.Sequential(backbone, head)`` captured ONCE in a CUDA graph and replayed per step
+    ("CUDA-graph capture of the whole head").  The ~2 000 launches of a step (cuDNN, ATen and the
+    C-ABI kernels, which launch on torch's current stream and therefore land in the capture) become one graph launch:
+    at small batches, where the step is launch-bound, that is the whole step time.
+
+    The batch lives in static device buffers (``__call__`` copies the new batch into them), the parameter gradients in
+    the graph's private pool (never set them to None); the optimizer and the scheduler stay eager, so learning-rate
+    schedules and checkpoints work unchanged.  Random draws inside the head (``torch.multinomial``) use torch's
+    graph-safe Philox state.  Single process only: under DDP the bucketed all-reduce hooks are not capturable this way.
+    """
+
+    def __init__(self, model, example_batch, warmup=3):
+        if not torch.cuda.is_available():
+            raise RuntimeError('bihome_b200: GraphedStep needs a CUDA device (no CPU fallback)')
+        self.model = model
+        self.static = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        params = [p for p in model.parameters() if p.requires_grad]
+        # the warm-up passes must not count: BatchNorm running statistics (and their batch counters) are put back afterwards
+        buffers = [(b, b.detach().clone()) for b in model.buffers()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # warm-up off the capture: lazy initialisation (cuDNN plans, function attributes)
+            for _ in range(warmup):
+                for p in params:
+                    p.grad = None
+                loss, _, _ = model(dict(self.static))
+                loss.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        for p in params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.delta_gt, self.delta_hat = model(dict(self.static))
+            self.loss.backward()
+        with torch.no_grad():
+            for b, saved in buffers:
+                b.copy_(saved)
+
+    def __call__(self, batch):
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.delta_gt, self.delta_hat
+
+
+def graphed_train_step(step, data, optimizer, scheduler=None, gradient_clip=-1):
+    """train_step with the forward + backward replayed from a GraphedStep"""
+    loss, delta_gt, delta_hat = step(data)
+    if gradient_clip > 0:
+        torch.nn.utils.clip_grad_norm_(step.model.parameters(), gradient_clip)
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    return loss, delta_gt, delta_hat

@@ -529,13 +529,19 @@ def _fh_moments(x):
     return s[:C], s[C:].view(C, C)
 
 
+def _fh_tf32():
+    """K6 replaces two cuDNN convolutions: it multiplies in TF32 exactly when they would (torch.backends.cudnn.allow_tf32,
+    torch's default) and float32-faithfully otherwise"""
+    return int(bool(torch.backends.cudnn.allow_tf32))
+
+
 def _fh_fwd(x, W1, b1, W2, b2):
     """x [B,C,H,W] channels-last, folded W1 [hid,C], b1 [hid], W2 [2,hid], b2 [2] -> field [B,2,H,W] (planar)"""
     B, C, H, W = x.shape
     out = torch.empty(B, 2, H, W, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _timed('bh_fieldhead_fwd'):
         cabi.check(cabi.lib().bh_fieldhead_fwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(out), B, H * W, C,
-                                               W1.shape[0], _stream()), 'bh_fieldhead_fwd')
+                                               W1.shape[0], _fh_tf32(), _stream()), 'bh_fieldhead_fwd')
     return out
 
 
@@ -549,7 +555,7 @@ def _fh_bwd(x, W1, b1, W2, g_out):
     gx = torch.empty_like(x)
     with torch.cuda.device(x.device), _timed('bh_fieldhead_bwd'):
         cabi.check(lib.bh_fieldhead_bwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(g_out), _ptr(gx), _ptr(parts), B, H * W, C,
-                                        hid, _stream()), 'bh_fieldhead_bwd')
+                                        hid, _fh_tf32(), _stream()), 'bh_fieldhead_bwd')
     s = parts.sum(0)
     return (gx, s[:hid * C].view(hid, C), s[hid * C:hid * C + hid], s[hid * C + hid:hid * C + 3 * hid].view(2, hid),
             s[hid * C + 3 * hid:])
@@ -624,8 +630,11 @@ class _FieldHead(torch.autograd.Function):
         if training:
             g1, g2 = grads[4], grads[5]
             gx = _fh_affine(x, g1.to(x.dtype).contiguous(), (g2 + g2.t()).to(x.dtype).contiguous(), gx)
-        return (gx, grads[0].to(W1.dtype).reshape(W1.shape), grads[1].to(b1.dtype), grads[2].to(gamma.dtype),
-                grads[3].to(beta.dtype), gW2.to(W2.dtype).reshape(W2.shape), gb2.to(W2.dtype), None, None, None, None)
+        # gradients in the parameters' own strides (a channels-last model keeps its 1x1 kernels as [hid,cin,1,1] with strides
+        # [cin,1,cin,cin]): DDP's bucket views expect exactly that layout
+        like = lambda g, p: torch.empty_like(p).copy_(g.to(p.dtype).reshape(p.shape))
+        return (gx, like(grads[0], W1), grads[1].to(b1.dtype), grads[2].to(gamma.dtype),
+                grads[3].to(beta.dtype), like(gW2, W2), gb2.to(W2.dtype), None, None, None, None)
 
 
 def field_head_enabled(device=None):

@@ -149,6 +149,15 @@ class Model(nn.Module):
         field = perspective_field.reshape(B, 2, -1).permute(0, 2, 1)
         return self_coordinate_field + field, self_coordinate_field, self_four_points
 
+    def _corner_points(self, Wf, Hf, device):
+        """[[0,0],[Wf,0],[Wf,Hf],[0,Hf]] on the device, built once per geometry: a host-to-device copy per step would
+        synchronise the host and cannot be captured in a CUDA graph (engine.GraphedStep)"""
+        key = (int(Wf), int(Hf), str(device))
+        cache = self.__dict__.setdefault('_corner_cache', {})
+        if key not in cache:
+            cache[key] = torch.tensor([[0, 0], [Wf, 0], [Wf, Hf], [0, Hf]], device=device, dtype=torch.float32)
+        return cache[key]
+
     def _field_to_delta(self, pf, which):
         """DSAC branch of the reference's forward (:164-178 / :187-205) -> (delta_hats [B,n,4,2], scores or None)."""
         B, _, Hf, Wf = pf.shape
@@ -160,7 +169,7 @@ class Model(nn.Module):
             # one hypothesis: softmax score == 1, nothing but H is needed -> fused K4 straight from the field
             if choice is None:
                 choice = sample_choice(Hf * Wf, B * M, pf.device)
-            four = torch.tensor([[0, 0], [Wf, 0], [Wf, Hf], [0, Hf]], device=pf.device, dtype=torch.float32)
+            four = self._corner_points(Wf, Hf, pf.device)
             _, delta = F.dltn_field(pf, choice.reshape(B, M), four)
             return delta.reshape(B, 1, 4, 2), torch.ones(B, 1, device=pf.device, dtype=pf.dtype)
         cf = self.coordinate_field_12 if which == 0 else self.coordinate_field_21

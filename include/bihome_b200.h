@@ -205,7 +205,11 @@ int bh_pairgen_image(const uint8_t* images, const int32_t* index, const double* 
  *   bh_fieldhead_grid        CTAs the moments (what = 0) / backward (what = 1) launch uses == rows of `partials`.
  *   bh_fieldhead_moments     partials [grid, cin + cin*cin] double: per-CTA sums of x_i, then of x_i x_k (the full
  *                            symmetric matrix, row-major); the caller adds the rows (fixed order).
- *   bh_fieldhead_fwd         out = W2 relu(W1 x + b1) + b2.
+ *   bh_fieldhead_fwd         out = W2 relu(W1 x + b1) + b2.  fwd / bwd run on the tensor cores (mma.sync TF32,
+ *                            csrc/fieldhead_mma.cu) when HW % 32 == 0, on scalar per-pixel kernels otherwise.  tf32 = 0:
+ *                            operands split into a TF32 head and a float32 remainder, three products per step --
+ *                            float32-faithful; tf32 = 1: operands rounded to TF32, one product -- the arithmetic of the
+ *                            cuDNN convolutions this replaces under torch.backends.cudnn.allow_tf32 (the caller passes it)
  *   bh_fieldhead_bwd         gx [n_pix, cin] = d/dx (overwritten); partials [grid, hid*cin + hid + 2*hid + 2] float:
  *                            per-CTA { gW1 | gb1 | gW2 | gb2 }, the caller adds the rows.
  *   bh_fieldhead_affine      gx (+)= a + M x per pixel, a [cin], M [cin,cin]: the adjoint of the moments (how the
@@ -215,9 +219,9 @@ int bh_fieldhead_supported(int cin, int hid);
 int bh_fieldhead_grid(int what, long long n_pix);
 int bh_fieldhead_moments(const float* x, double* partials, long long n_pix, int cin, bh_stream_t stream);
 int bh_fieldhead_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* out,
-                     int B, int HW, int cin, int hid, bh_stream_t stream);
+                     int B, int HW, int cin, int hid, int tf32, bh_stream_t stream);
 int bh_fieldhead_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* gOut, float* gx,
-                     float* partials, int B, int HW, int cin, int hid, bh_stream_t stream);
+                     float* partials, int B, int HW, int cin, int hid, int tf32, bh_stream_t stream);
 int bh_fieldhead_affine(const float* x, const float* a, const float* M, float* gx, long long n_pix, int cin,
                         int accumulate, bh_stream_t stream);
 
@@ -235,6 +239,7 @@ int bh_mace(const float* delta_gt, const float* delta_hat, float* out, int B, bh
  *   "warp_variant" tile kernels: bit 0 = four warps per tile (8 rows each) instead of two (16 rows each)
  *   "loss_variant" 0 auto, 1 ldg cluster kernel, 2 TMA cluster kernel, 3 persistent TMA stream
  *   "loss_cluster" 0 auto, 1 | 2 | 4 | 8 CTAs per cluster
+ *   "fieldhead_variant" 0 auto (the tensor-core kernels when HW % 32 == 0), 1 the scalar per-pixel kernels
  * returns BH_E_UNSUPPORTED for an unknown key.
  * ------------------------------------------------------------------------------------------- */
 int bh_tune_set(const char* key, int value);

@@ -262,3 +262,28 @@ def test_no_data_race_under_thread_sanitizer():
     if 'FATAL: ThreadSanitizer' in r.stderr and 'data race' not in r.stderr:
         pytest.skip('ThreadSanitizer cannot run here: ' + r.stderr.strip().splitlines()[0])
     assert r.returncode == 0 and 'data race' not in r.stderr and r.stdout.startswith('ok'), r.stderr[-2000:]
+
+
+def test_tensor_core_kernels_fragment_mapping_on_the_lane_emulator():
+    """csrc/fieldhead_mma.cu takes its mma.sync fragments straight from 128-bit loads and from accumulator registers; the
+    lane-by-lane restatement of that data movement (tests/emu/mma_lane_emulator.py, on top of the PTX ISA fragment layout of
+    mma.m16n8k8) must reproduce the dense algebra: forward field, d/dx and the four weight gradients"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+    import mma_lane_emulator as E
+    rs = np.random.RandomState(0)
+    HW, B = 64, 2
+    n = B * HW
+    x, W1, b1 = rs.randn(n, 16), rs.randn(128, 16) * 0.3, rs.randn(128) * 0.2
+    W2, b2, g_out = rs.randn(2, 128) * 0.2, rs.randn(2), rs.randn(B, 2, HW)
+    pre = x @ W1.T + b1
+    h = np.maximum(pre, 0)
+    out = (h @ W2.T + b2).reshape(B, HW, 2).transpose(0, 2, 1)
+    G = g_out.transpose(0, 2, 1).reshape(n, 2)
+    gh = (G @ W2) * (pre > 0)
+    assert np.abs(E.fwd(x, W1, b1, W2, b2, HW) - out).max() < 1e-12
+    assert np.abs(E.gx(x, W1, b1, W2, g_out, HW) - gh @ W1).max() < 1e-12
+    gW1, gb1, gW2, gb2 = E.gw(x, W1, b1, W2, g_out, HW)
+    assert np.abs(gW1 - gh.T @ x).max() < 1e-12 and np.abs(gb1 - gh.sum(0)).max() < 1e-12
+    assert np.abs(gW2 - G.T @ h).max() < 1e-12 and np.abs(gb2 - G.sum(0)).max() < 1e-12

@@ -25,10 +25,34 @@ def k6_on_this_device():
         pytest.skip("K6 did not pass this device's self-test (or BH_FIELD_HEAD=aten): the backbone uses the ATen modules")
 
 
+def tf32_rna(t):
+    """round a float32 tensor to the nearest TF32 number, ties away from zero (PTX cvt.rna.tf32.f32), as float64"""
+    bits = t.float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32).double()
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize('B,H,W', [(1, 4, 8), (3, 9, 7), (2, 128, 128), (5, 33, 65)])
-def test_device_entry_points_vs_float64(k6_on_this_device, B, H, W):
+@pytest.mark.parametrize('variant', ['auto', 'scalar', 'tf32'])
+@pytest.mark.parametrize('B,H,W', [(1, 4, 8), (3, 9, 7), (2, 128, 128), (5, 33, 65), (7, 16, 24), (300, 8, 8)])
+def test_device_entry_points_vs_float64(k6_on_this_device, B, H, W, variant):
+    """'auto' runs the tensor-core kernels (csrc/fieldhead_mma.cu: mma.sync TF32 with float32 head + remainder operands)
+    wherever H*W is a multiple of 32 and the scalar kernels elsewhere; 'scalar' forces the per-pixel kernels; 'tf32' is the
+    tensor-core path with torch.backends.cudnn.allow_tf32 on (operands rounded to TF32, one product), compared with the
+    float64 evaluation of the SAME rounded operands"""
     import bihome_b200.functional as F
+    if variant == 'tf32' and (H * W) % 32:
+        pytest.skip('the scalar kernels have no TF32 mode')
+    saved = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = variant == 'tf32'
+    F.tune('fieldhead_variant', 1 if variant == 'scalar' else 0)
+    try:
+        _entry_points_vs_float64(F, B, H, W, variant == 'tf32')
+    finally:
+        F.tune('fieldhead_variant', 0)
+        torch.backends.cudnn.allow_tf32 = saved
+
+
+def _entry_points_vs_float64(F, B, H, W, tf32):
     gen = torch.Generator().manual_seed(B * 100 + H)
     x = torch.relu(torch.randn(B, 16, H, W, generator=gen) + 0.3).cuda().contiguous(memory_format=torch.channels_last)
     W1 = (torch.randn(128, 16, generator=gen) * 0.3).cuda()
@@ -37,18 +61,32 @@ def test_device_entry_points_vs_float64(k6_on_this_device, B, H, W):
     b2 = torch.randn(2, generator=gen).cuda()
     g = torch.randn(B, 2, H, W, generator=gen).cuda()
     d = lambda t: t.double()
-    pre = torch.nn.functional.conv2d(d(x), d(W1).view(128, 16, 1, 1), d(b1))
+    rnd = tf32_rna if tf32 else d                          # what the contraction operands look like inside the kernel
+    pre = torch.nn.functional.conv2d(rnd(x), rnd(W1).view(128, 16, 1, 1), d(b1))
     g = mute_knife_edge_pixels(g, pre, 1e-4)             # float32 kernel against float64 reference: see the helper
     s1, s2 = F._fh_moments(x)
     r1, r2 = cpu_kernels.fh_moments(x)
     assert rel_l2(s1.cpu().numpy(), r1.cpu().numpy()) < 1e-6 and rel_l2(s2.cpu().numpy(), r2.cpu().numpy()) < 1e-6
     out = F._fh_fwd(x, W1, b1, W2, b2)
-    ref = cpu_kernels.fh_fwd(d(x), d(W1), d(b1), d(W2), d(b2))
+    ref = cpu_kernels.fh_fwd(rnd(x), rnd(W1), d(b1), d(W2), d(b2))
     assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
     got = F._fh_bwd(x, W1, b1, W2, g)
-    want = cpu_kernels.fh_bwd(d(x), d(W1), d(b1), d(W2), d(g))
+    if tf32:
+        # every contraction with its operands rounded the way the kernels round them: gh and h (activations), x, W1, g
+        X = rnd(x).permute(0, 2, 3, 1).reshape(-1, 16)
+        P = X @ rnd(W1).t() + d(b1)
+        G = d(g).permute(0, 2, 3, 1).reshape(-1, 2)
+        gh = (G @ d(W2)) * (P > 0)
+        ghr, hr = tf32_rna(gh.float()), tf32_rna(torch.relu(P).float())
+        gx = torch.empty_like(x, dtype=torch.float64)
+        gx.copy_((ghr @ rnd(W1)).reshape(B, H, W, 16).permute(0, 3, 1, 2))
+        want = (gx, ghr.t() @ X, gh.sum(0), tf32_rna(G.float()).t() @ hr, G.sum(0))
+        tol = 5e-5          # gh / h are rounded from float32 values that differ in the last bit between kernel and reference
+    else:
+        want = cpu_kernels.fh_bwd(d(x), d(W1), d(b1), d(W2), d(g))
+        tol = 2e-5
     for a, b, name in zip(got, want, ('gx', 'gW1', 'gb1', 'gW2', 'gb2')):
-        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, name
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < tol, name
     a, M = torch.randn(16, generator=gen).cuda(), torch.randn(16, 16, generator=gen).cuda()
     gx = got[0].clone()
     F._fh_affine(x, a, M, gx)

@@ -83,8 +83,10 @@ def forward_loss(model, data, loss_fn):
 
 
 def train_one_epoch(model, loader, optimizer, gradient_clip, scheduler, loss_fn, epoch, steps_per_epoch, checkpointer,
-                    checkpoint_arguments, log_step, summary_writer, self_supervised=False, log_verbose=False, max_steps=None):
+                    checkpoint_arguments, log_step, summary_writer, self_supervised=False, log_verbose=False, max_steps=None,
+                    cuda_graph=False):
     model.train()
+    graphed = None
     # a checkpoint written in the middle of an epoch (--max_steps) resumes at the iteration after it: no step is repeated
     # and no TensorBoard step number is reused
     skip = min(max(checkpoint_arguments['step'] - epoch * steps_per_epoch, 0), steps_per_epoch)
@@ -93,7 +95,19 @@ def train_one_epoch(model, loader, optimizer, gradient_clip, scheduler, loss_fn,
     for iter_no, data in enumerate(batches, start=skip):
         step = epoch * steps_per_epoch + iter_no + 1
         logging_step = step % log_step == 0
-        optimizer.zero_grad(set_to_none=True)
+        if cuda_graph and loss_fn in STRING_LOSSES and not logging_step:
+            # forward + backward replayed from one CUDA graph (engine.GraphedStep); logging steps stay eager (they read
+            # scalars back to the host)
+            if graphed is None:
+                graphed = engine.GraphedStep(model, data)
+            loss, delta_gt, delta_hat = engine.graphed_train_step(graphed, data, optimizer, scheduler, gradient_clip)
+            if max_steps is not None and step >= max_steps:
+                break
+            continue
+        if graphed is None:
+            optimizer.zero_grad(set_to_none=True)
+        else:
+            optimizer.zero_grad(set_to_none=False)      # the graph owns the gradient buffers
         if logging_step and not isinstance(summary_writer, _NullWriter):
             data['summary_writer'] = summary_writer
             data['summary_writer_step'] = step
@@ -156,7 +170,7 @@ def eval_one_epoch(model, loader, loss_fn, epoch, steps_per_epoch, summary_write
 
 def do_train(model, train_loader, test_loader, optimizer, gradient_clip, scheduler, loss_fn, epochs, steps_per_epoch,
              checkpointer, checkpoint_arguments, log_dir='logs', log_step=1, self_supervised=False, log_verbose=False,
-             rank=0, max_steps=None, world=1):
+             rank=0, max_steps=None, world=1, cuda_graph=False):
     writer = make_summary_writer(log_dir, enabled=rank == 0)
     start_epoch = checkpoint_arguments['step'] // steps_per_epoch
     if hasattr(train_loader, 'step'):
@@ -166,7 +180,8 @@ def do_train(model, train_loader, test_loader, optimizer, gradient_clip, schedul
             print('Training epoch: {}'.format(epoch))
         t0 = time.perf_counter()
         step = train_one_epoch(model, train_loader, optimizer, gradient_clip, scheduler, loss_fn, epoch, steps_per_epoch,
-                               checkpointer, checkpoint_arguments, log_step, writer, self_supervised, log_verbose, max_steps)
+                               checkpointer, checkpoint_arguments, log_step, writer, self_supervised, log_verbose, max_steps,
+                               cuda_graph=cuda_graph and world == 1)
         torch.cuda.synchronize()
         if rank == 0:
             done = step - epoch * steps_per_epoch
@@ -189,7 +204,8 @@ def _plain(model):
     return model.module if isinstance(model, torch.nn.parallel.DistributedDataParallel) else model
 
 
-def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, channels_last=True, log_dir=None, init_seed=0):
+def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, channels_last=True, log_dir=None, init_seed=0,
+         cuda_graph=False):
     config = engine.load_config(config_file_path)
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
@@ -240,7 +256,7 @@ def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, 
     do_train(net, train_loader, test_loader, optimizer, gradient_clip, scheduler, loss_fn, solver['NUM_EPOCHS'],
              len(train_loader), checkpointer, arguments, log_dir=log_dir, log_step=config['LOGGING']['STEP'],
              self_supervised=self_supervised, log_verbose=config['LOGGING'].get('VERBOSE', False), rank=rank, max_steps=max_steps,
-             world=world)
+             world=world, cuda_graph=cuda_graph)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -255,5 +271,7 @@ if __name__ == '__main__':
     ap.add_argument('--log_dir', type=str, default=None, help='override LOGGING.DIR')
     ap.add_argument('--nchw', dest='channels_last', action='store_false')
     ap.add_argument('--init_seed', type=int, default=0, help='torch seed for the initial weights (same on every rank)')
+    ap.add_argument('--cuda_graph', action='store_true',
+                    help='replay forward + backward from one CUDA graph (single GPU; pays off at small, launch-bound batches)')
     a = ap.parse_args()
-    main(a.config_file, a.batch_size, a.max_steps, a.synthetic_pool, a.channels_last, a.log_dir, a.init_seed)
+    main(a.config_file, a.batch_size, a.max_steps, a.synthetic_pool, a.channels_last, a.log_dir, a.init_seed, a.cuda_graph)
