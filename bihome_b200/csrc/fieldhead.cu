@@ -307,6 +307,7 @@ int launch_fieldhead_fwd_mma(const float* x, const float* W1, const float* b1, c
                              int HW, int tf32, cudaStream_t stream);
 int launch_fieldhead_bwd_mma(const float* x, const float* W1, const float* b1, const float* W2, const float* gOut, float* gx, float* partials,
                              long long n_pix, int HW, int tf32, cudaStream_t stream);
+int launch_fieldhead_moments_mma(const float* x, double* partials, long long n_pix, int grid, cudaStream_t stream);
 inline bool use_mma(int HW, int cin, int hid) { return g_tune[kTuneFieldheadVariant] != 1 && fieldhead_mma_ok(HW, cin, hid); }
 
 inline int fh_grid(long long n_items, int per_sm) {
@@ -335,6 +336,8 @@ extern "C" int bh_fieldhead_moments(const float* x, double* partials, long long 
     if (n_pix <= 0) return BH_E_SHAPE;
     if (cin != 16) return BH_E_UNSUPPORTED;
     if (!aligned16(x)) return BH_E_ALIGN;
+    if (g_tune[kTuneFieldheadVariant] != 1 && (n_pix % 8) == 0)
+        return launch_fieldhead_moments_mma(x, partials, n_pix, bh_fieldhead_grid(0, n_pix), reinterpret_cast<cudaStream_t>(stream));
     moments_kernel<16><<<bh_fieldhead_grid(0, n_pix), kMomThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, partials, n_pix);
     return launch_status();
 }

@@ -11,6 +11,7 @@
 //                       registers, quad reduction, planar field out
 //   fieldhead_gx_mma    the same recomputation, gh = relu'(pre) * (W2^T g) on the accumulators, which ARE the A fragments
 //                       of gx[16 px, 16] += gh[16 px, 8 hid] W1[8 hid, 16] (no data movement between the two GEMMs)
+//   moments_mma         X^T X over the pixels (BatchNorm's batch statistics from the input moments), three-product form
 //   fieldhead_gw_mma    hidden units on the M side: pre^T[16 hid, 8 px] tiles, whose accumulators are the A fragments of
 //                       gW1[16 hid, 16] += gh^T x and gW2^T[16 hid, 2] += h^T g; per-CTA partial sums (fixed order)
 // Fragment layouts (PTX ISA, mma.m16n8k8 .tf32; g = lane >> 2, t = lane & 3):
@@ -370,6 +371,85 @@ __global__ void __launch_bounds__(kMmaThreads) fieldhead_gw_mma_kernel(const flo
     // gb2: threads 0..31 hold output 0, 32..63 output 1
     ab2 = warp_sum(ab2);
     if (warp < 2 && lane == 0) dst[kHid * kCin + 3 * kHid + warp] = ab2;
+}
+
+// ---- input moments ---------------------------------------------------------------------------------------------------
+// sum_p x_i and sum_p x_i x_k of the [N,16] input: X^T X with the pixels as the contraction index.  One 8-pixel block is
+// one k-step; the four values a lane loads -- x[p+t][g], x[p+t][g+8], x[p+t+4][g], x[p+t+4][g+8] -- are at the same time its
+// A fragment (channels on the rows) and its B fragments for the two 8-channel column tiles, so the kernel is four scalar
+// loads, four splits and six tensor-core instructions per 8 pixels.  Always the float32-faithful three-product form: the
+// second moments feed a variance (E[xx] - mm) and must not carry TF32 rounding.  float32 accumulation over 128 pixels, then
+// float64 (as the scalar kernel: partials[cta][16 + 256] double).
+__global__ void __launch_bounds__(kMmaThreads) moments_mma_kernel(const float* __restrict__ x, double* __restrict__ partials,
+                                                                 long long n_pix) {
+    constexpr int kStats = kCin + kCin * kCin;
+    __shared__ double sAcc[kMmaWarps][kStats];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    double d2[2][4], d1[2] = {0.0, 0.0};
+#pragma unroll
+    for (int n = 0; n < 2; ++n) d2[n][0] = d2[n][1] = d2[n][2] = d2[n][3] = 0.0;
+    const long long n_blocks = n_pix / 8;
+    const long long stride = static_cast<long long>(gridDim.x) * kMmaWarps * 16;
+    // a warp takes runs of 16 consecutive 8-pixel blocks (128 pixels = 8 KB contiguous)
+    for (long long b0 = (static_cast<long long>(blockIdx.x) * kMmaWarps + warp) * 16; b0 < n_blocks; b0 += stride) {
+        // every 8-pixel block starts from a zero accumulator and is added to the running float32 sums with a round-to-nearest
+        // FADD: accumulating 48 instructions in the tensor core's own adder (which truncates) biased the sums by -1.7e-6
+        float c[2][4], s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.0f;
+        const int nb = static_cast<int>(n_blocks - b0 < 16 ? n_blocks - b0 : 16);
+#pragma unroll 4
+        for (int k = 0; k < nb; ++k) {
+            const float* p = x + ((b0 + k) * 8 + t) * kCin + g;
+            const float v0 = __ldg(p), v1 = __ldg(p + 8), v2 = __ldg(p + 4 * kCin), v3 = __ldg(p + 4 * kCin + 8);
+            s0 += v0 + v2;
+            s1 += v1 + v3;
+            uint32_t hi[4], lo[4];
+            split_tf32<true>(v0, hi[0], lo[0]);
+            split_tf32<true>(v1, hi[1], lo[1]);
+            split_tf32<true>(v2, hi[2], lo[2]);
+            split_tf32<true>(v3, hi[3], lo[3]);
+            float c0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, c1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            mma3<true>(c0, hi, lo, hi[0], hi[2], lo[0], lo[2]);   // columns = channels 0..7: b0 = x[p+t][g], b1 = x[p+t+4][g]
+            mma3<true>(c1, hi, lo, hi[1], hi[3], lo[1], lo[3]);   // columns = channels 8..15
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { c[0][e] += c0[e]; c[1][e] += c1[e]; }
+        }
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d2[n][e] += static_cast<double>(c[n][e]);
+        d1[0] += static_cast<double>(s0);
+        d1[1] += static_cast<double>(s1);
+    }
+    // sums over the four lanes that hold the same channel; c layout: rows g / g+8, columns 8n + 2t / 8n + 2t + 1
+    for (int o = 1; o < 4; o <<= 1) {
+        d1[0] += __shfl_xor_sync(0xffffffffu, d1[0], o);
+        d1[1] += __shfl_xor_sync(0xffffffffu, d1[1], o);
+    }
+    if (t == 0) {
+        sAcc[warp][g] = d1[0];
+        sAcc[warp][g + 8] = d1[1];
+    }
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        sAcc[warp][kCin + g * kCin + 8 * n + 2 * t] = d2[n][0];
+        sAcc[warp][kCin + g * kCin + 8 * n + 2 * t + 1] = d2[n][1];
+        sAcc[warp][kCin + (g + 8) * kCin + 8 * n + 2 * t] = d2[n][2];
+        sAcc[warp][kCin + (g + 8) * kCin + 8 * n + 2 * t + 1] = d2[n][3];
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kStats; q += kMmaThreads) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kMmaWarps; ++w) v += sAcc[w][q];
+        partials[static_cast<long long>(blockIdx.x) * kStats + q] = v;
+    }
+}
+
+int launch_fieldhead_moments_mma(const float* x, double* partials, long long n_pix, int grid, cudaStream_t stream) {
+    moments_mma_kernel<<<grid, kMmaThreads, 0, stream>>>(x, partials, n_pix);
+    return launch_status();
 }
 
 inline int mma_grid(long long n_items, int per_sm) {

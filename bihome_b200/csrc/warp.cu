@@ -1577,6 +1577,158 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- channels-last feature maps, warp-cooperative geometry ---------------------------------------------------------------
+// The thread-per-(pixel, channel quad) kernel above repeats the projection, the two divisions and the 64-bit index arithmetic of
+// a pixel in every one of its C/4 threads: 235 instructions per 16 output bytes, 70 % SM utilisation at 34 % of the DRAM
+// bandwidth (profiles/r01d_ncu_kernels.csv).  Here a warp takes 32 consecutive output pixels of one sample; lane L computes
+// the tap geometry of pixel L ONCE, then the warp visits the pixels in groups of 32 / LPP, the geometry arrives by shuffle
+// and every lane moves 16-byte channel quads: 512 contiguous bytes per tap and warp.
+// LPP = lanes per pixel = min(32, C/4) (a power of two); a lane owns C/4/LPP quads of its pixel.
+struct TapPack {
+    int off;           // (y0 * Ws + x0) * C
+    int bits;          // validity of nw / ne / sw / se (bit 0..3), bit 4 = the pixel exists
+    float wx0, wx1, wy0, wy1;
+};
+__device__ __forceinline__ TapPack pack_taps(const Taps& t, int Ws, int C, bool live) {
+    TapPack p;
+    p.off = (t.y0 * Ws + t.x0) * C;
+    p.bits = live ? (16 | (t.inx0 && t.iny0 ? 1 : 0) | (t.inx1 && t.iny0 ? 2 : 0) | (t.inx0 && t.iny1 ? 4 : 0) | (t.inx1 && t.iny1 ? 8 : 0)) : 0;
+    p.wx0 = t.wx0; p.wx1 = t.wx1; p.wy0 = t.wy0; p.wy1 = t.wy1;
+    return p;
+}
+__device__ __forceinline__ TapPack shfl_taps(const TapPack& p, int src_lane) {
+    TapPack r;
+    r.off = __shfl_sync(0xffffffffu, p.off, src_lane);
+    r.bits = __shfl_sync(0xffffffffu, p.bits, src_lane);
+    r.wx0 = __shfl_sync(0xffffffffu, p.wx0, src_lane);
+    r.wx1 = __shfl_sync(0xffffffffu, p.wx1, src_lane);
+    r.wy0 = __shfl_sync(0xffffffffu, p.wy0, src_lane);
+    r.wy1 = __shfl_sync(0xffffffffu, p.wy1, src_lane);
+    return r;
+}
+__device__ __forceinline__ float blend_w(const TapPack& t, float nw, float ne, float sw, float se) {
+    return fmaf(fmaf(nw, t.wx0, ne * t.wx1), t.wy0, fmaf(sw, t.wx0, se * t.wx1) * t.wy1);   // == blend()
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256, 3)
+    warp_fwd_nhwc_coop_kernel(const float* __restrict__ src, const float* __restrict__ H, float* __restrict__ out, int C, int Hs,
+                              int Ws, int Ho, int Wo) {
+    constexpr int G = 32 / LPP;                       // pixels the warp handles at a time
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int sub = lane / LPP, ql = lane % LPP;
+    const int qpl = (C >> 2) / LPP;
+    const Hmat hm = load_h(H, b);
+    const int npix = Ho * Wo;
+    const float* sb = src + static_cast<long long>(b) * Hs * Ws * C;
+    float* ob = out + static_cast<long long>(b) * npix * C;
+    const int row = Ws * C;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int r0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; r0 < npix; r0 += warps * 32) {
+        const int r = min(r0 + lane, npix - 1);
+        const int y = r / Wo, x = r - y * Wo;
+        float u, v, rw;
+        project(hm, static_cast<float>(x), static_cast<float>(y), u, v, rw);
+        const TapPack mine = pack_taps(make_taps(u, v, Ws, Hs), Ws, C, r0 + lane < npix);
+#pragma unroll 2
+        for (int j = 0; j < 32; j += G) {
+            const TapPack t = shfl_taps(mine, j + sub);
+            if (!(t.bits & 16)) continue;
+            const float* sp = sb + t.off + 4 * ql;
+            float* op = ob + static_cast<long long>(r0 + j + sub) * C + 4 * ql;
+            for (int k = 0; k < qpl; ++k, sp += 4 * LPP, op += 4 * LPP) {
+                const float4 nw = ld4_or_zero(sp, t.bits & 1);
+                const float4 ne = ld4_or_zero(sp + C, t.bits & 2);
+                const float4 sw = ld4_or_zero(sp + row, t.bits & 4);
+                const float4 se = ld4_or_zero(sp + row + C, t.bits & 8);
+                float4 o;
+                o.x = blend_w(t, nw.x, ne.x, sw.x, se.x);
+                o.y = blend_w(t, nw.y, ne.y, sw.y, se.y);
+                o.z = blend_w(t, nw.z, ne.z, sw.z, se.z);
+                o.w = blend_w(t, nw.w, ne.w, sw.w, se.w);
+                stg_stream(reinterpret_cast<float4*>(op), o);
+            }
+        }
+    }
+}
+
+// backward -> dH (no image gradient): same walk; the channel sums of d out/du, d out/dv are reduced over the LPP lanes of a
+// pixel and handed back to the lane that owns the pixel's geometry, which accumulates the nine dH terms.
+// grid = (chunks, B), partials[b][chunk][9] as warp_bwd_generic_kernel.
+template <int LPP>
+__global__ void __launch_bounds__(256, 3)
+    warp_bwd_nhwc_coop_kernel(const float* __restrict__ src, const float* __restrict__ H, const float* __restrict__ gOut,
+                              const float* __restrict__ gMaskPooled, float* __restrict__ partials, int C, int Hs, int Ws, int Ho,
+                              int Wo, int pool) {
+    constexpr int G = 32 / LPP;
+    __shared__ float red[9 * 8];
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int sub = lane / LPP, ql = lane % LPP;
+    const int qpl = (C >> 2) / LPP;
+    const Hmat hm = load_h(H, b);
+    const int npix = Ho * Wo;
+    const float* sb = src + static_cast<long long>(b) * Hs * Ws * C;
+    const float* gb = gOut + static_cast<long long>(b) * npix * C;
+    const int row = Ws * C;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0f;
+    for (int r0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; r0 < npix; r0 += warps * 32) {
+        const bool live = r0 + lane < npix;
+        const int r = min(r0 + lane, npix - 1);
+        const int y = r / Wo, x = r - y * Wo;
+        float u, v, rw;
+        project(hm, static_cast<float>(x), static_cast<float>(y), u, v, rw);
+        const Taps taps = make_taps(u, v, Ws, Hs);
+        const TapPack mine = pack_taps(taps, Ws, C, live);
+        float my_gu = 0.0f, my_gv = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < 32; j += G) {
+            const TapPack t = shfl_taps(mine, j + sub);
+            float gu = 0.0f, gv = 0.0f;
+            if (t.bits & 16) {
+                const float* sp = sb + t.off + 4 * ql;
+                const float* gp = gb + static_cast<long long>(r0 + j + sub) * C + 4 * ql;
+                for (int k = 0; k < qpl; ++k, sp += 4 * LPP, gp += 4 * LPP) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gp));
+                    const float4 nw = ld4_or_zero(sp, t.bits & 1);
+                    const float4 ne = ld4_or_zero(sp + C, t.bits & 2);
+                    const float4 sw = ld4_or_zero(sp + row, t.bits & 4);
+                    const float4 se = ld4_or_zero(sp + row + C, t.bits & 8);
+                    // blend_grad per channel: du = (ne - nw) wy0 + (se - sw) wy1, dv = (sw - nw) wx0 + (se - ne) wx1
+                    gu = fmaf(g.x, fmaf(ne.x - nw.x, t.wy0, (se.x - sw.x) * t.wy1), gu); gv = fmaf(g.x, fmaf(sw.x - nw.x, t.wx0, (se.x - ne.x) * t.wx1), gv);
+                    gu = fmaf(g.y, fmaf(ne.y - nw.y, t.wy0, (se.y - sw.y) * t.wy1), gu); gv = fmaf(g.y, fmaf(sw.y - nw.y, t.wx0, (se.y - ne.y) * t.wx1), gv);
+                    gu = fmaf(g.z, fmaf(ne.z - nw.z, t.wy0, (se.z - sw.z) * t.wy1), gu); gv = fmaf(g.z, fmaf(sw.z - nw.z, t.wx0, (se.z - ne.z) * t.wx1), gv);
+                    gu = fmaf(g.w, fmaf(ne.w - nw.w, t.wy0, (se.w - sw.w) * t.wy1), gu); gv = fmaf(g.w, fmaf(sw.w - nw.w, t.wx0, (se.w - ne.w) * t.wx1), gv);
+                }
+            }
+#pragma unroll
+            for (int o = LPP >> 1; o > 0; o >>= 1) {
+                gu += __shfl_xor_sync(0xffffffffu, gu, o);
+                gv += __shfl_xor_sync(0xffffffffu, gv, o);
+            }
+            // pixel j + s lives in lanes [s LPP, (s+1) LPP): lane L fetches its own pixel's sums in the iteration that covers it
+            const int from = ((lane - j) & (G - 1)) * LPP;
+            const float ru = __shfl_sync(0xffffffffu, gu, from), rv = __shfl_sync(0xffffffffu, gv, from);
+            if (lane >= j && lane < j + G) { my_gu = ru; my_gv = rv; }
+        }
+        if (live) {
+            if (gMaskPooled != nullptr) {
+                float du, dv;
+                cover_grad(taps, du, dv);
+                const float gm = __ldg(gMaskPooled + (static_cast<long long>(b) * (Ho / pool) + y / pool) * (Wo / pool) + x / pool) /
+                                 static_cast<float>(pool * pool);
+                my_gu = fmaf(gm, du, my_gu);
+                my_gv = fmaf(gm, dv, my_gv);
+            }
+            accum_gh(acc, my_gu, my_gv, u, v, rw, static_cast<float>(x), static_cast<float>(y));
+        }
+    }
+    block_sum<9>(acc, red);
+    store9(acc, partials + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * 9);
+}
+
 // one 128-bit reduction (SASS REDG.E.ADD.F32x4) instead of four scalar atomics
 __device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -1902,6 +2054,30 @@ inline int launch_bwd_tile(const float* src, const float* H, const float* gOut, 
                                                                                  tiles_x, tile_magic(tiles_x), planes);
     return launch_status();
 }
+// warp-cooperative channels-last kernels: C/4 a power of two up to 32, or a multiple of 32; 32-bit element offsets per sample
+inline bool nhwc_coop_ok(int B, int C, int Hs, int Ws, int Ho, int Wo) {
+    const int cq = C / 4;
+    const bool shape = cq >= 32 ? (cq % 32) == 0 : (cq & (cq - 1)) == 0;
+    return g_tune[kTuneWarpPath] == 0 && B <= 65535 && shape && static_cast<long long>(Hs) * Ws * C < (1ll << 31) &&
+           static_cast<long long>(Ho) * Wo * C < (1ll << 31);
+}
+inline int launch_fwd_nhwc_coop(const float* src, const float* H, float* out, int B, int C, int Hs, int Ws, int Ho, int Wo,
+                                cudaStream_t stream) {
+    const int cq = C / 4;
+    // 8 warps of 32 pixels per CTA; enough CTAs per sample to fill the machine a few times over, never more than the pixels give
+    const long long per_sample = (static_cast<long long>(Ho) * Wo + 255) / 256;
+    long long gx = (static_cast<long long>(kNumSMs) * 16 + B - 1) / B;
+    if (gx > per_sample) gx = per_sample;
+    if (gx < 1) gx = 1;
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(B));
+    if (cq >= 32) warp_fwd_nhwc_coop_kernel<32><<<grid, 256, 0, stream>>>(src, H, out, C, Hs, Ws, Ho, Wo);
+    else if (cq == 16) warp_fwd_nhwc_coop_kernel<16><<<grid, 256, 0, stream>>>(src, H, out, C, Hs, Ws, Ho, Wo);
+    else if (cq == 8) warp_fwd_nhwc_coop_kernel<8><<<grid, 256, 0, stream>>>(src, H, out, C, Hs, Ws, Ho, Wo);
+    else if (cq == 4) warp_fwd_nhwc_coop_kernel<4><<<grid, 256, 0, stream>>>(src, H, out, C, Hs, Ws, Ho, Wo);
+    else if (cq == 2) warp_fwd_nhwc_coop_kernel<2><<<grid, 256, 0, stream>>>(src, H, out, C, Hs, Ws, Ho, Wo);
+    else warp_fwd_nhwc_coop_kernel<1><<<grid, 256, 0, stream>>>(src, H, out, C, Hs, Ws, Ho, Wo);
+    return launch_status();
+}
 // the fixed-order sum behind a programmatic dependent launch: its blocks are resident when the producer grid drains
 inline int launch_bwd_finish(const float* partials, float* gH, int B, int chunks, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
@@ -1943,6 +2119,8 @@ extern "C" int bh_warp_fwd(const float* src, const float* H, float* out, float* 
             rc = ring_blk(Hs, Ws) == 128 ? launch_fwd_ring<128>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream)
                                          : launch_fwd_ring<64>(src, H, out, mask_pooled, B, C, Hs, Ws, Ho, Wo, fuse_mask, stream);
             mask_done = mask_done || fuse_mask;
+        } else if (channels_last && (C % 4) == 0 && nhwc_coop_ok(B, C, Hs, Ws, Ho, Wo)) {
+            rc = launch_fwd_nhwc_coop(src, H, out, B, C, Hs, Ws, Ho, Wo, stream);
         } else if (channels_last && (C % 4) == 0) {
             const long long n = static_cast<long long>(B) * Ho * Wo * (C / 4);
             warp_fwd_nhwc_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, H, out, B, C, Hs, Ws, Ho, Wo);
@@ -2021,7 +2199,15 @@ extern "C" int bh_warp_bwd(const float* src, const float* H, const float* gOut, 
     float* partials = static_cast<float*>(workspace);
     const Layout ls = make_layout(C > 0 ? C : 1, Hs, Ws, channels_last), lo = make_layout(C > 0 ? C : 1, Ho, Wo, channels_last);
     dim3 grid(chunks, B);
-    if (vec)
+    if (vec && !gSrc && nhwc_coop_ok(B, C, Hs, Ws, Ho, Wo)) {
+        const int cq = C / 4;
+        if (cq >= 32) warp_bwd_nhwc_coop_kernel<32><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, pool);
+        else if (cq == 16) warp_bwd_nhwc_coop_kernel<16><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, pool);
+        else if (cq == 8) warp_bwd_nhwc_coop_kernel<8><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, pool);
+        else if (cq == 4) warp_bwd_nhwc_coop_kernel<4><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, pool);
+        else if (cq == 2) warp_bwd_nhwc_coop_kernel<2><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, pool);
+        else warp_bwd_nhwc_coop_kernel<1><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, C, Hs, Ws, Ho, Wo, pool);
+    } else if (vec)
         warp_bwd_generic_kernel<true><<<grid, 256, 0, stream>>>(src, H, gOut, gMaskPooled, partials, gSrc, C, Hs, Ws, Ho, Wo,
                                                                  pool, ls, lo);
     else

@@ -43,11 +43,18 @@ def timings():
     return out
 
 
+# BH_NVTX=1: every C-ABI call sits inside an NVTX range named after its entry point (nsys / ncu --nvtx timelines show
+# bh_warp_fwd, bh_bihome_fwd_bwd, ... between the cuDNN kernels of the backbone); off by default
+_NVTX = os.environ.get('BH_NVTX', '0') == '1'
+
+
 class _timed:
     def __init__(self, name):
         self.name = name
 
     def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
         if _TIMING is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
@@ -57,6 +64,8 @@ class _timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             _TIMING.append((self.name, self.e0, e1))
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         return False
 
 

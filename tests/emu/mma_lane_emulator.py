@@ -166,3 +166,27 @@ def gw(x, W1, b1, W2, gOut, HW):
                     gW2[0, r0], gW2[1, r0], gW2[0, r1], gW2[1, r1] = aW2[i][l]
     gb2[:] = gOut.sum((0, 2))
     return gW1, gb1, gW2, gb2
+
+
+def moments(x):
+    """moments_mma_kernel: (sum_p x_i [16], sum_p x_i x_k [16,16]); one 8-pixel block per k-step, the lane's four loads serve
+    as A fragment and as both B fragments"""
+    c = [np.zeros((32, 4)), np.zeros((32, 4))]
+    s0, s1 = np.zeros(32), np.zeros(32)
+    for k in range(x.shape[0] // 8):
+        v0, v1 = x[k * 8 + T, G], x[k * 8 + T, G + 8]
+        v2, v3 = x[k * 8 + T + 4, G], x[k * 8 + T + 4, G + 8]
+        s0 += v0 + v2
+        s1 += v1 + v3
+        a = np.stack([v0, v1, v2, v3], 1)
+        c[0] = mma(c[0], a, v0, v2)
+        c[1] = mma(c[1], a, v1, v3)
+    M, S = np.zeros((16, 16)), np.zeros(16)
+    q0, q1 = quad_sum(s0), quad_sum(s1)
+    for l in range(32):
+        g, t = l >> 2, l & 3
+        S[g], S[g + 8] = q0[l], q1[l]
+        for n in range(2):
+            M[g, 8 * n + 2 * t], M[g, 8 * n + 2 * t + 1] = c[n][l, 0], c[n][l, 1]
+            M[g + 8, 8 * n + 2 * t], M[g + 8, 8 * n + 2 * t + 1] = c[n][l, 2], c[n][l, 3]
+    return S, M

@@ -287,3 +287,5 @@ def test_tensor_core_kernels_fragment_mapping_on_the_lane_emulator():
     gW1, gb1, gW2, gb2 = E.gw(x, W1, b1, W2, g_out, HW)
     assert np.abs(gW1 - gh.T @ x).max() < 1e-12 and np.abs(gb1 - gh.sum(0)).max() < 1e-12
     assert np.abs(gW2 - G.T @ h).max() < 1e-12 and np.abs(gb2 - G.sum(0)).max() < 1e-12
+    S, M = E.moments(x)
+    assert np.abs(S - x.sum(0)).max() < 1e-12 and np.abs(M - x.T @ x).max() < 1e-12

@@ -131,6 +131,10 @@ WARP_SHAPES = [
     (3, 2, 37, 53, 29, 31, False),         # odd sizes -> generic
     (2, 8, 40, 40, 40, 40, True),          # channels-last vec4
     (2, 6, 33, 20, 17, 24, True),          # channels-last generic
+    (3, 4, 33, 31, 25, 27, True),          # warp-cooperative channels-last kernels: one lane per pixel ...
+    (2, 64, 40, 48, 40, 48, True),         # ... 16 lanes per pixel (the sweep's C = 64)
+    (2, 128, 24, 24, 30, 26, True),        # ... 32 lanes per pixel, partial last group of 32 pixels
+    (1, 256, 20, 20, 20, 20, True),        # ... two channel quads per lane
 ]
 
 
@@ -184,6 +188,13 @@ def test_warp_paths_vs_oracle(F, warp_path, B, C, Hs, Ws, Ho, Wo, nhwc):
     # coordinates beyond 256 px have twice the ulp of the 128-px north-star patches
     assert rel_l2(gH.cpu().numpy(), gH64.numpy()) < (TOL if max(Hs, Ws) <= 128 else 3e-5)
     assert rel_l2(gi.cpu().numpy(), gi64.numpy()) < 2e-5     # tap weights carry the fp32 coordinate ulp (7.6e-6 px at 64..128)
+    if nhwc:
+        # without an image gradient the channels-last backward takes the warp-cooperative dH-only kernel (same project(),
+        # hence the same bilinear cells as the oracle's; the planar dH-only kernels round their reciprocal differently and
+        # are compared on smooth images in test_warp_golden_gradients / test_gpu_fullsize)
+        Hd = H.float().cuda().requires_grad_(True)
+        gH2, = torch.autograd.grad((F.warp(x.detach(), Hd, Ho, Wo) * gO.float().cuda()).sum(), Hd)
+        assert rel_l2(gH2.cpu().numpy(), gH64.numpy()) < TOL
 
 
 def _warp_direct_autograd(img, H, Ho, Wo, cells=None):

@@ -233,6 +233,7 @@ def main():
     ap.add_argument('--warp-only', action='store_true', help='time only the 1-channel image warp (forward + backward)')
     ap.add_argument('--dirty', action='store_true', help='flush by memset only (leaves the L2 full of dirty lines: adds their write-back to every timing)')
     ap.add_argument('--loss-cl', action='store_true', help='time the fused loss for every cluster size (BH_LOSS_CL knob)')
+    ap.add_argument('--feature-warp', action='store_true', help='time the channels-last feature-map warp (forward, backward to dH) over the sweep')
     ap.add_argument('--triplet', action='store_true', help='time K3g (the other loss variants) against the ATen op chain it replaces')
     ap.add_argument('--field-head', action='store_true', help='time K6 (the Zeng field head) against the ATen modules')
     a = ap.parse_args()
@@ -253,6 +254,10 @@ def main():
         torch.cuda.synchronize()
         return
     t = Timer(a.iters, dirty=a.dirty)
+    if a.feature_warp:
+        for B, P, C in ((64, 128, 64), (256, 128, 64), (64, 128, 256), (16, 256, 64), (256, 64, 128)):
+            bench_feature_warp(B, P, C, t)
+        return
     if a.triplet:
         for B, C, h, nhwc in ((256, 64, 32, True), (256, 64, 32, False), (64, 1, 128, False), (1024, 64, 32, True)):
             bench_triplet(B, C, h, nhwc, t)
