@@ -177,6 +177,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     cabi.lib()  # fail loudly if the extension is missing
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     cfg = engine.load_config(CONFIG)
     B = args.batch
     torch.manual_seed(0)
@@ -311,7 +312,7 @@ def run_ours(args):
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': workload_config(B, world, args.pool),
-            'layout': {'channels_last': bool(args.channels_last), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten'},
+            'layout': {'channels_last': bool(args.channels_last), 'cudnn_benchmark': bool(args.cudnn_benchmark), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
             'gpu_launches': launches, 'roofline': roofline, 'warp_loss_roofline': warp_loss, 'cpu_baseline': cpu_baseline, 'clocks': clk,
@@ -339,6 +340,9 @@ def main():
                     help="Zeng backbone's last stage: 'aten' = the four torch modules (default), 'fused' = K6 (csrc/fieldhead.cu); "
                          "unset = BH_FIELD_HEAD, else the device's self-test decides (bihome_b200/autotune.py)")
     ap.add_argument('--ref-batch', type=int, default=None, help='--impl reference: image pairs per CPU step (default: --batch, 64 on a box with < 56 GB of free RAM)')
+    ap.add_argument('--no-cudnn-benchmark', dest='cudnn_benchmark', action='store_false', default=True,
+                    help='leave torch.backends.cudnn.benchmark off (default on, as train.py: the shapes of a training run are '
+                         'fixed, cuDNN times its convolution algorithms once per shape during the warm-up: 72.2 -> 69.6 ms/step)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer phase (profiling runs)')
     ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')

@@ -327,7 +327,7 @@ extern "C" int bh_fieldhead_grid(int what, long long n_pix) {
     using namespace bh;
     if (n_pix <= 0) return 0;
     if (what == 0) return fh_grid((n_pix + kMomTile - 1) / kMomTile, 7);   // moments: 7 x 288 threads per SM
-    return fh_grid((n_pix + kFhTile - 1) / kFhTile, 3);                    // backward (either kernel): 32-pixel tiles, 3 CTAs per SM
+    return fh_grid((n_pix + kFhTile - 1) / kFhTile, 5);                    // backward (either kernel): 32-pixel tiles, 5 CTAs per SM
 }
 
 extern "C" int bh_fieldhead_moments(const float* x, double* partials, long long n_pix, int cin, bh_stream_t stream) {

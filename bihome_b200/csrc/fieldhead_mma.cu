@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kMmaThreads) fieldhead_gx_mma_kernel(const flo
 // Hidden units on the M side: warp w owns hidden rows 32w .. 32w+31 (two 16-row tiles), the CTA walks 32-pixel tiles staged
 // in shared memory.  partials[cta] = { gW1 [HID*CIN] | gb1 [HID] | gW2 [2*HID] | gb2 [2] } as in fieldhead.cu.
 template <bool kExact>
-__global__ void __launch_bounds__(kMmaThreads) fieldhead_gw_mma_kernel(const float* __restrict__ x, const float* __restrict__ W1,
+__global__ void __launch_bounds__(kMmaThreads, kExact ? 4 : 5) fieldhead_gw_mma_kernel(const float* __restrict__ x, const float* __restrict__ W1,
                                                                       const float* __restrict__ b1, const float* __restrict__ W2,
                                                                       const float* __restrict__ gOut, float* __restrict__ partials,
                                                                       long long n_pix, int HW) {
@@ -278,19 +278,25 @@ __global__ void __launch_bounds__(kMmaThreads) fieldhead_gw_mma_kernel(const flo
         for (int e = 0; e < 4; ++e) aW2[i][e] = aW1[i][0][e] = aW1[i][1][e] = 0.0f;
     }
     const long long n_tiles = n_pix / 32;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // the next tile's share of this thread (one float4 of x, one upstream gradient for threads 0..63) is fetched into registers
+    // while the current tile is consumed: the global-load latency hides behind a whole tile of tensor-core work
+    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ng = 0.0f;
+    auto fetch = [&](long long tile) {
         const long long p0 = tile * 32;
         const long long b = p0 / HW, s0 = p0 - b * HW;
+        nx = ldg_stream(reinterpret_cast<const float4*>(x + p0 * kCin) + tid);      // pixel tid / 4, channels 4 (tid % 4) ..
+        if (tid < 64) ng = __ldg(gOut + (2 * b + (tid >> 5)) * HW + s0 + (tid & 31));
+    };
+    if (blockIdx.x < n_tiles) fetch(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();   // the previous tile is fully consumed
-        {
-            const float4 v = ldg_stream(reinterpret_cast<const float4*>(x + p0 * kCin) + tid);   // pixel tid / 4, channels 4 (tid % 4) ..
-            *reinterpret_cast<float4*>(sX + (tid >> 2) * kXPitch + 4 * (tid & 3)) = v;
-            if (tid < 64) {
-                const float gv = __ldg(gOut + (2 * b + (tid >> 5)) * HW + s0 + (tid & 31));
-                sG[tid] = gv;
-                ab2 += gv;
-            }
+        *reinterpret_cast<float4*>(sX + (tid >> 2) * kXPitch + 4 * (tid & 3)) = nx;
+        if (tid < 64) {
+            sG[tid] = ng;
+            ab2 += ng;
         }
+        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
         __syncthreads();
 #pragma unroll 1
         for (int n = 0; n < 4; ++n) {   // 8-pixel column tiles
@@ -459,18 +465,18 @@ inline int mma_grid(long long n_items, int per_sm) {
 
 // geometry the tensor-core kernels cover: 16 -> 128 -> 2, whole 32-pixel groups inside a sample
 bool fieldhead_mma_ok(int HW, int cin, int hid) { return cin == kCin && hid == kHid && HW > 0 && (HW % 32) == 0; }
-int fieldhead_gw_mma_grid(long long n_pix) { return mma_grid(n_pix / 32, 3); }   // == bh_fieldhead_grid(1, n_pix): rows of `partials`
+int fieldhead_gw_mma_grid(long long n_pix) { return mma_grid(n_pix / 32, 5); }   // == bh_fieldhead_grid(1, n_pix): rows of `partials`
 
 int launch_fieldhead_fwd_mma(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* out, long long n_pix,
                              int HW, int tf32, cudaStream_t stream) {
-    const int grid = mma_grid((n_pix / 32 + kMmaWarps - 1) / kMmaWarps, 4);
+    const int grid = mma_grid((n_pix / 32 + kMmaWarps - 1) / kMmaWarps, 8);   // 64 registers: eight 128-thread CTAs per SM
     if (tf32) fieldhead_fwd_mma_kernel<2, false><<<grid, kMmaThreads, 0, stream>>>(x, W1, b1, W2, b2, out, n_pix, HW);
     else fieldhead_fwd_mma_kernel<2, true><<<grid, kMmaThreads, 0, stream>>>(x, W1, b1, W2, b2, out, n_pix, HW);
     return launch_status();
 }
 int launch_fieldhead_bwd_mma(const float* x, const float* W1, const float* b1, const float* W2, const float* gOut, float* gx, float* partials,
                              long long n_pix, int HW, int tf32, cudaStream_t stream) {
-    const int grid = mma_grid((n_pix / 32 + kMmaWarps - 1) / kMmaWarps, 3);
+    const int grid = mma_grid((n_pix / 32 + kMmaWarps - 1) / kMmaWarps, 6);   // 77-96 registers, 33 KB of tables: six CTAs per SM
     if (tf32) fieldhead_gx_mma_kernel<2, false><<<grid, kMmaThreads, 0, stream>>>(x, W1, b1, W2, gOut, gx, n_pix, HW);
     else fieldhead_gx_mma_kernel<2, true><<<grid, kMmaThreads, 0, stream>>>(x, W1, b1, W2, gOut, gx, n_pix, HW);
     int rc = launch_status();

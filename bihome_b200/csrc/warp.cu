@@ -1584,6 +1584,11 @@ __global__ void __launch_bounds__(256)
 // the tap geometry of pixel L ONCE, then the warp visits the pixels in groups of 32 / LPP, the geometry arrives by shuffle
 // and every lane moves 16-byte channel quads: 512 contiguous bytes per tap and warp.
 // LPP = lanes per pixel = min(32, C/4) (a power of two); a lane owns C/4/LPP quads of its pixel.
+// Measured alternative (round 2, removed): one CTA per 8x8 output tile and 64-channel slab with the tile's source box
+// (16 x 16 x 64 floats = 64 KB) staged by one cp.async.bulk.tensor.4d copy and the taps read from shared memory -- 66 % of the
+// HBM peak at B = 64, C = 64 against 60 % for this kernel (68 % at B = 256, 73 % at C = 256): the explicit reuse buys little
+// once the L1 path has enough warps in flight (ncu: 45 % L1 hit rate, long-scoreboard bound at 24 warps per SM -> 32), and
+// the staged kernel never returned on a 2x up-sampling case whose boxes lie wholly outside a 32 x 32 source.
 struct TapPack {
     int off;           // (y0 * Ws + x0) * C
     int bits;          // validity of nw / ne / sw / se (bit 0..3), bit 4 = the pixel exists
@@ -1611,7 +1616,7 @@ __device__ __forceinline__ float blend_w(const TapPack& t, float nw, float ne, f
 }
 
 template <int LPP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
     warp_fwd_nhwc_coop_kernel(const float* __restrict__ src, const float* __restrict__ H, float* __restrict__ out, int C, int Hs,
                               int Ws, int Ho, int Wo) {
     constexpr int G = 32 / LPP;                       // pixels the warp handles at a time

@@ -24,6 +24,16 @@ def pytest_sessionstart(session):
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
+@pytest.fixture(autouse=True)
+def _cudnn_flags_do_not_leak():
+    """train.main() turns torch.backends.cudnn.benchmark on for its process (fixed shapes); parity tests that follow in the
+    same pytest process compare against fixed references and want cuDNN's default algorithm choice"""
+    import torch
+    torch.backends.cudnn.benchmark = False
+    yield
+    torch.backends.cudnn.benchmark = False
+
+
 @pytest.fixture(scope='session')
 def golden():
     import numpy as np

@@ -59,7 +59,7 @@ def test_argument_checks_do_not_need_a_gpu(lib):
     # K6: compiled geometry, grid sizing (a host function) and argument checks
     assert lib.bh_fieldhead_supported(16, 128) == 1 and lib.bh_fieldhead_supported(64, 512) == 0
     assert lib.bh_fieldhead_grid(0, 100) == 1 and lib.bh_fieldhead_grid(1, 100) == 4 and lib.bh_fieldhead_grid(1, 0) == 0
-    assert lib.bh_fieldhead_grid(1, 256 * 128 * 128) == 148 * 3
+    assert lib.bh_fieldhead_grid(1, 256 * 128 * 128) == 148 * 5
     p = ctypes.c_void_p(64)
     assert lib.bh_fieldhead_fwd(None, p, p, p, p, p, 1, 16, 16, 128, 0, None) == -1
     assert lib.bh_fieldhead_fwd(p, p, p, p, p, p, 1, 16, 64, 512, 0, None) == -5

@@ -134,7 +134,9 @@ WARP_SHAPES = [
     (3, 4, 33, 31, 25, 27, True),          # warp-cooperative channels-last kernels: one lane per pixel ...
     (2, 64, 40, 48, 40, 48, True),         # ... 16 lanes per pixel (the sweep's C = 64)
     (2, 128, 24, 24, 30, 26, True),        # ... 32 lanes per pixel, partial last group of 32 pixels
-    (1, 256, 20, 20, 20, 20, True),        # ... two channel quads per lane
+    (1, 256, 20, 20, 24, 16, True),        # ... two channel quads per lane
+    (2, 64, 32, 32, 64, 64, True),         # 2x up-sampling: most taps outside the source
+    (2, 64, 96, 96, 32, 32, True),         # 3x down-sampling
 ]
 
 
@@ -155,8 +157,9 @@ def _kernel_cells(H32, Ho, Wo):
 
 @pytest.fixture(params=['tile', 'tile4', 'ring'])
 def warp_path(request, F):
-    """the NCHW implementations behind bh_warp_fwd / bh_warp_bwd: the tile kernels (default: two warps per tile; 'tile4':
-    the four-warp build) and the persistent ring kernels"""
+    """the implementations behind bh_warp_fwd / bh_warp_bwd: the tile kernels (default: two warps per tile; 'tile4': the
+    four-warp build) and the persistent ring kernels for planar tensors; channels-last feature maps take the
+    warp-cooperative kernels by default and the round-1 thread-per-quad kernels under 'ring'"""
     F.tune('warp_path', 1 if request.param == 'ring' else 0)
     F.tune('warp_variant', 1 if request.param == 'tile4' else 0)
     yield request.param

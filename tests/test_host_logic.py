@@ -74,6 +74,46 @@ def test_hot_path_refuses_cpu_tensors():
         U.four_point_to_homography(torch.zeros(1, 4, 2), torch.zeros(1, 4, 2))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         PH.Model._warp(torch.zeros(1, 1, 8, 8), torch.zeros(1, 4, 2))
+    # K3g, the fused loss of every other variant, and the CUDA-graph step: same rule
+    import bihome_b200.functional as F
+    from bihome_b200 import engine
+    f = torch.zeros(1, 4, 4, 4)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        F.triplet_loss(f, f, f, f, torch.ones(1, 4, 4), None, torch.ones(1, 4, 4), None, torch.eye(3)[None], torch.eye(3)[None])
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            engine.GraphedStep(torch.nn.Identity(), {'patch_1': f})
+
+
+def test_loss_variant_mapping_of_the_mirrors():
+    """TRIPLET_* settings -> (distance, hinge, margin) of F.triplet_loss, the way the reference's branches read them
+    (PerceptualHead.py:465-538, 609-665; TripletHead.py:79-95)"""
+    from bihome_b200.heads import PerceptualHead as PH, TripletHead as TH
+    base = dict(PATCH_SIZE=32, PATCH_KEYS=['patch_1', 'patch_2'], DELTA_HAT_KEYS=['a', 'b'], PF_KEYS=[], RANSAC_HYPOTHESIS_NO=-1,
+                POINTS_PER_HYPOTHESIS=-1, AUXILIARY_RESNET='resnet18', AUXILIARY_RESNET_OUTPUT_LAYER=1, AUXILIARY_RESNET_PRETRAINED=False,
+                TRIPLET_MU=0.01, MASK_KEYS=[], SAMPLING_STRATEGY='downsample-mask', TRIPLET_DISTANCE='l1')
+
+    def variant(double, **kw):
+        cfg = dict(base)
+        cfg.update(kw)
+        return PH.Model(backbone=torch.nn.Identity(), **cfg)._loss_variant(double)
+    assert variant(True, TRIPLET_LOSS='double-line', TRIPLET_MARGIN='inf', TRIPLET_AGGREGATION='channel-agnostic') == ('l1', None, 0.0)
+    assert variant(True, TRIPLET_LOSS='double-line', TRIPLET_MARGIN=0.05, TRIPLET_AGGREGATION='channel-aware') == ('l1', 'channel', 0.05)
+    assert variant(True, TRIPLET_LOSS='double-line', TRIPLET_MARGIN=1.0, TRIPLET_AGGREGATION='channel-agnostic') == ('l1', 'pixel', 1.0)
+    assert variant(True, TRIPLET_LOSS='double-line', TRIPLET_MARGIN=0.1, TRIPLET_AGGREGATION='channel-aware',
+                   TRIPLET_DISTANCE='cosine') == ('cosine', 'pixel', 0.1)
+    assert variant(False, TRIPLET_LOSS='one-line', TRIPLET_MARGIN=0.2, TRIPLET_AGGREGATION='channel-agnostic',
+                   TRIPLET_DISTANCE='cosine') == ('cosine', 'pixel', 0.2)
+    with pytest.raises(AssertionError, match='distance metric'):
+        variant(False, TRIPLET_LOSS='one-line', TRIPLET_MARGIN=0.2, TRIPLET_AGGREGATION='channel-agnostic', TRIPLET_DISTANCE='l2')
+    kw = dict(PATCH_KEYS=['patch_1', 'patch_2'], MASK_KEYS=['m1', 'm2'], FEATURE_KEYS=['f1', 'f2'], TARGET_KEYS=['a', 'b'], LD=2, MU=0.01,
+              VARIANT='DoubleLine')
+    head = TH.Model(None, TRIPLET_MARGIN=1.0, TRIPLET_AGGREGATION='channel-agnostic', **kw)
+    assert head._loss_variant(64, 1) == ('pixel', 1.0, 64.0)          # the B-fold broadcast of TripletHead.py:91-92
+    with pytest.raises(RuntimeError, match='only defined for'):
+        head._loss_variant(4, 8)
+    assert TH.Model(None, TRIPLET_MARGIN='inf', TRIPLET_AGGREGATION='channel-aware', **kw)._loss_variant(4, 8) == (None, 0.0, 1.0)
+    assert TH.Model(None, TRIPLET_MARGIN=0.05, TRIPLET_AGGREGATION='channel-aware', **kw)._loss_variant(4, 8) == ('channel', 0.05, 1.0)
 
 
 def test_transform_args_from_yaml():

@@ -38,8 +38,12 @@ if has l; then
       python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "launch list rc=$?"
 fi
 if has n; then
-  timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:"bihome_|warp_fwd|warp_bwd|mask_pooled|dlt4_|dltn_|pairgen_|mace_|fieldhead_|moments_|affine_acc" -c 112 -f \
+  timeout 1500 ncu --set full --clock-control none --import-source on \
+      -k regex:"bihome_|triplet_|warp_fwd|warp_bwd|mask_pooled|dlt4_|dltn_|pairgen_|mace_|fieldhead_|moments_|affine_acc" -c 260 -f \
       -o gpurun_out/prof_kernels_$TAG python tools/microbench.py --once > gpurun_out/once_$TAG.log 2>&1; echo "ncu full rc=$?"
+  # the report itself can exceed what gpurun brings back (64 MiB): export the raw page here and keep the report only if small
+  ncu -i gpurun_out/prof_kernels_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw_$TAG.csv 2> /dev/null
+  ls -la gpurun_out/prof_kernels_$TAG.ncu-rep
+  if [ $(stat -c %s gpurun_out/prof_kernels_$TAG.ncu-rep) -gt 30000000 ]; then rm -f gpurun_out/prof_kernels_$TAG.ncu-rep; fi
 fi
 ls -la gpurun_out

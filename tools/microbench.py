@@ -248,7 +248,7 @@ def main():
         bench_small(256, 128, t)
         F.mace(torch.randn(256, 4, 2, device='cuda'), torch.randn(256, 4, 2, device='cuda'))
         F.coverage_mask(rand_h(256, 128)[0].detach(), (128, 128), (128, 128), pool=8)      # the stand-alone analytic mask kernel
-        bench_field_head(64, 128, t)
+        bench_field_head(256, 128, t)
         bench_triplet(256, 64, 32, True, t)
         bench_triplet(64, 1, 128, False, t)
         torch.cuda.synchronize()

@@ -46,8 +46,12 @@ if os.path.isfile(src):
 
 # ---- ncu --set full: a few metrics per captured kernel --------------------------------------------------------
 rep = os.path.join(G, 'prof_kernels_%s.ncu-rep' % tag)
-if os.path.isfile(rep):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+raw_csv = os.path.join(G, 'prof_kernels_raw_%s.csv' % tag)
+if os.path.isfile(rep) or os.path.isfile(raw_csv):
+    if os.path.isfile(raw_csv) and os.path.getsize(raw_csv) > 1000:      # exported on the GPU box (tools/gpu_round.sh)
+        raw = open(raw_csv).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'gpu__time_duration.sum',
@@ -77,6 +81,32 @@ if os.path.isfile(rep):
             json.dump({'dram_bytes_per_launch': total, 'kernels': {k: sum(v) / len(v) for k, v in per.items()},
                        'source': 'ncu --set full, %s, tools/microbench.py --once (B=256, C=64, h=w=32, channels-last)' % os.path.basename(rep)}, f, indent=1)
         print('wrote loss_traffic.json', total)
+
+    # dram traffic per launch of the other entry points bench.py may name in its roofline block (first captured geometry of
+    # each kernel = the B = 256 north-star shape of tools/microbench.py --once)
+    ENTRY = {'bh_bihome_fwd_bwd': ('bihome_stream_kernel', 'bihome_finish_kernel'),
+             'bh_fieldhead_bwd': ('fieldhead_gx_mma_kernel', 'fieldhead_gw_mma_kernel'), 'bh_fieldhead_fwd': ('fieldhead_fwd_mma_kernel',),
+             'bh_fieldhead_moments': ('moments_mma_kernel',), 'bh_fieldhead_affine': ('affine_acc_kernel',),
+             'bh_warp_fwd': ('warp_fwd_tile_kernel',), 'bh_warp_bwd': ('warp_bwd_tile_kernel', 'warp_bwd_finish_kernel'),
+             'bh_pairgen_apply': ('pairgen_apply_kernel',)}
+    ig = hdr.index('launch__grid_size')
+    first = {}
+    for r in rows[2:]:
+        for keys in ENTRY.values():
+            for key in keys:
+                if key in r[ik]:
+                    geo = first.setdefault(key, (r[ig], []))
+                    if geo[0] == r[ig]:
+                        geo[1].append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+    traffic = {}
+    for entry, keys in ENTRY.items():
+        if all(k in first for k in keys):
+            traffic[entry] = sum(sum(first[k][1]) / len(first[k][1]) for k in keys)
+    if traffic:
+        traffic['source'] = 'ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), %s, tools/microbench.py --once, B = 256' % tag
+        with open(os.path.join(P, 'kernel_traffic.json'), 'w') as f:
+            json.dump(traffic, f, indent=1)
+        print('wrote kernel_traffic.json', traffic)
 
 mb = os.path.join(G, 'microbench_%s.jsonl' % tag)
 if os.path.isfile(mb):

@@ -205,13 +205,15 @@ def _plain(model):
 
 
 def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, channels_last=True, log_dir=None, init_seed=0,
-         cuda_graph=False):
+         cuda_graph=False, cudnn_benchmark=True):
     config = engine.load_config(config_file_path)
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit('train.py: no CUDA device -- the biHomE hot path runs on sm_100a kernels only (no CPU fallback)')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    # fixed shapes for the whole run: let cuDNN time its convolution algorithms once per shape (3.8 % of the step on a B200)
+    torch.backends.cudnn.benchmark = cudnn_benchmark
     if world > 1 and not dist.is_initialized():
         dist.init_process_group('nccl', device_id=device)
 
@@ -273,5 +275,7 @@ if __name__ == '__main__':
     ap.add_argument('--init_seed', type=int, default=0, help='torch seed for the initial weights (same on every rank)')
     ap.add_argument('--cuda_graph', action='store_true',
                     help='replay forward + backward from one CUDA graph (single GPU; pays off at small, launch-bound batches)')
+    ap.add_argument('--no_cudnn_benchmark', dest='cudnn_benchmark', action='store_false')
     a = ap.parse_args()
-    main(a.config_file, a.batch_size, a.max_steps, a.synthetic_pool, a.channels_last, a.log_dir, a.init_seed, a.cuda_graph)
+    main(a.config_file, a.batch_size, a.max_steps, a.synthetic_pool, a.channels_last, a.log_dir, a.init_seed, a.cuda_graph,
+         a.cudnn_benchmark)
