@@ -1,8 +1,8 @@
-"""K6 on the device: every entry point of csrc/fieldhead.cu against plain torch ops evaluated in float64 on the GPU, the
-whole stage and the whole Zeng backbone against the ATen modules.  Companion of tests/test_field_head.py (host algebra,
-host emulation, ThreadSanitizer -- all on CPU).  K6 runs on a device only after its self-test passed there
-(bihome_b200/autotune.py); these tests follow that verdict (BH_TEST_UNVERIFIED=1 forces them).  Named to sort last: the
-kernels of this file are the only ones that had not run on hardware when they were committed."""
+"""K6 on the device: every entry point of csrc/fieldhead.cu / fieldhead_mma.cu (scalar kernels, tensor-core kernels in their
+float32-faithful and TF32 modes) against plain torch ops evaluated in float64 on the GPU, the whole stage and the whole Zeng
+backbone against the ATen modules.  Companion of tests/test_field_head.py (host algebra, host emulation of the scalar kernels,
+lane-level emulation of the tensor-core fragment mapping, ThreadSanitizer -- all on CPU).  K6 runs on a device only after its
+self-test passed there (bihome_b200/autotune.py); these tests follow that verdict (BH_TEST_UNVERIFIED=1 forces them)."""
 import copy
 import os
 
@@ -17,7 +17,7 @@ from test_field_head import compare_stage, make_stage, mute_knife_edge_pixels
 @pytest.fixture
 def k6_on_this_device():
     """K6 runs on a device only after its self-test (bihome_b200/autotune.py, in a child process) passed there; the GPU
-    tests below follow that verdict, or BH_TEST_UNVERIFIED=1 forces them (first bring-up on hardware)"""
+    tests below follow that verdict, or BH_TEST_UNVERIFIED=1 forces them (bring-up on new hardware)"""
     if os.environ.get('BH_TEST_UNVERIFIED') == '1':
         return
     import bihome_b200.functional as F
