@@ -280,3 +280,31 @@ def test_reference_optimizer_state_loads_into_the_engine(tmp_path):
         for k in sd1['state']:
             assert torch.equal(sd1['state'][k]['exp_avg'], sd2['state'][k]['exp_avg'])
         one_step(m2, o2, s2)          # and training goes on
+
+
+def test_bench_reference_arm_line_follows_the_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): ONE JSON line with the GPU arm's metric,
+    unit and `config` object, `impl`, a `cpu_baseline` describing the run and an `e2e` block without copies"""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, 'bench.py')
+    r = subprocess.run([sys.executable, bench, '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-batch', '2'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
+    import bench as B
+    assert line['impl'] == 'reference' and line['metric'] == B.METRIC and line['unit'] == B.UNIT and line['higher_is_better'] is True
+    assert line['config'] == B.workload_config(256, 1, 256)          # the same object the GPU arm prints
+    assert line['steps'] == 1 and line['warmup'] == 0 and line['n_gpus'] == 1 and line['value'] > 0
+    cb = line['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == line['value'] and 'B=2' in cb['sample']
+    assert line['e2e'] == {'value': line['value'], 'unit': B.UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # under torchrun only rank 0 works; the other ranks exit 0 without output
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    r = subprocess.run([sys.executable, bench, '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'], capture_output=True,
+                       text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ''
