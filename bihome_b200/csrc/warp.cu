@@ -1685,8 +1685,13 @@ __global__ void __launch_bounds__(256, 3)
         const int y = r / Wo, x = r - y * Wo;
         float u, v, rw;
         project(hm, static_cast<float>(x), static_cast<float>(y), u, v, rw);
-        const Taps taps = make_taps(u, v, Ws, Hs);
-        const TapPack mine = pack_taps(taps, Ws, C, live);
+        float cdu = 0.0f, cdv = 0.0f;          // coverage gradient of this lane's pixel (the taps themselves need not stay live)
+        TapPack mine;
+        {
+            const Taps taps = make_taps(u, v, Ws, Hs);
+            mine = pack_taps(taps, Ws, C, live);
+            if (gMaskPooled != nullptr) cover_grad(taps, cdu, cdv);
+        }
         float my_gu = 0.0f, my_gv = 0.0f;
 #pragma unroll 1
         for (int j = 0; j < 32; j += G) {
@@ -1720,12 +1725,10 @@ __global__ void __launch_bounds__(256, 3)
         }
         if (live) {
             if (gMaskPooled != nullptr) {
-                float du, dv;
-                cover_grad(taps, du, dv);
                 const float gm = __ldg(gMaskPooled + (static_cast<long long>(b) * (Ho / pool) + y / pool) * (Wo / pool) + x / pool) /
                                  static_cast<float>(pool * pool);
-                my_gu = fmaf(gm, du, my_gu);
-                my_gv = fmaf(gm, dv, my_gv);
+                my_gu = fmaf(gm, cdu, my_gu);
+                my_gv = fmaf(gm, cdv, my_gv);
             }
             accum_gh(acc, my_gu, my_gv, u, v, rw, static_cast<float>(x), static_cast<float>(y));
         }
