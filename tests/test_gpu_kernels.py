@@ -376,3 +376,29 @@ def test_bihome_loss_upstream_scale(F):
 def test_mace(F):
     a, b = torch.randn(9, 4, 2), torch.randn(9, 4, 2)
     assert abs(F.mace(a.cuda(), b.cuda()).item() - R().mace(a.numpy(), b.numpy())) < 1e-6
+
+
+def test_feature_warp_fuzz_shapes(F):
+    """channels-last feature warp (warp-cooperative kernels, the thread-per-quad kernels for other channel counts, the generic
+    kernel for C % 4 != 0) on ragged shapes: 24 deterministic draws, forward and dH against the float64 closed form"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=24, deadline=None, derandomize=True)
+    @given(B=st.integers(1, 3), C=st.sampled_from([4, 8, 12, 16, 24, 32, 64, 128]), Hs=st.integers(5, 40), Ws=st.integers(5, 40),
+           Ho=st.integers(1, 37), Wo=st.integers(1, 37))
+    def run(B, C, Hs, Ws, Ho, Wo):
+        gen = torch.Generator().manual_seed(B * 7919 + C * 31 + Hs * 13 + Wo)
+        img = torch.rand(B, C, Hs, Ws, generator=gen, dtype=torch.float64).float().double()
+        H = _rand_h(B, min(Hs, Ws), gen).float().double()
+        gO = torch.randn(B, C, Ho, Wo, generator=gen, dtype=torch.float64).float().double()
+        cells = _kernel_cells(H.numpy().astype(np.float32), Ho, Wo)
+        H64 = H.clone().requires_grad_(True)
+        ref = _warp_direct_autograd(img, H64, Ho, Wo, cells)
+        gH64, = torch.autograd.grad((ref * gO).sum(), H64)
+        x = img.float().cuda().contiguous(memory_format=torch.channels_last)
+        Hc = H.float().cuda().requires_grad_(True)
+        out = F.warp(x, Hc, Ho, Wo)
+        assert rel_l2(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+        gH, = torch.autograd.grad((out * gO.float().cuda()).sum(), Hc)
+        assert rel_l2(gH.cpu().numpy(), gH64.numpy()) < 2e-5
+    run()

@@ -194,3 +194,19 @@ def test_triplet_loss_full_size_properties(F):
     assert torch.allclose(open_parts[:, 1], parts[:, 1] + big, rtol=1e-5)
     swap_b, swap_parts = F.triplet_loss(f2, f1, f2w, f1w, a2, None, a1, None, H21, H12, lines=2, distance='l1', hinge=None, mu=0.01)
     assert torch.allclose(swap_parts[:, 0], parts[:, 1], rtol=1e-6, atol=1e-6) and torch.allclose(swap_parts[:, 1], parts[:, 0], rtol=1e-6, atol=1e-6)
+
+
+def test_triplet_loss_fuzz_shapes(F):
+    """ragged shapes the fixed cases do not reach: channel counts that are not multiples of four, pixel counts that are not
+    multiples of four or of the tile sizes, one-pixel maps, both layouts -- 30 deterministic draws against the oracle"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(B=st.integers(1, 4), C=st.sampled_from([1, 2, 3, 4, 5, 8, 12, 16, 20, 32]), h=st.integers(1, 9), w=st.integers(1, 9),
+           nhwc=st.booleans(), case=st.sampled_from(CASES))
+    def run(B, C, h, w, nhwc, case):
+        lines, distance, hinge, margin, crd = case
+        if distance == 'cosine' and C == 1:
+            return
+        test_triplet_loss_vs_oracle(F, lines, distance, hinge, margin, crd, B, C, h, w, nhwc)
+    run()

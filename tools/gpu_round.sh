@@ -34,8 +34,11 @@ if has m; then
   timeout 600 python tools/microbench.py > gpurun_out/microbench_$TAG.jsonl 2>&1; echo "microbench rc=$?"; head -14 gpurun_out/microbench_$TAG.jsonl
 fi
 if has l; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches_$TAG.csv \
-      python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "launch list rc=$?"
+  # application only: ncu would otherwise follow the field head's self-test into its child process; cudnn.benchmark off: its
+  # trial launches are not part of a step
+  BH_FIELD_HEAD=fused timeout 900 ncu --target-processes application-only --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv \
+      --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-cudnn-benchmark \
+      > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "launch list rc=$?"
 fi
 if has n; then
   timeout 1500 ncu --set full --clock-control none --import-source on \
