@@ -145,11 +145,13 @@ __device__ __forceinline__ void grad_elem(float x1w, float x2, float x2w, float 
             if (!(phi<kDist>(e1, inv_c) - p3 + m1 > 0.0f)) c1 = 0.0f;
             if (!(phi<kDist>(e2, inv_c) - p3 + m2 > 0.0f)) c2 = 0.0f;
         }
-        const float d1 = c1 * dphi<kDist>(e1, inv_c), d2 = c2 * dphi<kDist>(e2, inv_c), d3 = (c1 + c2) * dphi<kDist>(e3, inv_c);
-        ga = d1;
-        gb = d2;
-        gc = -d2 - d3;
-        gd = -d1 + d3;
+        // d/df1 = -c2 phi'(e2) - (c1 + c2) phi'(e3), d/df2 = -c1 phi'(e1) + (c1 + c2) phi'(e3), grouped by weight: when one
+        // line's weight is tiny and the signs oppose, the large terms cancel exactly instead of leaving their rounding error
+        const float p1 = dphi<kDist>(e1, inv_c), p2 = dphi<kDist>(e2, inv_c), p3 = dphi<kDist>(e3, inv_c);
+        ga = c1 * p1;
+        gb = c2 * p2;
+        gc = -fmaf(c2, p2 + p3, c1 * p3);
+        gd = fmaf(c1, p3 - p1, c2 * p3);
     }
 }
 

@@ -100,6 +100,10 @@ SHAPES = [
 def test_triplet_loss_vs_oracle(F, lines, distance, hinge, margin, crd, B, C, h, w, nhwc):
     if C == 1 and distance == 'cosine':
         pytest.skip('cosine similarity of one-channel maps is +-1: no gradient to compare')
+    _compare_with_oracle(F, lines, distance, hinge, margin, crd, B, C, h, w, nhwc, TOL)
+
+
+def _compare_with_oracle(F, lines, distance, hinge, margin, crd, B, C, h, w, nhwc, TOL):
     mu = 0.01
     scale = (1.0, 1.0) if hinge != 'pixel' else (float(B), 0.5)
     f, masks, H12, H21 = _inputs(B, C, h, w, distance, hinge, margin, seed0=1000 * lines + 10 * C + h)
@@ -129,6 +133,8 @@ def test_triplet_loss_vs_oracle(F, lines, distance, hinge, margin, crd, B, C, h,
         assert rel_l2(parts[:, 3].cpu().numpy(), p64['den2'].detach().numpy()) < TOL
         assert rel_l2(parts[:, 4].cpu().numpy(), p64['ln3'].detach().numpy()) < TOL
     used = [i for i in range(10) if g64[i] is not None and float(g64[i].abs().max()) > 0]
+    if not used:          # every hinge closed (tiny maps): nothing carries a gradient
+        return
     g = torch.autograd.grad(loss_b.sum(), [leaves[i] for i in used], allow_unused=True)
     names = ['f1', 'f2', 'f1w', 'f2w', 'a1', 'b2', 'a2', 'b1', 'H12', 'H21']
     for gi, i in zip(g, used):
@@ -198,7 +204,9 @@ def test_triplet_loss_full_size_properties(F):
 
 def test_triplet_loss_fuzz_shapes(F):
     """ragged shapes the fixed cases do not reach: channel counts that are not multiples of four, pixel counts that are not
-    multiples of four or of the tile sizes, one-pixel maps, both layouts -- 30 deterministic draws against the oracle"""
+    multiples of four or of the tile sizes, one-pixel maps, both layouts -- 30 deterministic draws against the oracle.
+    Tolerance 1e-4: a map of a few pixels has no averaging, a loss that is a difference of nearly equal cosines (or a gradient
+    left over after two weights cancel) carries the float32 rounding of its terms."""
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=30, deadline=None, derandomize=True)
@@ -208,5 +216,5 @@ def test_triplet_loss_fuzz_shapes(F):
         lines, distance, hinge, margin, crd = case
         if distance == 'cosine' and C == 1:
             return
-        test_triplet_loss_vs_oracle(F, lines, distance, hinge, margin, crd, B, C, h, w, nhwc)
+        _compare_with_oracle(F, lines, distance, hinge, margin, crd, B, C, h, w, nhwc, 1e-4)
     run()
