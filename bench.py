@@ -270,13 +270,19 @@ def run_ours(args):
     px = 128 * 128
     ALG = {'bh_warp_fwd': 270336, 'bh_warp_bwd': 270408, 'bh_bihome_fwd_bwd': LOSS_BYTES_PER_PAIR,
            'bh_pairgen_apply': 2 * 3 * (128 + 64) ** 2 + 2 * 4 * 128 * 128,
-           'bh_fieldhead_moments': 64 * px, 'bh_fieldhead_fwd': 72 * px, 'bh_fieldhead_bwd': 136 * px, 'bh_fieldhead_affine': 192 * px}
+           'bh_fieldhead_moments': 64 * px, 'bh_fieldhead_fwd': 72 * px, 'bh_fieldhead_bwd': 136 * px, 'bh_fieldhead_affine': 192 * px,
+           # K7 per pass over one sample's [64,64,64] stem tensor (1 MiB): forward reads it twice (the batch statistics force the
+           # second pass) and writes the pooled quarter; backward reads it twice, writes its gradient, reads the pooled gradient
+           # and the 1-byte window codes twice
+           'bh_stem_fwd': 2 * 1048576 + 262144, 'bh_stem_bwd': 3 * 1048576 + 2 * (262144 + 65536)}
     NAMES = {'bh_bihome_fwd_bwd': 'bihome_stream_kernel<false,1> + bihome_finish_kernel (bh_bihome_fwd_bwd, channels-last C=64, B<512)',
              'bh_fieldhead_bwd': 'fieldhead_gx_mma_kernel + fieldhead_gw_mma_kernel (bh_fieldhead_bwd: mma.sync TF32 tensor-core kernels, '
                                  'bound by the mma.sync issue rate and the ReLU/projection epilogue, not by HBM)',
              'bh_fieldhead_fwd': 'fieldhead_fwd_mma_kernel (bh_fieldhead_fwd, mma.sync TF32)',
              'bh_warp_fwd': 'warp_fwd_tile_kernel (bh_warp_fwd: TMA box per 32x32 tile)', 'bh_warp_bwd': 'warp_bwd_tile_kernel + finish (bh_warp_bwd)',
-             'bh_pairgen_apply': 'pairgen_apply_kernel (bh_pairgen_apply: instruction bound, cv2-exact colour math)'}
+             'bh_pairgen_apply': 'pairgen_apply_kernel (bh_pairgen_apply: instruction bound, cv2-exact colour math)',
+             'bh_stem_fwd': 'bn_stats_kernel + bn_finalize_kernel + stem_pool_fwd_kernel (bh_stem_fwd: BatchNorm -> ReLU -> MaxPool, channels-last)',
+             'bh_stem_bwd': 'stem_bwd_reduce_kernel + stem_bwd_finalize_kernel + stem_bwd_apply_kernel (bh_stem_bwd)'}
     for name, per_pair in ALG.items():
         if name in kernels and kernels[name]['avg_ms'] > 0:
             gbs = per_pair * B / (kernels[name]['avg_ms'] * 1e-3) / 1e9
@@ -312,7 +318,8 @@ def run_ours(args):
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': workload_config(B, world, args.pool),
-            'layout': {'channels_last': bool(args.channels_last), 'cudnn_benchmark': bool(args.cudnn_benchmark), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten'},
+            'layout': {'channels_last': bool(args.channels_last), 'cudnn_benchmark': bool(args.cudnn_benchmark), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten',
+                       'stem': 'fused (K7)' if 'bh_stem_fwd' in kernels else 'aten'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
             'gpu_launches': launches, 'roofline': roofline, 'warp_loss_roofline': warp_loss, 'cpu_baseline': cpu_baseline, 'clocks': clk,

@@ -87,7 +87,12 @@ class Model(nn.Module):
         self.load_state_dict(picked, strict=False)
 
     def _forward(self, x):
-        for i in range(1, 8):
+        # layer1 = Conv2d 7x7/2 -> BatchNorm2d -> ReLU -> MaxPool2d(3, 2, 1): after the convolution (cuDNN) the three
+        # memory-bound modules run as one stage (K7, csrc/stem.cu) when the tensor is channels-last and BatchNorm trains
+        conv, bn, act, pool = self.layer1
+        x = conv(x)
+        x = F.stem(bn, x) if F.stem_supported(bn, pool, x) else pool(act(bn(x)))
+        for i in range(2, 8):
             x = getattr(self, 'layer%d' % i)(x)
         # layer8 (1x1 conv -> BatchNorm -> ReLU -> 1x1 conv at full resolution) is 21 passes over a [B,128,P,P] tensor
         # through ATen; K6 computes it per pixel from the 16-channel input when the device's self-test picked it

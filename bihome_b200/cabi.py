@@ -36,6 +36,10 @@ SIGNATURES = {
     'bh_fieldhead_fwd': (_i, [_vp] * 6 + [_i, _i, _i, _i, _i, _vp]),
     'bh_fieldhead_bwd': (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _vp]),
     'bh_fieldhead_affine': (_i, [_vp] * 4 + [ctypes.c_longlong, _i, _i, _vp]),
+    'bh_stem_supported': (_i, [_i]),
+    'bh_stem_workspace_bytes': (_sz, [_i]),
+    'bh_stem_fwd': (_i, [_vp] * 5 + [_f, _f] + [_vp] * 4 + [_sz, _i, _i, _i, _i, _vp]),
+    'bh_stem_bwd': (_i, [_vp] * 8 + [_sz, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -75,7 +75,7 @@ __device__ __forceinline__ void jacobi9(double* A, double* V, int lane) {
         }
         off = warp_sum(off);
         dia = warp_sum(dia);
-        if (off <= 1e-28 * dia) break;  // off-diagonal mass below 1e-14 relative: converged in float64
+        if (off <= 1e-26 * dia) break;  // off-diagonal mass below 1e-13 relative (the next sweep would square it)
         for (int round = 0; round < 9; ++round) {
             if (lane < 4) {
                 // circle method: slot 0 is fixed (the bye, index 9), slots 1..9 hold indices rotated by `round`
@@ -85,12 +85,17 @@ __device__ __forceinline__ void jacobi9(double* A, double* V, int lane) {
                 int p = (k - 1 + round) % 9, q = (9 - k - 1 + round + 9) % 9;   // slots k and 9-k
                 if (p > q) { const int t = p; p = q; q = t; }
                 const double apq = A[p * 9 + q], app = A[p * 9 + p], aqq = A[q * 9 + q];
+                // rotation that annihilates A[p][q], |angle| <= pi/4, without a division: with al = aqq - app, be = 2 apq,
+                // cos 2phi = |al| / rho, c = sqrt((1 + cos 2phi) / 2), s = sign(al) be / (2 rho c) -- two rsqrt instead of the
+                // textbook's div, sqrt, div, sqrt, div chain (the rotation parameters are the serial part of every round)
                 double c = 1.0, s = 0.0;
-                if (fabs(apq) > 1e-300) {
-                    const double theta = (aqq - app) / (2.0 * apq);
-                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    c = 1.0 / sqrt(t * t + 1.0);
-                    s = t * c;
+                const double al = aqq - app, be = 2.0 * apq, r2 = al * al + be * be;
+                if (fabs(apq) > 1e-300 && r2 > 1e-300) {
+                    const double ir = rsqrt(r2);
+                    const double hc = fma(0.5 * fabs(al), ir, 0.5);
+                    const double ih = rsqrt(hc);
+                    c = hc * ih;
+                    s = (al >= 0.0 ? be : -be) * (0.5 * ir) * ih;
                 }
                 cs[lane][0] = c; cs[lane][1] = s;
                 pq[lane][0] = p; pq[lane][1] = q;

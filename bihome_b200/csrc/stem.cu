@@ -1,0 +1,415 @@
+// K7: the ResNet stem's BatchNorm2d (batch statistics) -> ReLU -> MaxPool2d(3, stride 2, padding 1) as ONE streaming stage,
+// channels-last.  Row f3 of the hot-path table ("fusions around the frozen extractor"): the same three modules open the
+// frozen perceptual extractor (torchvision resnet.bn1 / relu / maxpool, reference src/heads/PerceptualHead.py:56-58, four
+// passes per training step) and the Zeng backbone (layer1, reference src/backbones/Rethinking.py:31-36, two passes).
+//
+// Through ATen the stage is six passes over a [B,64,64,64] tensor forward (BatchNorm statistics + normalise, ReLU, pooling
+// with int64 indices: 2.1 GB of traffic at B = 256) and about as many backward.  Here:
+//   forward   bn_stats_kernel        read x once: per-channel sum / sum of squares (float32 runs of 16 pixels, float64 above)
+//             bn_finalize_kernel     fixed-order float64 reduction of the per-CTA partials -> scale, shift, mean, 1/std and
+//                                    the running statistics (momentum update, unbiased variance) in place
+//             stem_pool_fwd_kernel   read x once more, write the POOLED output (a quarter of the elements) and one byte per
+//                                    output with the window position of its maximum (ATen keeps an int64 index)
+//   backward  stem_bwd_reduce_kernel read x, the pooled upstream gradient and the codes: sum dy, sum dy * xhat per channel
+//             stem_bwd_finalize_kernel  -> gamma / beta gradients and the three per-channel coefficients of the input gradient
+//             stem_bwd_apply_kernel  gx = a dy + b x + c   (BatchNorm's batch-statistics backward folded into an affine map)
+// Compulsory traffic per pass at B = 256 (x = 268 MB, pooled tensors 67 MB, codes 17 MB): forward 2 x 268 + 67 + 17 = 620 MB,
+// backward 3 x 268 + 2 x (67 + 17) = 972 MB.  HBM bound; no re-read beyond the second pass that the statistics force.
+//
+// Semantics kept (torch.nn.functional.batch_norm / max_pool2d): biased variance for the normalisation, unbiased for
+// running_var, eps inside the square root; the pooling maximum is the FIRST maximum in row-major window order (ATen's
+// `val > maxval` scan), padding never wins; a window whose maximum is 0 (every pre-activation <= 0) passes no gradient,
+// exactly as threshold_backward does after max_pool2d_backward.
+#include <math.h>
+
+#include "bh_common.cuh"
+
+namespace bh {
+
+constexpr int kStemThreads = 256;
+constexpr int kStemRun = 16;        // pixels a thread accumulates in float32 before it adds to its float64 sums
+constexpr int kStemRows = 8;        // pooled rows one forward work item walks
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---- per-CTA partial sums -> partials[cta][stat][C] (float64), fixed order ------------------------------------------
+// every thread holds 8 float64 sums (two statistics x its channel quad); pixel lanes are added in lane order
+__device__ __forceinline__ void stem_cta_partials(const double (&s)[8], double* __restrict__ partials, int Q, int lq, int C) {
+    __shared__ double red[8 * kStemThreads];
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[(k * PL + pl) * Q + q] = s[k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 8 * Q; o += kStemThreads) {
+        const int k = o >> lq, qq = o & (Q - 1);
+        double sum = 0.0;
+        for (int p = 0; p < PL; ++p) sum += red[(k * PL + p) * Q + qq];
+        partials[(static_cast<size_t>(blockIdx.x) * 2 + (k >> 2)) * C + qq * 4 + (k & 3)] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(kStemThreads) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ partials,
+                                                                long long n_pix, int Q, int lq) {
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long p = static_cast<long long>(blockIdx.x) * PL + pl;
+    while (p < n_pix) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll 4
+        for (int u = 0; u < kStemRun; ++u) {
+            if (p < n_pix) {
+                const float4 v = ldg_stream(x4 + p * Q + q);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+            }
+            p += stride;
+        }
+        s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+        s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+    }
+    stem_cta_partials(s, partials, Q, lq, Q * 4);
+}
+
+// one warp per channel: lanes stride over the CTAs' partials, shuffle tree (fixed order => bit reproducible)
+__device__ __forceinline__ void stem_sum_partials(const double* __restrict__ partials, int G, int C, int c, double& s0, double& s1) {
+    const int lane = threadIdx.x & 31;
+    s0 = 0.0; s1 = 0.0;
+    for (int g = lane; g < G; g += 32) {
+        s0 += partials[(static_cast<size_t>(g) * 2 + 0) * C + c];
+        s1 += partials[(static_cast<size_t>(g) * 2 + 1) * C + c];
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+}
+
+// stats [4][C]: scale = gamma / std, shift = beta - mean * scale, mean, 1/std
+__global__ void __launch_bounds__(kStemThreads) bn_finalize_kernel(const double* __restrict__ partials, int G, int C, double n,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                   float momentum, float eps, float* __restrict__ stats) {
+    const int c = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s, ss;
+    stem_sum_partials(partials, G, C, c, s, ss);
+    if ((threadIdx.x & 31) != 0) return;
+    const double mean = s / n;
+    const double var = fmax(ss / n - mean * mean, 0.0);
+    const float mean_f = static_cast<float>(mean);
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = (gamma ? gamma[c] : 1.0f) * invstd;
+    stats[c] = sc;
+    stats[C + c] = fmaf(-mean_f, sc, beta ? beta[c] : 0.0f);
+    stats[2 * C + c] = mean_f;
+    stats[3 * C + c] = invstd;
+    if (running_mean) running_mean[c] = fmaf(momentum, mean_f - running_mean[c], running_mean[c]);
+    if (running_var) {
+        const float unbiased = static_cast<float>(n > 1.0 ? var * n / (n - 1.0) : var);
+        running_var[c] = fmaf(momentum, unbiased - running_var[c], running_var[c]);
+    }
+}
+
+// ---- forward: normalise, ReLU, 3x3 / stride-2 maximum ----------------------------------------------------------------
+struct RowMax {
+    float4 m;      // horizontal maximum of relu(scale x + shift) over the (up to) three columns of the window
+    int kx[4];     // window column 0..2 of that maximum, per channel of the quad
+};
+__device__ __forceinline__ void take(float v, int k, float& m, int& km) {
+    if (v > m) { m = v; km = k; }
+}
+__device__ __forceinline__ RowMax stem_row(const float* __restrict__ xn, int iy, int ox, int H, int W, int C, int q, const float4& sc,
+                                           const float4& sh) {
+    RowMax r;
+    r.m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    r.kx[0] = r.kx[1] = r.kx[2] = r.kx[3] = 0;
+    if (iy < 0 || iy >= H) return r;
+    const float* row = xn + (static_cast<size_t>(iy) * W) * C + 4 * q;
+    float4 v[3];
+    bool in[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ix = 2 * ox - 1 + k;
+        in[k] = ix >= 0 && ix < W;
+        if (in[k]) v[k] = ld4(row + static_cast<size_t>(ix) * C);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!in[k]) continue;
+        take(fmaxf(fmaf(v[k].x, sc.x, sh.x), 0.0f), k, r.m.x, r.kx[0]);
+        take(fmaxf(fmaf(v[k].y, sc.y, sh.y), 0.0f), k, r.m.y, r.kx[1]);
+        take(fmaxf(fmaf(v[k].z, sc.z, sh.z), 0.0f), k, r.m.z, r.kx[2]);
+        take(fmaxf(fmaf(v[k].w, sc.w, sh.w), 0.0f), k, r.m.w, r.kx[3]);
+    }
+    return r;
+}
+__device__ __forceinline__ void stem_merge(float& m, int& code, float rm, int rk, int ky) {
+    if (rm > m) { m = rm; code = 3 * ky + rk; }
+}
+
+// work item = (sample, strip of kStemRows pooled rows, PL pooled columns); a thread marches down its column: the bottom
+// row of one window is the top row of the next, so every input row is loaded once per strip
+template <bool kCode>
+__global__ void __launch_bounds__(kStemThreads) stem_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                                     float* __restrict__ y, uint8_t* __restrict__ code, int H,
+                                                                     int W, int Ho, int Wo, int Q, int lq, int strips, int xblocks) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    int item = blockIdx.x;
+    const int xb = item % xblocks;
+    item /= xblocks;
+    const int strip = item % strips, n = item / strips;
+    const int ox = xb * PL + pl;
+    if (ox >= Wo) return;
+    const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
+    const float* xn = x + static_cast<size_t>(n) * H * W * C;
+    const int oy0 = strip * kStemRows, oy1 = min(oy0 + kStemRows, Ho);
+    RowMax top = stem_row(xn, 2 * oy0 - 1, ox, H, W, C, q, sc, sh);
+    for (int oy = oy0; oy < oy1; ++oy) {
+        const RowMax mid = stem_row(xn, 2 * oy, ox, H, W, C, q, sc, sh);
+        const RowMax bot = stem_row(xn, 2 * oy + 1, ox, H, W, C, q, sc, sh);
+        float4 m = top.m;
+        int cd[4] = {top.kx[0], top.kx[1], top.kx[2], top.kx[3]};
+        stem_merge(m.x, cd[0], mid.m.x, mid.kx[0], 1); stem_merge(m.y, cd[1], mid.m.y, mid.kx[1], 1);
+        stem_merge(m.z, cd[2], mid.m.z, mid.kx[2], 1); stem_merge(m.w, cd[3], mid.m.w, mid.kx[3], 1);
+        stem_merge(m.x, cd[0], bot.m.x, bot.kx[0], 2); stem_merge(m.y, cd[1], bot.m.y, bot.kx[1], 2);
+        stem_merge(m.z, cd[2], bot.m.z, bot.kx[2], 2); stem_merge(m.w, cd[3], bot.m.w, bot.kx[3], 2);
+        const size_t o = ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * C + 4 * q;
+        stg_stream(reinterpret_cast<float4*>(y + o), m);
+        if (kCode) *reinterpret_cast<uint32_t*>(code + o) = static_cast<uint32_t>(cd[0]) | (static_cast<uint32_t>(cd[1]) << 8) |
+                                                             (static_cast<uint32_t>(cd[2]) << 16) | (static_cast<uint32_t>(cd[3]) << 24);
+        top = bot;
+    }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------------------
+// A thread owns a 2x2 block of input pixels (rows 2k, 2k+1, columns 2m, 2m+1) of its channel quad.  The block is touched by
+// exactly four windows -- (k,m), (k,m+1), (k+1,m), (k+1,m+1) -- at nine fixed (pixel, window position) pairs, so the
+// upstream gradient is gathered with no divergence and no atomics:
+//   pixel (2k,   2m)   : window (k,m) position (1,1)
+//   pixel (2k,   2m+1) : (k,m) (1,2) ; (k,m+1) (1,0)
+//   pixel (2k+1, 2m)   : (k,m) (2,1) ; (k+1,m) (0,1)
+//   pixel (2k+1, 2m+1) : (k,m) (2,2) ; (k,m+1) (2,0) ; (k+1,m) (0,2) ; (k+1,m+1) (0,0)
+struct StemBlock {
+    float4 x[4];    // the four pixels, row-major
+    float4 dy[4];   // gradient w.r.t. the BatchNorm output at those pixels (ReLU and pooling undone)
+    bool in[4];
+};
+__device__ __forceinline__ float pick(uint32_t codes, int ch, int want, float g) {
+    return ((codes >> (8 * ch)) & 0xffu) == static_cast<uint32_t>(want) ? g : 0.0f;
+}
+__device__ __forceinline__ float4 pick4(uint32_t codes, int want, const float4& g) {
+    return make_float4(pick(codes, 0, want, g.x), pick(codes, 1, want, g.y), pick(codes, 2, want, g.z), pick(codes, 3, want, g.w));
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float4 gate4(const float4& d, const float4& x, const float4& sc, const float4& sh) {
+    return make_float4(fmaf(x.x, sc.x, sh.x) > 0.0f ? d.x : 0.0f, fmaf(x.y, sc.y, sh.y) > 0.0f ? d.y : 0.0f,
+                       fmaf(x.z, sc.z, sh.z) > 0.0f ? d.z : 0.0f, fmaf(x.w, sc.w, sh.w) > 0.0f ? d.w : 0.0f);
+}
+__device__ __forceinline__ void stem_block(StemBlock& b, const float* __restrict__ xn, const float* __restrict__ gn,
+                                           const uint8_t* __restrict__ cn, int k, int m, int H, int W, int Ho, int Wo, int C, int q,
+                                           const float4& sc, const float4& sh) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool wy = k + 1 < Ho, wx = m + 1 < Wo;
+    const size_t w00 = (static_cast<size_t>(k) * Wo + m) * C + 4 * q;
+    const size_t w01 = w00 + C, w10 = w00 + static_cast<size_t>(Wo) * C, w11 = w10 + C;
+    // the four windows: gradient quad and the four position codes
+    const float4 g00 = ld4(gn + w00);
+    const uint32_t c00 = __ldg(reinterpret_cast<const uint32_t*>(cn + w00));
+    const float4 g01 = wx ? ld4(gn + w01) : zero;
+    const uint32_t c01 = wx ? __ldg(reinterpret_cast<const uint32_t*>(cn + w01)) : 0xffffffffu;
+    const float4 g10 = wy ? ld4(gn + w10) : zero;
+    const uint32_t c10 = wy ? __ldg(reinterpret_cast<const uint32_t*>(cn + w10)) : 0xffffffffu;
+    const float4 g11 = (wx && wy) ? ld4(gn + w11) : zero;
+    const uint32_t c11 = (wx && wy) ? __ldg(reinterpret_cast<const uint32_t*>(cn + w11)) : 0xffffffffu;
+    const int iy = 2 * k, ix = 2 * m;
+    b.in[0] = true;
+    b.in[1] = ix + 1 < W;
+    b.in[2] = iy + 1 < H;
+    b.in[3] = b.in[1] && b.in[2];
+    const float* p = xn + (static_cast<size_t>(iy) * W + ix) * C + 4 * q;
+    b.x[0] = ldg_stream(reinterpret_cast<const float4*>(p));
+    b.x[1] = b.in[1] ? ldg_stream(reinterpret_cast<const float4*>(p + C)) : zero;
+    b.x[2] = b.in[2] ? ldg_stream(reinterpret_cast<const float4*>(p + static_cast<size_t>(W) * C)) : zero;
+    b.x[3] = b.in[3] ? ldg_stream(reinterpret_cast<const float4*>(p + static_cast<size_t>(W) * C + C)) : zero;
+    b.dy[0] = pick4(c00, 4, g00);
+    b.dy[1] = pick4(c00, 5, g00); add4(b.dy[1], pick4(c01, 3, g01));
+    b.dy[2] = pick4(c00, 7, g00); add4(b.dy[2], pick4(c10, 1, g10));
+    b.dy[3] = pick4(c00, 8, g00); add4(b.dy[3], pick4(c01, 6, g01)); add4(b.dy[3], pick4(c10, 2, g10)); add4(b.dy[3], pick4(c11, 0, g11));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b.dy[i] = b.in[i] ? gate4(b.dy[i], b.x[i], sc, sh) : zero;
+}
+
+// item = (sample, block row k, xblock); partials[cta][0][C] = sum dy, [cta][1][C] = sum dy * xhat
+__global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                                       const float* __restrict__ gy, const uint8_t* __restrict__ code,
+                                                                       double* __restrict__ partials, int N, int H, int W, int Ho,
+                                                                       int Wo, int Q, int lq, int xblocks) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q), mu = ld4(stats + 2 * C + 4 * q), is = ld4(stats + 3 * C + 4 * q);
+    const float4 off = make_float4(-mu.x * is.x, -mu.y * is.y, -mu.z * is.z, -mu.w * is.w);   // xhat = x * invstd + off
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long items = static_cast<long long>(N) * Ho * xblocks;
+    long long item = blockIdx.x;
+    while (item < items) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll 1
+        for (int u = 0; u < 4 && item < items; ++u, item += gridDim.x) {
+            const int xb = static_cast<int>(item % xblocks);
+            const long long t = item / xblocks;
+            const int k = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
+            const int m = xb * PL + pl;
+            if (m >= Wo) continue;
+            StemBlock blk;
+            stem_block(blk, x + static_cast<size_t>(n) * H * W * C, gy + static_cast<size_t>(n) * Ho * Wo * C,
+                       code + static_cast<size_t>(n) * Ho * Wo * C, k, m, H, W, Ho, Wo, C, q, sc, sh);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 d = blk.dy[i], xv = blk.x[i];
+                a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+                b.x = fmaf(d.x, fmaf(xv.x, is.x, off.x), b.x); b.y = fmaf(d.y, fmaf(xv.y, is.y, off.y), b.y);
+                b.z = fmaf(d.z, fmaf(xv.z, is.z, off.z), b.z); b.w = fmaf(d.w, fmaf(xv.w, is.w, off.w), b.w);
+            }
+        }
+        s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+        s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+    }
+    stem_cta_partials(s, partials, Q, lq, C);
+}
+
+// coef [3][C]: gx = a dy + b x + c with a = scale, b = -scale * c2 / std, c = -scale * (c1 - c2 * mean / std),
+// c1 = mean(dy), c2 = mean(dy * xhat): BatchNorm's batch-statistics backward.  ggamma = sum dy * xhat, gbeta = sum dy.
+__global__ void __launch_bounds__(kStemThreads) stem_bwd_finalize_kernel(const double* __restrict__ partials, int G, int C, double n,
+                                                                         const float* __restrict__ stats, float* __restrict__ coef,
+                                                                         float* __restrict__ ggamma, float* __restrict__ gbeta) {
+    const int c = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s1, s2;
+    stem_sum_partials(partials, G, C, c, s1, s2);
+    if ((threadIdx.x & 31) != 0) return;
+    const double sc = stats[c], mean = stats[2 * C + c], invstd = stats[3 * C + c];
+    const double c1 = s1 / n, c2 = s2 / n;
+    coef[c] = static_cast<float>(sc);
+    coef[C + c] = static_cast<float>(-sc * c2 * invstd);
+    coef[2 * C + c] = static_cast<float>(-sc * (c1 - c2 * mean * invstd));
+    if (ggamma) ggamma[c] = static_cast<float>(s2);
+    if (gbeta) gbeta[c] = static_cast<float>(s1);
+}
+
+__global__ void __launch_bounds__(kStemThreads, 3) stem_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                                      const float* __restrict__ coef, const float* __restrict__ gy,
+                                                                      const uint8_t* __restrict__ code, float* __restrict__ gx, int H,
+                                                                      int W, int Ho, int Wo, int Q, int lq, int xblocks) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    int item = blockIdx.x;
+    const int xb = item % xblocks;
+    item /= xblocks;
+    const int k = item % Ho, n = item / Ho;
+    const int m = xb * PL + pl;
+    if (m >= Wo) return;
+    const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
+    const float4 ca = ld4(coef + 4 * q), cb = ld4(coef + C + 4 * q), cc = ld4(coef + 2 * C + 4 * q);
+    StemBlock blk;
+    stem_block(blk, x + static_cast<size_t>(n) * H * W * C, gy + static_cast<size_t>(n) * Ho * Wo * C,
+               code + static_cast<size_t>(n) * Ho * Wo * C, k, m, H, W, Ho, Wo, C, q, sc, sh);
+    float* out = gx + (static_cast<size_t>(n) * H * W + static_cast<size_t>(2 * k) * W + 2 * m) * C + 4 * q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!blk.in[i]) continue;
+        const float4 d = blk.dy[i], xv = blk.x[i];
+        const float4 r = make_float4(fmaf(ca.x, d.x, fmaf(cb.x, xv.x, cc.x)), fmaf(ca.y, d.y, fmaf(cb.y, xv.y, cc.y)),
+                                     fmaf(ca.z, d.z, fmaf(cb.z, xv.z, cc.z)), fmaf(ca.w, d.w, fmaf(cb.w, xv.w, cc.w)));
+        stg_stream(reinterpret_cast<float4*>(out + (static_cast<size_t>(i >> 1) * W + (i & 1)) * C), r);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+struct StemGeo {
+    int Q, lq, PL, Ho, Wo, xblocks;
+};
+inline int stem_geo(int N, int H, int W, int C, StemGeo& g) {
+    if (N <= 0 || H <= 0 || W <= 0 || C < 4) return BH_E_SHAPE;
+    if (C % 4 != 0 || C > 4 * kStemThreads) return BH_E_UNSUPPORTED;
+    g.Q = C / 4;
+    if (g.Q & (g.Q - 1)) return BH_E_UNSUPPORTED;          // channel quads per pixel must divide the CTA: C = 4 .. 1024, a power of two
+    g.lq = 0;
+    while ((1 << g.lq) < g.Q) ++g.lq;
+    g.PL = kStemThreads / g.Q;
+    g.Ho = (H - 1) / 2 + 1;
+    g.Wo = (W - 1) / 2 + 1;
+    g.xblocks = (g.Wo + g.PL - 1) / g.PL;
+    if (static_cast<long long>(N) * g.Ho * g.xblocks > 0x7fffffffll) return BH_E_SHAPE;
+    return BH_OK;
+}
+inline int stem_reduce_grid() { return kNumSMs * 8; }
+inline size_t stem_ws_doubles(int C) { return static_cast<size_t>(stem_reduce_grid()) * 2 * C; }
+
+}  // namespace bh
+
+extern "C" int bh_stem_supported(int C) {
+    bh::StemGeo g;
+    return bh::stem_geo(1, 2, 2, C, g) == BH_OK ? 1 : 0;
+}
+
+extern "C" size_t bh_stem_workspace_bytes(int C) {
+    if (C <= 0) return 0;
+    return bh::stem_ws_doubles(C) * sizeof(double) + static_cast<size_t>(3) * C * sizeof(float);
+}
+
+extern "C" int bh_stem_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                           float momentum, float eps, float* y, uint8_t* code, float* stats, void* ws, size_t ws_bytes, int N,
+                           int H, int W, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!x || !y || !stats || !ws) return BH_E_NULL;
+    StemGeo g;
+    const int rc = stem_geo(N, H, W, C, g);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(x) || !aligned16(y) || !aligned16(stats) || !aligned16(ws) || (code && (reinterpret_cast<uintptr_t>(code) & 3u)))
+        return BH_E_ALIGN;
+    if (ws_bytes < bh_stem_workspace_bytes(C)) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long n_pix = static_cast<long long>(N) * H * W;
+    const long long want = (n_pix + static_cast<long long>(g.PL) * kStemRun - 1) / (static_cast<long long>(g.PL) * kStemRun);
+    const int G = static_cast<int>(want < stem_reduce_grid() ? want : stem_reduce_grid());
+    double* partials = static_cast<double*>(ws);
+    bn_stats_kernel<<<G, kStemThreads, 0, s>>>(x, partials, n_pix, g.Q, g.lq);
+    int st = launch_status();
+    if (st != BH_OK) return st;
+    bn_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(n_pix), gamma, beta, running_mean,
+                                                            running_var, momentum, eps, stats);
+    st = launch_status();
+    if (st != BH_OK) return st;
+    const int strips = (g.Ho + kStemRows - 1) / kStemRows;
+    const long long items = static_cast<long long>(N) * strips * g.xblocks;
+    if (code) stem_pool_fwd_kernel<true><<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, y, code, H, W, g.Ho, g.Wo, g.Q, g.lq, strips, g.xblocks);
+    else stem_pool_fwd_kernel<false><<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, y, nullptr, H, W, g.Ho, g.Wo, g.Q, g.lq, strips, g.xblocks);
+    return launch_status();
+}
+
+extern "C" int bh_stem_bwd(const float* x, const float* stats, const uint8_t* code, const float* gy, float* gx, float* ggamma,
+                           float* gbeta, void* ws, size_t ws_bytes, int N, int H, int W, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!x || !stats || !code || !gy || !gx || !ws) return BH_E_NULL;
+    StemGeo g;
+    const int rc = stem_geo(N, H, W, C, g);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(x) || !aligned16(gy) || !aligned16(gx) || !aligned16(stats) || !aligned16(ws) || (reinterpret_cast<uintptr_t>(code) & 3u))
+        return BH_E_ALIGN;
+    if (ws_bytes < bh_stem_workspace_bytes(C)) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long items = static_cast<long long>(N) * g.Ho * g.xblocks;
+    const long long want = (items + 3) / 4;
+    const int G = static_cast<int>(want < stem_reduce_grid() ? want : stem_reduce_grid());
+    double* partials = static_cast<double*>(ws);
+    float* coef = reinterpret_cast<float*>(partials + stem_ws_doubles(C));
+    stem_bwd_reduce_kernel<<<G, kStemThreads, 0, s>>>(x, stats, gy, code, partials, N, H, W, g.Ho, g.Wo, g.Q, g.lq, g.xblocks);
+    int st = launch_status();
+    if (st != BH_OK) return st;
+    stem_bwd_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(N) * H * W, stats, coef, ggamma, gbeta);
+    st = launch_status();
+    if (st != BH_OK) return st;
+    stem_bwd_apply_kernel<<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, coef, gy, code, gx, H, W, g.Ho, g.Wo, g.Q, g.lq, g.xblocks);
+    return launch_status();
+}

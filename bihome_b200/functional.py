@@ -12,6 +12,7 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   pairgen_draw(...) / pairgen_apply(...)                   K5   HomographyNetPrep pipeline (src/data/transforms.py:456-576)
   mace(delta_gt, delta_hat)                                     train.py:401-404
   field_head(stage, x)                                     K6   Zeng backbone layer8       (src/backbones/Rethinking.py:144-147)
+  stem(bn, x)                                              K7   bn1 -> relu -> maxpool     (PerceptualHead.py:56-58, Rethinking.py:31-36)
 """
 import ctypes
 import os
@@ -687,3 +688,80 @@ def field_head(stage, x):
             bn.running_mean.mul_(1 - m).add_(mean_y.to(bn.running_mean.dtype), alpha=m)
             bn.running_var.mul_(1 - m).add_((var_y * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=m)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K7: ResNet stem, BatchNorm2d (batch statistics) -> ReLU -> MaxPool2d(3, 2, 1) as one channels-last stage
+# ------------------------------------------------------------------------------------------------
+def _stem_ws(C, device):
+    return torch.empty(int(cabi.lib().bh_stem_workspace_bytes(C)), device=device, dtype=torch.uint8)
+
+
+class _Stem(torch.autograd.Function):
+    """y = maxpool3x3/2(relu(batch_norm(x))) for channels-last x (csrc/stem.cu); the running statistics are updated in place"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps):
+        N, C, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, C, Ho, Wo), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        want_bwd = any(ctx.needs_input_grad[:3])
+        code = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.uint8) if want_bwd else None
+        stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
+        ws = _stem_ws(C, x.device)
+        with torch.cuda.device(x.device), _timed('bh_stem_fwd'):
+            cabi.check(cabi.lib().bh_stem_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(momentum),
+                                              float(eps), _ptr(y), _ptr(code), _ptr(stats), _ptr(ws), ws.numel(), N, H, W, C,
+                                              _stream()), 'bh_stem_fwd')
+        if want_bwd:
+            ctx.save_for_backward(x, stats, code)
+            ctx.affine = (gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, stats, code = ctx.saved_tensors
+        N, C, H, W = x.shape
+        if not _is_nhwc(gy) and not (C == 1 and gy.is_contiguous()):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(x)
+        has_g, has_b = ctx.affine
+        gg = torch.empty(C, device=x.device, dtype=torch.float32) if has_g and ctx.needs_input_grad[1] else None
+        gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_b and ctx.needs_input_grad[2] else None
+        ws = _stem_ws(C, x.device)
+        with torch.cuda.device(x.device), _timed('bh_stem_bwd'):
+            cabi.check(cabi.lib().bh_stem_bwd(_ptr(x), _ptr(stats), _ptr(code), _ptr(gy), _ptr(gx), _ptr(gg), _ptr(gb), _ptr(ws),
+                                              ws.numel(), N, H, W, C, _stream()), 'bh_stem_bwd')
+        return gx, gg, gb, None, None, None, None
+
+
+def stem_supported(bn, pool, x):
+    """can K7 stand in for ``pool(relu(bn(x)))``?  BatchNorm2d on batch statistics with a float momentum, MaxPool2d(3, 2, 1),
+    a channels-last float32 CUDA tensor whose channel count the library is compiled for.  BH_STEM=aten keeps the modules."""
+    if os.environ.get('BH_STEM', 'fused') == 'aten':
+        return False
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and _is_nhwc(x)):
+        return False
+    nn = torch.nn
+    if not (isinstance(bn, nn.BatchNorm2d) and isinstance(pool, nn.MaxPool2d)):
+        return False
+    if not (bn.training or bn.running_mean is None) or bn.momentum is None or bn.num_features != x.shape[1]:
+        return False
+    if bn.weight is not None and bn.weight.dtype != torch.float32:
+        return False
+    as2 = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+    if (as2(pool.kernel_size) != (3, 3) or as2(pool.stride) != (2, 2) or as2(pool.padding) != (1, 1) or as2(pool.dilation) != (1, 1)
+            or pool.ceil_mode or pool.return_indices):
+        return False
+    return bool(cabi.lib().bh_stem_supported(int(x.shape[1])))
+
+
+def stem(bn, x):
+    """``max_pool2d(relu(bn(x)), 3, 2, 1)`` in training mode: same output, same gradients (input, weight, bias), same
+    running-statistics update (incl. num_batches_tracked) as the three modules; call only when stem_supported() said yes"""
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.num_batches_tracked is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked.add_(1)
+    return _Stem.apply(x, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
+                       float(bn.momentum), float(bn.eps))

@@ -73,7 +73,9 @@ class AuxiliaryResnet(nn.Module):
             x = nn.functional.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation)
         else:
             x = r.conv1(x)
-        x = r.maxpool(r.relu(r.bn1(x)))
+        # bn1 -> relu -> maxpool (reference :56-58) as one stage (K7) on channels-last tensors; the extractor's BatchNorm runs
+        # on batch statistics like the reference's (the head never puts it in eval mode during training)
+        x = F.stem(r.bn1, x) if F.stem_supported(r.bn1, r.maxpool, x) else r.maxpool(r.relu(r.bn1(x)))
         x = r.layer1(x)
         if self.auxiliary_resnet_output_layer > 1:
             x = r.layer2(x)

@@ -226,6 +226,33 @@ int bh_fieldhead_affine(const float* x, const float* a, const float* M, float* g
                         int accumulate, bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7  ResNet stem: BatchNorm2d (batch statistics) -> ReLU -> MaxPool2d(3, stride 2, padding 1), channels-last, one stage
+ *
+ * replaces: src/heads/PerceptualHead.py:56-58  resnet.bn1 -> relu -> maxpool of the frozen extractor (AuxiliaryResnet, in
+ *             train mode: batch statistics, four passes per step) and
+ *           src/backbones/Rethinking.py:31-36,293  layer1's BatchNorm2d -> ReLU -> MaxPool2d (two passes per step):
+ *           six ATen / cuDNN passes over a [B,64,P/2,P/2] tensor forward (pooling keeps int64 indices), as many backward.
+ *
+ * x [N,H,W,C] channels-last (the convolution's output), y [N,Ho,Wo,C] with Ho = (H-1)/2 + 1, Wo = (W-1)/2 + 1;
+ * C a power of two, 4 <= C <= 1024 (bh_stem_supported).  gamma / beta [C] or NULL (affine = False).
+ *   bh_stem_fwd   batch mean / biased variance per channel (float64 reduction, fixed order), running_mean / running_var
+ *                 (NULL = not tracked) updated in place with `momentum` and the unbiased variance, then
+ *                 y = maxpool(relu(x * scale + shift)).  stats [4,C] out: scale = gamma / std, shift = beta - mean * scale,
+ *                 mean, 1/std (saved for the backward).  code [N,Ho,Wo,C] uint8 out or NULL (no backward wanted): window
+ *                 position 3 ky + kx of each maximum, first maximum in row-major order as ATen's max_pool2d.
+ *   bh_stem_bwd   gy [N,Ho,Wo,C] -> gx [N,H,W,C] (overwritten) through the pooling, the ReLU and BatchNorm's batch-statistics
+ *                 backward; ggamma / gbeta [C] (overwritten) or NULL.
+ * ws: bh_stem_workspace_bytes(C) bytes, 16-byte aligned, contents irrelevant between calls.
+ * ------------------------------------------------------------------------------------------- */
+int bh_stem_supported(int C);
+size_t bh_stem_workspace_bytes(int C);
+int bh_stem_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                float eps, float* y, uint8_t* code, float* stats, void* ws, size_t ws_bytes, int N, int H, int W, int C,
+                bh_stream_t stream);
+int bh_stem_bwd(const float* x, const float* stats, const uint8_t* code, const float* gy, float* gx, float* ggamma, float* gbeta,
+                void* ws, size_t ws_bytes, int N, int H, int W, int C, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MACE: mean over B*4 corners of ||delta_gt - delta_hat||_2  (train.py:401-404, eval.py:133-134)
  * out: 1 float (overwritten).
  * ------------------------------------------------------------------------------------------- */

@@ -1,0 +1,227 @@
+"""K7 (csrc/stem.cu) on the device: BatchNorm2d (batch statistics) -> ReLU -> MaxPool2d(3, 2, 1) as one channels-last stage
+against the three ATen modules it replaces (reference src/heads/PerceptualHead.py:56-58, src/backbones/Rethinking.py:31-36),
+evaluated in float64 on the same inputs: output, running statistics, num_batches_tracked, input / weight / bias gradients.
+
+ReLU and the pooling maximum are discontinuous in their gradients: an input whose pre-activation is within round-off of zero,
+or a window whose two largest values are within round-off of each other, may route its gradient differently in two correct
+float32 evaluations.  The exact-parity cases therefore build inputs on a lattice -- per channel a random permutation of
+equidistant levels, the bias chosen so that zero sits midway between two levels -- so that every decision has a margin of
+>= 1e-4 and the comparison can be element-wise; the north-star sized case uses Gaussian data and bounds the few knife-edge
+elements instead."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+TOL = 1e-5
+
+
+def _modules(C, affine=True, track=True, momentum=0.1, seed=0):
+    torch.manual_seed(seed)
+    bn = torch.nn.BatchNorm2d(C, affine=affine, track_running_stats=track, momentum=momentum)
+    if track:
+        with torch.no_grad():
+            bn.running_mean.normal_()
+            bn.running_var.uniform_(0.5, 2.0)
+    return bn, torch.nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+
+
+def _lattice_input(N, C, H, W, bn, seed):
+    """x [N,C,H,W] float32 whose channel c holds a random permutation of n = N*H*W equidistant levels (shifted and scaled per
+    channel); bn.weight random with both signs, bn.bias such that the ReLU threshold lies midway between two levels"""
+    rng = np.random.RandomState(seed)
+    n = N * H * W
+    x = np.empty((N, C, H, W), np.float32)
+    for c in range(C):
+        levels = ((np.arange(n) + 0.5) / n * 4.0 - 2.0) * rng.uniform(0.5, 3.0) + rng.uniform(-3.0, 3.0)
+        x[:, c] = rng.permutation(levels).reshape(N, H, W).astype(np.float32)
+    if bn.affine:
+        xd = x.astype(np.float64)
+        mean, var = xd.mean(axis=(0, 2, 3)), xd.var(axis=(0, 2, 3))
+        gamma = rng.uniform(0.5, 1.5, C) * rng.choice([-1.0, 1.0], C)
+        beta = np.empty(C)
+        for c in range(C):
+            lv = np.sort(xd[:, c].ravel())
+            j = rng.randint(n // 4, 3 * n // 4)
+            cross = 0.5 * (lv[j] + lv[j + 1])           # relu threshold between two levels
+            beta[c] = -(cross - mean[c]) / math.sqrt(var[c] + bn.eps) * gamma[c]
+        with torch.no_grad():
+            bn.weight.copy_(torch.from_numpy(gamma).float())
+            bn.bias.copy_(torch.from_numpy(beta).float())
+    return torch.from_numpy(x)
+
+
+def _reference(bn, pool, x, g):
+    """the three modules in float64 (on the tensor's device) -> y, gx, gweight, gbias, running_mean, running_var, tracked"""
+    import copy
+    bn64 = copy.deepcopy(bn).double()
+    bn64.train()
+    x64 = x.double().requires_grad_(True)
+    y = pool(torch.relu(bn64(x64)))
+    (y * g.double()).sum().backward()
+    return (y.detach(), x64.grad, bn64.weight.grad if bn64.affine else None, bn64.bias.grad if bn64.affine else None,
+            bn64.running_mean, bn64.running_var, bn64.num_batches_tracked)
+
+
+def _close(a, b, tol, what):
+    a, b = a.double(), b.double()
+    scale = float(b.abs().max().clamp_min(1e-30))
+    err = float((a - b).abs().max()) / scale
+    assert err <= tol, '%s: max error %.3e of the largest magnitude (%.3e)' % (what, err, scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,C,H,W', [(2, 8, 12, 12), (3, 64, 16, 20), (2, 16, 9, 7), (2, 4, 5, 6), (1, 128, 8, 8), (2, 256, 6, 6),
+                                     (1, 1024, 4, 6), (8, 64, 32, 32), (1, 32, 2, 3)])
+def test_stem_matches_the_modules(N, C, H, W):
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    bn, pool = _modules(C, seed=C + H)
+    x = _lattice_input(N, C, H, W, bn, seed=N * 1000 + W).to(dev).contiguous(memory_format=torch.channels_last)
+    bn = bn.to(dev).train()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    g = torch.randn(N, C, Ho, Wo, generator=torch.Generator().manual_seed(5)).to(dev)
+    ref = _reference(bn, pool, x, g)
+    if C == 1 or not F.stem_supported(bn, pool, x):
+        pytest.fail('K7 refuses a geometry it is documented for: %r' % ((N, C, H, W),))
+    xs = x.clone().requires_grad_(True)
+    y = F.stem(bn, xs)
+    assert y.shape == (N, C, Ho, Wo) and y.is_contiguous(memory_format=torch.channels_last)
+    (y * g).sum().backward()
+    _close(y.detach(), ref[0], TOL, 'output')
+    _close(bn.running_mean, ref[4], TOL, 'running_mean')
+    _close(bn.running_var, ref[5], TOL, 'running_var')
+    assert int(bn.num_batches_tracked) == int(ref[6])
+    _close(xs.grad, ref[1], 5 * TOL, 'input gradient')
+    _close(bn.weight.grad, ref[2], 5 * TOL, 'weight gradient')
+    _close(bn.bias.grad, ref[3], 5 * TOL, 'bias gradient')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('affine,track', [(False, True), (True, False), (False, False)])
+def test_stem_without_affine_or_running_statistics(affine, track):
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    N, C, H, W = 3, 16, 10, 14
+    bn, pool = _modules(C, affine=affine, track=track, momentum=0.3)
+    x = _lattice_input(N, C, H, W, bn, seed=11).to(dev).contiguous(memory_format=torch.channels_last)
+    if not affine:   # no bias to place the threshold: shift the data instead so that zero is not a level
+        x = x + 1e-3
+    bn = bn.to(dev).train()
+    g = torch.randn(N, C, 5, 7, generator=torch.Generator().manual_seed(6)).to(dev)
+    y64, gx64, gw64, gb64, rm64, rv64, _ = _reference(bn, pool, x, g)
+    assert F.stem_supported(bn, pool, x)
+    xs = x.clone().requires_grad_(True)
+    y = F.stem(bn, xs)
+    (y * g).sum().backward()
+    _close(y.detach(), y64, TOL, 'output')
+    _close(xs.grad, gx64, 5 * TOL, 'input gradient')
+    if track:
+        _close(bn.running_mean, rm64, TOL, 'running_mean')
+        _close(bn.running_var, rv64, TOL, 'running_var')
+    if affine:
+        _close(bn.weight.grad, gw64, 5 * TOL, 'weight gradient')
+        _close(bn.bias.grad, gb64, 5 * TOL, 'bias gradient')
+
+
+@pytest.mark.gpu
+def test_stem_frozen_and_no_grad_paths():
+    """the frozen extractor: parameters without gradient (input gradient only), and the no_grad passes (no codes kept)"""
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    N, C, H, W = 4, 64, 16, 16
+    bn, pool = _modules(C)
+    x = _lattice_input(N, C, H, W, bn, seed=3).to(dev).contiguous(memory_format=torch.channels_last)
+    bn = bn.to(dev).train()
+    for p in bn.parameters():
+        p.requires_grad = False
+    g = torch.randn(N, C, 8, 8, generator=torch.Generator().manual_seed(7)).to(dev)
+    y64, gx64 = _reference(bn, pool, x, g)[:2]
+    xs = x.clone().requires_grad_(True)
+    y = F.stem(bn, xs)
+    (y * g).sum().backward()
+    _close(y.detach(), y64, TOL, 'output')
+    _close(xs.grad, gx64, 5 * TOL, 'input gradient')
+    assert bn.weight.grad is None and bn.bias.grad is None
+    with torch.no_grad():
+        y2 = F.stem(bn, x)
+    _close(y2, y64, TOL, 'output under no_grad')
+    assert not y2.requires_grad
+
+
+@pytest.mark.gpu
+def test_stem_refuses_what_it_does_not_cover():
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    bn, pool = _modules(64)
+    bn = bn.to(dev)
+    x = torch.randn(2, 64, 8, 8, device=dev)
+    assert not F.stem_supported(bn, pool, x)                                            # NCHW
+    xl = x.contiguous(memory_format=torch.channels_last)
+    assert F.stem_supported(bn, pool, xl)
+    assert not F.stem_supported(bn.eval(), pool, xl)                                    # running statistics: ATen modules
+    bn.train()
+    assert not F.stem_supported(bn, torch.nn.MaxPool2d(2, 2), xl)
+    assert not F.stem_supported(bn, torch.nn.MaxPool2d(3, 2, 1, ceil_mode=True), xl)
+    bn48, _ = _modules(48)
+    assert not F.stem_supported(bn48.to(dev), pool, torch.randn(2, 48, 8, 8, device=dev).contiguous(memory_format=torch.channels_last))
+    bn_cma = torch.nn.BatchNorm2d(64, momentum=None).to(dev)
+    assert not F.stem_supported(bn_cma, pool, xl)                                       # cumulative average: ATen modules
+
+
+@pytest.mark.gpu
+def test_stem_north_star_size_and_speed():
+    """[256,64,64,64] (the stem of the B = 256 step): output and statistics element-wise; gradients with Gaussian data differ
+    from a float64 evaluation only at knife-edge decisions -- at most a handful of the 67 M elements -- and the stage beats the
+    three ATen modules it replaces (forward + backward) by a wide margin"""
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    N, C, H, W = 256, 64, 64, 64
+    bn, pool = _modules(C)
+    bn = bn.to(dev).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.3)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    x = (torch.randn(N, C, H, W, device=dev, generator=gen) * 1.7 + 0.4).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(N, C, 32, 32, device=dev, generator=gen).contiguous(memory_format=torch.channels_last)
+    import copy
+    bn_ref = copy.deepcopy(bn)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = F.stem(bn, xa)
+    (ya * g).sum().backward()
+    yb = pool(torch.relu(bn_ref(xb)))
+    (yb * g).sum().backward()
+    _close(ya.detach(), yb.detach(), 2e-5, 'output')
+    _close(bn.running_mean, bn_ref.running_mean, 1e-5, 'running_mean')
+    _close(bn.running_var, bn_ref.running_var, 1e-5, 'running_var')
+    scale = float(xb.grad.abs().max())
+    bad = int(((xa.grad - xb.grad).abs() > 1e-4 * scale).sum())
+    assert bad <= 2000, '%d of %d input-gradient elements differ' % (bad, xa.grad.numel())
+    werr = float((bn.weight.grad - bn_ref.weight.grad).abs().max() / bn_ref.weight.grad.abs().max())
+    berr = float((bn.bias.grad - bn_ref.bias.grad).abs().max() / bn_ref.bias.grad.abs().max())
+    assert werr < 2e-2 and berr < 2e-2, (werr, berr)      # ~1 knife-edge element per channel against a sum of ~500
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+
+    def run_fused():
+        xs = x.detach().requires_grad_(True)
+        (F.stem(bn, xs) * g).sum().backward()
+
+    def run_aten():
+        xs = x.detach().requires_grad_(True)
+        (pool(torch.relu(bn_ref(xs))) * g).sum().backward()
+    t_fused, t_aten = timed(run_fused), timed(run_aten)
+    print('K7 stem fwd+bwd at [256,64,64,64]: fused %.3f ms, ATen modules %.3f ms' % (t_fused, t_aten))
+    assert t_fused < 0.7 * t_aten, (t_fused, t_aten)
