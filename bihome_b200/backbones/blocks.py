@@ -9,6 +9,8 @@ import warnings
 import torch.nn as nn
 import torchvision.models as models
 
+from .. import functional as F
+
 
 def _conv(cin, cout, k, stride=1, bias=False):
     return nn.Conv2d(cin, cout, kernel_size=k, padding=k // 2, stride=stride, bias=bias)
@@ -41,7 +43,23 @@ class _Residual(nn.Module):
 
     def forward(self, x):
         skip = x if self.lower_is_identity else self.lower_branch(x)
-        return nn.functional.relu(self.upper_branch(x) + skip)
+        # the memory-bound stages between the convolutions run fused (K7b, csrc/stem.cu) on channels-last CUDA tensors in
+        # training: BatchNorm2d -> ReLU inside the branch, BatchNorm2d + skip -> ReLU at its end; anything else (eval mode,
+        # NCHW, CPU) takes the modules one by one
+        mods = list(self.upper_branch)
+        h, i, n = x, 0, len(mods)
+        while i < n:
+            m = mods[i]
+            if isinstance(m, nn.BatchNorm2d):
+                if i + 1 < n and isinstance(mods[i + 1], nn.ReLU) and F.bnact_supported(m, h):
+                    h = F.bn_relu(m, h)
+                    i += 2
+                    continue
+                if i == n - 1 and F.bnact_supported(m, h, skip):
+                    return F.bn_relu(m, h, residual=skip)
+            h = m(h)
+            i += 1
+        return nn.functional.relu(h + skip)
 
 
 class ResNet34ConvBlock(_Residual):

@@ -325,6 +325,127 @@ __global__ void __launch_bounds__(kStemThreads, 3) stem_bwd_apply_kernel(const f
     }
 }
 
+// =======================================================================================================================
+// K7b: BatchNorm2d (batch statistics) [+ residual] -> ReLU without pooling: the inner stages of the residual blocks
+// (reference src/backbones/utils.py, torchvision BasicBlock / Bottleneck of the extractor).  Same statistics kernels; the
+// element-wise passes see x as [n_pix, C] rows.
+//   forward   y = relu(x * scale + shift [+ r])
+//   backward  dy = gy where the ReLU was open: decided from y when there is a residual (y is the block's saved output),
+//             recomputed from x otherwise (no extra read).  With a residual the reduce pass also WRITES dy -- it is the
+//             residual's gradient -- and the apply pass reads that instead of gy and y.
+// =======================================================================================================================
+template <bool kRes>
+__global__ void __launch_bounds__(kStemThreads) bnact_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
+                                                                 const float* __restrict__ stats, float* __restrict__ y,
+                                                                 long long n_pix, int Q, int lq) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* r4 = reinterpret_cast<const float4*>(r);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    long long p = static_cast<long long>(blockIdx.x) * PL + pl;
+    for (; p + 3 * stride < n_pix; p += 4 * stride) {
+        float4 v[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream(x4 + (p + u * stride) * Q + q);
+        if (kRes) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = ldg_stream(r4 + (p + u * stride) * Q + q);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float4 o = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z), fmaf(v[u].w, sc.w, sh.w));
+            if (kRes) { o.x += w[u].x; o.y += w[u].y; o.z += w[u].z; o.w += w[u].w; }
+            o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
+            y4[(p + u * stride) * Q + q] = o;      // the next convolution reads it: leave it in L2
+        }
+    }
+    for (; p < n_pix; p += stride) {
+        const float4 v = ldg_stream(x4 + p * Q + q);
+        float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+        if (kRes) {
+            const float4 w = ldg_stream(r4 + p * Q + q);
+            o.x += w.x; o.y += w.y; o.z += w.z; o.w += w.w;
+        }
+        o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
+        y4[p * Q + q] = o;
+    }
+}
+
+// partials[cta][0][C] = sum dy, [cta][1][C] = sum dy * xhat; kRes: gr = dy written
+template <bool kRes>
+__global__ void __launch_bounds__(kStemThreads) bnact_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                        const float* __restrict__ stats, const float* __restrict__ gy,
+                                                                        float* __restrict__ gr, double* __restrict__ partials,
+                                                                        long long n_pix, int Q, int lq) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q), mu = ld4(stats + 2 * C + 4 * q), is = ld4(stats + 3 * C + 4 * q);
+    const float4 off = make_float4(-mu.x * is.x, -mu.y * is.y, -mu.z * is.z, -mu.w * is.w);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    float4* gr4 = reinterpret_cast<float4*>(gr);
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long p = static_cast<long long>(blockIdx.x) * PL + pl;
+    while (p < n_pix) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll 4
+        for (int u = 0; u < kStemRun; ++u) {
+            if (p < n_pix) {
+                const float4 xv = ldg_stream(x4 + p * Q + q);
+                float4 d = ldg_stream(g4 + p * Q + q);
+                if (kRes) {
+                    const float4 yv = ldg_stream(y4 + p * Q + q);
+                    d.x = yv.x > 0.0f ? d.x : 0.0f; d.y = yv.y > 0.0f ? d.y : 0.0f;
+                    d.z = yv.z > 0.0f ? d.z : 0.0f; d.w = yv.w > 0.0f ? d.w : 0.0f;
+                    gr4[p * Q + q] = d;
+                } else {
+                    d = gate4(d, xv, sc, sh);
+                }
+                a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+                b.x = fmaf(d.x, fmaf(xv.x, is.x, off.x), b.x); b.y = fmaf(d.y, fmaf(xv.y, is.y, off.y), b.y);
+                b.z = fmaf(d.z, fmaf(xv.z, is.z, off.z), b.z); b.w = fmaf(d.w, fmaf(xv.w, is.w, off.w), b.w);
+            }
+            p += stride;
+        }
+        s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+        s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+    }
+    stem_cta_partials(s, partials, Q, lq, C);
+}
+
+// gx = a dy + b x + c; kRes: dy is read back from gr (written by the reduce pass), else gy gated by the recomputed ReLU
+template <bool kRes>
+__global__ void __launch_bounds__(kStemThreads) bnact_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                                       const float* __restrict__ coef, const float* __restrict__ g,
+                                                                       float* __restrict__ gx, long long n_pix, int Q, int lq) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
+    const float4 ca = ld4(coef + 4 * q), cb = ld4(coef + C + 4 * q), cc = ld4(coef + 2 * C + 4 * q);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* o4 = reinterpret_cast<float4*>(gx);
+    long long p = static_cast<long long>(blockIdx.x) * PL + pl;
+    for (; p < n_pix; p += 2 * stride) {
+        const bool two = p + stride < n_pix;
+        const float4 x0 = ldg_stream(x4 + p * Q + q), g0 = ldg_stream(g4 + p * Q + q);
+        float4 x1 = x0, g1 = g0;
+        if (two) { x1 = ldg_stream(x4 + (p + stride) * Q + q); g1 = ldg_stream(g4 + (p + stride) * Q + q); }
+        const float4 d0 = kRes ? g0 : gate4(g0, x0, sc, sh), d1 = kRes ? g1 : gate4(g1, x1, sc, sh);
+        stg_stream(o4 + p * Q + q, make_float4(fmaf(ca.x, d0.x, fmaf(cb.x, x0.x, cc.x)), fmaf(ca.y, d0.y, fmaf(cb.y, x0.y, cc.y)),
+                                               fmaf(ca.z, d0.z, fmaf(cb.z, x0.z, cc.z)), fmaf(ca.w, d0.w, fmaf(cb.w, x0.w, cc.w))));
+        if (two)
+            stg_stream(o4 + (p + stride) * Q + q, make_float4(fmaf(ca.x, d1.x, fmaf(cb.x, x1.x, cc.x)), fmaf(ca.y, d1.y, fmaf(cb.y, x1.y, cc.y)),
+                                                              fmaf(ca.z, d1.z, fmaf(cb.z, x1.z, cc.z)), fmaf(ca.w, d1.w, fmaf(cb.w, x1.w, cc.w))));
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 struct StemGeo {
     int Q, lq, PL, Ho, Wo, xblocks;
@@ -411,5 +532,81 @@ extern "C" int bh_stem_bwd(const float* x, const float* stats, const uint8_t* co
     st = launch_status();
     if (st != BH_OK) return st;
     stem_bwd_apply_kernel<<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, coef, gy, code, gx, H, W, g.Ho, g.Wo, g.Q, g.lq, g.xblocks);
+    return launch_status();
+}
+
+// ---- K7b entry points ---------------------------------------------------------------------------------------------------
+namespace bh {
+inline int bnact_geo(long long n_pix, int C, int& Q, int& lq, int& PL) {
+    if (n_pix <= 0 || C < 4) return BH_E_SHAPE;
+    if (C % 4 != 0 || C > 4 * kStemThreads) return BH_E_UNSUPPORTED;
+    Q = C / 4;
+    if (Q & (Q - 1)) return BH_E_UNSUPPORTED;
+    lq = 0;
+    while ((1 << lq) < Q) ++lq;
+    PL = kStemThreads / Q;
+    return BH_OK;
+}
+inline int bnact_stream_grid(long long n_pix, int PL, int per_thread) {
+    const long long want = (n_pix + static_cast<long long>(PL) * per_thread - 1) / (static_cast<long long>(PL) * per_thread);
+    const long long cap = static_cast<long long>(kNumSMs) * 16;
+    return static_cast<int>(want < cap ? want : cap);
+}
+}  // namespace bh
+
+extern "C" int bh_bnact_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
+                            float* running_var, float momentum, float eps, float* y, float* stats, void* ws, size_t ws_bytes,
+                            long long n_pix, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!x || !y || !stats || !ws) return BH_E_NULL;
+    int Q, lq, PL;
+    const int rc = bnact_geo(n_pix, C, Q, lq, PL);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(x) || !aligned16(y) || !aligned16(stats) || !aligned16(ws) || (residual && !aligned16(residual))) return BH_E_ALIGN;
+    if (ws_bytes < bh_stem_workspace_bytes(C)) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long want = (n_pix + static_cast<long long>(PL) * kStemRun - 1) / (static_cast<long long>(PL) * kStemRun);
+    const int G = static_cast<int>(want < stem_reduce_grid() ? want : stem_reduce_grid());
+    double* partials = static_cast<double*>(ws);
+    bn_stats_kernel<<<G, kStemThreads, 0, s>>>(x, partials, n_pix, Q, lq);
+    int st = launch_status();
+    if (st != BH_OK) return st;
+    bn_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(n_pix), gamma, beta, running_mean,
+                                                            running_var, momentum, eps, stats);
+    st = launch_status();
+    if (st != BH_OK) return st;
+    const int grid = bnact_stream_grid(n_pix, PL, 4);
+    if (residual) bnact_fwd_kernel<true><<<grid, kStemThreads, 0, s>>>(x, residual, stats, y, n_pix, Q, lq);
+    else bnact_fwd_kernel<false><<<grid, kStemThreads, 0, s>>>(x, nullptr, stats, y, n_pix, Q, lq);
+    return launch_status();
+}
+
+extern "C" int bh_bnact_bwd(const float* x, const float* y, const float* stats, const float* gy, float* gx, float* gresidual,
+                            float* ggamma, float* gbeta, void* ws, size_t ws_bytes, long long n_pix, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!x || !stats || !gy || !gx || !ws) return BH_E_NULL;
+    if (gresidual && !y) return BH_E_NULL;      // with a residual the ReLU decision comes from the saved output
+    int Q, lq, PL;
+    const int rc = bnact_geo(n_pix, C, Q, lq, PL);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(x) || !aligned16(gy) || !aligned16(gx) || !aligned16(stats) || !aligned16(ws) || (y && !aligned16(y)) ||
+        (gresidual && !aligned16(gresidual)))
+        return BH_E_ALIGN;
+    if (ws_bytes < bh_stem_workspace_bytes(C)) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long want = (n_pix + static_cast<long long>(PL) * kStemRun - 1) / (static_cast<long long>(PL) * kStemRun);
+    const int G = static_cast<int>(want < stem_reduce_grid() ? want : stem_reduce_grid());
+    double* partials = static_cast<double*>(ws);
+    float* coef = reinterpret_cast<float*>(partials + stem_ws_doubles(C));
+    if (gresidual) bnact_bwd_reduce_kernel<true><<<G, kStemThreads, 0, s>>>(x, y, stats, gy, gresidual, partials, n_pix, Q, lq);
+    else bnact_bwd_reduce_kernel<false><<<G, kStemThreads, 0, s>>>(x, nullptr, stats, gy, nullptr, partials, n_pix, Q, lq);
+    int st = launch_status();
+    if (st != BH_OK) return st;
+    stem_bwd_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(n_pix), stats, coef, ggamma, gbeta);
+    st = launch_status();
+    if (st != BH_OK) return st;
+    const int grid = bnact_stream_grid(n_pix, PL, 4);
+    if (gresidual) bnact_bwd_apply_kernel<true><<<grid, kStemThreads, 0, s>>>(x, stats, coef, gresidual, gx, n_pix, Q, lq);
+    else bnact_bwd_apply_kernel<false><<<grid, kStemThreads, 0, s>>>(x, stats, coef, gy, gx, n_pix, Q, lq);
     return launch_status();
 }

@@ -13,6 +13,7 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   mace(delta_gt, delta_hat)                                     train.py:401-404
   field_head(stage, x)                                     K6   Zeng backbone layer8       (src/backbones/Rethinking.py:144-147)
   stem(bn, x)                                              K7   bn1 -> relu -> maxpool     (PerceptualHead.py:56-58, Rethinking.py:31-36)
+  bn_relu(bn, x, residual=None)                            K7b  bn -> [+ skip] -> relu     (src/backbones/utils.py, torchvision BasicBlock)
 """
 import ctypes
 import os
@@ -39,8 +40,18 @@ def enable_timing(on=True):
 def timings():
     torch.cuda.synchronize()
     out = {}
-    for name, e0, e1 in (_TIMING or []):
+    for name, e0, e1, _ in (_TIMING or []):
         out.setdefault(name, []).append(e0.elapsed_time(e1))
+    return out
+
+
+def timing_bytes():
+    """{entry point: algorithmic bytes summed over its timed calls} for the entry points whose traffic depends on the call's
+    shapes (K7b works on tensors of many sizes within one step); call before enable_timing(False)"""
+    out = {}
+    for name, _, _, nbytes in (_TIMING or []):
+        if nbytes:
+            out[name] = out.get(name, 0) + nbytes
     return out
 
 
@@ -50,8 +61,9 @@ _NVTX = os.environ.get('BH_NVTX', '0') == '1'
 
 
 class _timed:
-    def __init__(self, name):
+    def __init__(self, name, nbytes=0):
         self.name = name
+        self.nbytes = nbytes
 
     def __enter__(self):
         if _NVTX:
@@ -64,7 +76,7 @@ class _timed:
         if _TIMING is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _TIMING.append((self.name, self.e0, e1))
+            _TIMING.append((self.name, self.e0, e1, self.nbytes))
         if _NVTX:
             torch.cuda.nvtx.range_pop()
         return False
@@ -765,3 +777,83 @@ def stem(bn, x):
             bn.num_batches_tracked.add_(1)
     return _Stem.apply(x, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
                        float(bn.momentum), float(bn.eps))
+
+
+# ------------------------------------------------------------------------------------------------
+# K7b: BatchNorm2d (batch statistics) [+ residual] -> ReLU, the inner stages of the residual blocks
+# ------------------------------------------------------------------------------------------------
+class _BnAct(torch.autograd.Function):
+    """y = relu(batch_norm(x) [+ residual]) for channels-last tensors (csrc/stem.cu, K7b)"""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, momentum, eps):
+        N, C, H, W = x.shape
+        n_pix = N * H * W
+        y = torch.empty_like(x)
+        stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
+        ws = _stem_ws(C, x.device)
+        # compulsory traffic of the stage: x (+ residual) in, y out
+        with torch.cuda.device(x.device), _timed('bh_bnact_fwd', x.numel() * 4 * (2 if residual is None else 3)):
+            cabi.check(cabi.lib().bh_bnact_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                                               float(momentum), float(eps), _ptr(y), _ptr(stats), _ptr(ws), ws.numel(), n_pix, C,
+                                               _stream()), 'bh_bnact_fwd')
+        if any(ctx.needs_input_grad[:4]):
+            if residual is None:
+                ctx.save_for_backward(x, stats)
+            else:
+                ctx.save_for_backward(x, stats, y)
+            ctx.has_residual = residual is not None
+            ctx.affine = (gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        saved = ctx.saved_tensors
+        x, stats = saved[0], saved[1]
+        y = saved[2] if ctx.has_residual else None
+        N, C, H, W = x.shape
+        if gy.stride() != x.stride():
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(x)
+        gr = torch.empty_like(x) if ctx.has_residual else None
+        has_g, has_b = ctx.affine
+        gg = torch.empty(C, device=x.device, dtype=torch.float32) if has_g and ctx.needs_input_grad[2] else None
+        gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_b and ctx.needs_input_grad[3] else None
+        ws = _stem_ws(C, x.device)
+        # compulsory traffic: x, gy (+ y) in, gx (+ gresidual) out
+        with torch.cuda.device(x.device), _timed('bh_bnact_bwd', x.numel() * 4 * (5 if ctx.has_residual else 3)):
+            cabi.check(cabi.lib().bh_bnact_bwd(_ptr(x), _ptr(y), _ptr(stats), _ptr(gy), _ptr(gx), _ptr(gr), _ptr(gg), _ptr(gb), _ptr(ws),
+                                               ws.numel(), N * H * W, C, _stream()), 'bh_bnact_bwd')
+        return gx, (gr if ctx.needs_input_grad[1] else None), gg, gb, None, None, None, None
+
+
+def bnact_supported(bn, x, residual=None):
+    """can K7b stand in for ``relu(bn(x))`` / ``relu(bn(x) + residual)``?  BatchNorm2d on batch statistics with a float momentum,
+    channels-last float32 CUDA tensors, a channel count the library is compiled for.  BH_BNACT=aten keeps the modules."""
+    if os.environ.get('BH_BNACT', 'fused') == 'aten':
+        return False
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and _is_nhwc(x)):
+        return False
+    if not isinstance(bn, torch.nn.BatchNorm2d) or bn.momentum is None or bn.num_features != x.shape[1]:
+        return False
+    if not (bn.training or bn.running_mean is None):
+        return False
+    if bn.weight is not None and bn.weight.dtype != torch.float32:
+        return False
+    if residual is not None and not (torch.is_tensor(residual) and residual.shape == x.shape and residual.dtype == x.dtype
+                                     and residual.device == x.device):
+        return False
+    return bool(cabi.lib().bh_stem_supported(int(x.shape[1])))
+
+
+def bn_relu(bn, x, residual=None):
+    """``relu(bn(x))`` or ``relu(bn(x) + residual)`` in training mode: same output, gradients (x, residual, weight, bias) and
+    running-statistics update as the modules; call only when bnact_supported() said yes"""
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.num_batches_tracked is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked.add_(1)
+    if residual is not None and residual.stride() != x.stride():
+        residual = residual.contiguous(memory_format=torch.channels_last)
+    return _BnAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
+                        float(bn.momentum), float(bn.eps))

@@ -34,6 +34,34 @@ def _make_resnet(name, pretrained):
     return fn(weights=None)
 
 
+def _tv_block(blk, x):
+    """torchvision BasicBlock / Bottleneck forward (conv -> bn -> relu ... conv -> bn, += identity, relu) with the BatchNorm /
+    residual / ReLU stages fused (K7b) where the tensors allow it; same modules, same parameters, same statistics updates"""
+    identity = x if blk.downsample is None else blk.downsample(x)
+    if isinstance(blk, models.resnet.Bottleneck):
+        stages = [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)]
+    else:
+        stages = [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)]
+    h = x
+    for k, (conv, bn) in enumerate(stages):
+        h = conv(h)
+        if k + 1 < len(stages):
+            h = F.bn_relu(bn, h) if F.bnact_supported(bn, h) else nn.functional.relu(bn(h))
+        elif F.bnact_supported(bn, h, identity):
+            h = F.bn_relu(bn, h, residual=identity)
+        else:
+            h = nn.functional.relu(bn(h) + identity)
+    return h
+
+
+def _run_layer(layer, x):
+    if not isinstance(layer, nn.Sequential):
+        return layer(x)
+    for blk in layer:
+        x = _tv_block(blk, x) if isinstance(blk, (models.resnet.BasicBlock, models.resnet.Bottleneck)) else blk(x)
+    return x
+
+
 class AuxiliaryResnet(nn.Module):
     """Frozen torchvision ResNet stem + layer1..k used as the perceptual feature extractor (reference :15-76)."""
 
@@ -76,13 +104,13 @@ class AuxiliaryResnet(nn.Module):
         # bn1 -> relu -> maxpool (reference :56-58) as one stage (K7) on channels-last tensors; the extractor's BatchNorm runs
         # on batch statistics like the reference's (the head never puts it in eval mode during training)
         x = F.stem(r.bn1, x) if F.stem_supported(r.bn1, r.maxpool, x) else r.maxpool(r.relu(r.bn1(x)))
-        x = r.layer1(x)
+        x = _run_layer(r.layer1, x)
         if self.auxiliary_resnet_output_layer > 1:
-            x = r.layer2(x)
+            x = _run_layer(r.layer2, x)
         if self.auxiliary_resnet_output_layer > 2:
-            x = r.layer3(x)
+            x = _run_layer(r.layer3, x)
         if self.auxiliary_resnet_output_layer > 3:
-            x = r.layer4(x)
+            x = _run_layer(r.layer4, x)
         if self.with_projection_head is not None:
             x = x.permute(0, 2, 3, 1)
             for layer in self.projection_head:

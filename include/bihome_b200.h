@@ -253,6 +253,27 @@ int bh_stem_bwd(const float* x, const float* stats, const uint8_t* code, const f
                 void* ws, size_t ws_bytes, int N, int H, int W, int C, bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7b  BatchNorm2d (batch statistics) [+ residual] -> ReLU, channels-last: the inner stages of the residual blocks
+ *
+ * replaces: src/backbones/utils.py (ResNet34ConvBlock / IdentityBlock / ResNet50* blocks: BatchNorm2d -> ReLU inside the
+ *           upper branch, `relu(upper_branch(x) + lower_branch(x))` at the end) and torchvision's BasicBlock / Bottleneck of
+ *           the frozen extractor (src/heads/PerceptualHead.py:60-68): BatchNorm, the residual add and the ReLU as separate
+ *           ATen / cuDNN passes forward, threshold_backward + batch_norm_backward backward.
+ *
+ * x, residual (or NULL), y, gy, gx, gresidual: [n_pix, C] rows (= channels-last [N,C,H,W], n_pix = N*H*W); C as for K7.
+ *   bh_bnact_fwd   statistics / running statistics / stats [4,C] as bh_stem_fwd; y = relu(x * scale + shift [+ residual]).
+ *   bh_bnact_bwd   gresidual == NULL: the ReLU decision is recomputed from x (y may be NULL).  gresidual != NULL: y (the saved
+ *                  output) decides, gresidual = gy where y > 0 (overwritten) is the gradient of the residual input.
+ *                  gx (overwritten) through BatchNorm's batch-statistics backward; ggamma / gbeta [C] or NULL.
+ * ws: bh_stem_workspace_bytes(C) bytes.
+ * ------------------------------------------------------------------------------------------- */
+int bh_bnact_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, float momentum, float eps, float* y, float* stats, void* ws, size_t ws_bytes, long long n_pix,
+                 int C, bh_stream_t stream);
+int bh_bnact_bwd(const float* x, const float* y, const float* stats, const float* gy, float* gx, float* gresidual, float* ggamma,
+                 float* gbeta, void* ws, size_t ws_bytes, long long n_pix, int C, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MACE: mean over B*4 corners of ||delta_gt - delta_hat||_2  (train.py:401-404, eval.py:133-134)
  * out: 1 float (overwritten).
  * ------------------------------------------------------------------------------------------- */

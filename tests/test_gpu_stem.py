@@ -225,3 +225,131 @@ def test_stem_north_star_size_and_speed():
     t_fused, t_aten = timed(run_fused), timed(run_aten)
     print('K7 stem fwd+bwd at [256,64,64,64]: fused %.3f ms, ATen modules %.3f ms' % (t_fused, t_aten))
     assert t_fused < 0.7 * t_aten, (t_fused, t_aten)
+
+
+# ---- K7b: BatchNorm2d [+ residual] -> ReLU ------------------------------------------------------------------------------
+def _lattice_residual(x, bn, seed):
+    """r on the lattice of z = bn(x): integer multiples (-3 .. 3) of the per-channel level spacing of z, so that z + r keeps
+    the margin of half a level to the ReLU threshold"""
+    xd = x.double()
+    n = xd.numel() // xd.shape[1]
+    flat = xd.permute(1, 0, 2, 3).reshape(xd.shape[1], -1)
+    dx = (flat.max(1).values - flat.min(1).values) / (n - 1)
+    sigma = torch.sqrt(flat.var(1, unbiased=False) + bn.eps)
+    sz = bn.weight.detach().double().cpu().abs() * dx / sigma
+    k = torch.randint(-3, 4, x.shape, generator=torch.Generator().manual_seed(seed)).double()
+    return (k * sz.view(1, -1, 1, 1)).float()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('residual', [False, True])
+@pytest.mark.parametrize('N,C,H,W', [(2, 16, 8, 8), (3, 64, 16, 20), (2, 32, 9, 7), (1, 4, 5, 6), (1, 128, 8, 8), (2, 256, 6, 6),
+                                     (1, 1024, 3, 2), (4, 64, 32, 32), (2, 16, 40, 24)])
+def test_bn_relu_matches_the_modules(N, C, H, W, residual):
+    import copy
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    bn, _ = _modules(C, seed=C + W)
+    x = _lattice_input(N, C, H, W, bn, seed=N * 100 + H)
+    r = _lattice_residual(x, bn, seed=9) if residual else None
+    x = x.to(dev).contiguous(memory_format=torch.channels_last)
+    bn = bn.to(dev).train()
+    g = torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+    bn64 = copy.deepcopy(bn).double()
+    x64 = x.double().requires_grad_(True)
+    r64 = r.to(dev).double().requires_grad_(True) if residual else None
+    y64 = torch.relu(bn64(x64) + r64) if residual else torch.relu(bn64(x64))
+    (y64 * g.double()).sum().backward()
+    rs = r.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True) if residual else None
+    assert F.bnact_supported(bn, x, rs)
+    xs = x.clone().requires_grad_(True)
+    y = F.bn_relu(bn, xs, residual=rs)
+    assert y.shape == x.shape and y.stride() == x.stride()
+    (y * g).sum().backward()
+    _close(y.detach(), y64.detach(), TOL, 'output')
+    _close(bn.running_mean, bn64.running_mean, TOL, 'running_mean')
+    _close(bn.running_var, bn64.running_var, TOL, 'running_var')
+    assert int(bn.num_batches_tracked) == int(bn64.num_batches_tracked)
+    _close(xs.grad, x64.grad, 5 * TOL, 'input gradient')
+    _close(bn.weight.grad, bn64.weight.grad, 5 * TOL, 'weight gradient')
+    _close(bn.bias.grad, bn64.bias.grad, 5 * TOL, 'bias gradient')
+    if residual:
+        _close(rs.grad, r64.grad, TOL, 'residual gradient')
+
+
+@pytest.mark.gpu
+def test_residual_blocks_fused_vs_modules():
+    """the backbone's residual blocks and the extractor's torchvision blocks with K7b on and off (BH_BNACT=aten): same output,
+    same parameter gradients, same running statistics -- up to float32 round-off through two convolutions"""
+    import copy
+    import os
+    import torchvision
+    from bihome_b200.backbones import blocks
+    from bihome_b200.heads.PerceptualHead import _run_layer
+    dev = torch.device('cuda', 0)
+    saved = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(3)
+        cases = [(blocks.ResNet34IdentityBlock(64), (4, 64, 16, 16)), (blocks.ResNet34ConvBlock(64, 128, 2), (4, 64, 16, 16)),
+                 (blocks.ResNet50DeconvBlock(32), (2, 32, 12, 12)), (torchvision.models.resnet34(weights=None).layer1, (4, 64, 16, 16))]
+        for mod, shape in cases:
+            fused = mod.to(dev).to(memory_format=torch.channels_last).train()
+            plain = copy.deepcopy(fused)
+            x = torch.randn(*shape, device=dev).contiguous(memory_format=torch.channels_last)
+            run = (lambda m, t: _run_layer(m, t)) if isinstance(mod, torch.nn.Sequential) else (lambda m, t: m(t))
+            xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ya = run(fused, xa)
+            os.environ['BH_BNACT'] = 'aten'
+            try:
+                yb = run(plain, xb)
+            finally:
+                del os.environ['BH_BNACT']
+            g = torch.randn_like(yb)
+            (ya * g).sum().backward()
+            (yb * g).sum().backward()
+            from conftest import rel_l2
+            assert rel_l2(ya.detach().cpu(), yb.detach().cpu()) < 1e-5
+            assert rel_l2(xa.grad.cpu(), xb.grad.cpu()) < 1e-3          # a ReLU within round-off of zero may switch
+            for (na, pa), (nb, pb) in zip(fused.named_parameters(), plain.named_parameters()):
+                assert rel_l2(pa.grad.cpu(), pb.grad.cpu()) < 2e-3, na
+            for (na, ba), (nb, bb) in zip(fused.named_buffers(), plain.named_buffers()):
+                assert rel_l2(ba.double().cpu(), bb.double().cpu()) < 1e-5, na
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+
+
+@pytest.mark.gpu
+def test_bn_relu_speed_at_backbone_shapes():
+    """forward + backward of relu(bn(x)) and relu(bn(x) + r) against the ATen modules at three shapes of the B = 256 step"""
+    import copy
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+    for shape in ((256, 64, 32, 32), (256, 128, 16, 16), (256, 32, 128, 128)):
+        bn = torch.nn.BatchNorm2d(shape[1]).to(dev).train()
+        ref = copy.deepcopy(bn)
+        x = torch.randn(*shape, device=dev).contiguous(memory_format=torch.channels_last)
+        r = torch.randn(*shape, device=dev).contiguous(memory_format=torch.channels_last)
+        g = torch.randn(*shape, device=dev).contiguous(memory_format=torch.channels_last)
+        for res in (False, True):
+            def fused():
+                xs, rs = x.detach().requires_grad_(True), r.detach().requires_grad_(True)
+                (F.bn_relu(bn, xs, residual=rs if res else None) * g).sum().backward()
+
+            def aten():
+                xs, rs = x.detach().requires_grad_(True), r.detach().requires_grad_(True)
+                (torch.relu(ref(xs) + rs if res else ref(xs)) * g).sum().backward()
+            tf, ta = timed(fused), timed(aten)
+            print('K7b %s residual=%s: fused %.3f ms, ATen %.3f ms' % (shape, res, tf, ta))
