@@ -185,13 +185,14 @@ def run_ours(args):
     if args.channels_last:
         model = model.to(memory_format=torch.channels_last)
     model.train()
+    use_graph = not args.eager
     net = model
-    if world > 1:
+    if world > 1 and not use_graph:
         net = engine.data_parallel(model, local)
     opt, sched = engine.build_optimizer(cfg, model)
     t = gpu_pairs.transform_args(cfg['DATA']['TRANSFORMS'])
     pool = gpu_pairs.synthetic_pool(args.pool, device=dev)
-    loader = gpu_pairs.GpuPairLoader(pool, B, B * (args.steps + args.warmup + 8) * 4, seed=cfg['DATA']['SAMPLER']['TRAIN_SEED'],
+    loader = gpu_pairs.GpuPairLoader(pool, B, B * (3 * args.steps + args.warmup + 16) * 4, seed=cfg['DATA']['SAMPLER']['TRAIN_SEED'],
                                      rank=rank, **t)
 
     def barrier():
@@ -207,26 +208,34 @@ def run_ours(args):
         dist.all_reduce(x, op=dist.ReduceOp.MAX)
         return float(x.item())
 
+    # The step, through the repo's public API.  Default: forward + backward replayed from ONE CUDA graph per rank
+    # (engine.GraphedStep = `train.py --cuda_graph`), K5 pair generation, the data-parallel gradient mean (one NCCL all-reduce of
+    # the flat gradient buffer) and Adam eager.  --eager: engine.train_step, DDP's bucketed all-reduce at N > 1.
+    graphed = engine.GraphedStep(model, loader.next_batch()) if use_graph else None
+
+    def one_step(batch):
+        if graphed is not None:
+            return engine.graphed_train_step(graphed, batch, opt, sched)
+        return engine.train_step(net, batch, opt, sched)
+
     # ---------------- device-resident throughput: `value` ----------------
     for _ in range(args.warmup):
-        engine.train_step(net, loader.next_batch(), opt, sched)
+        one_step(loader.next_batch())
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    F.enable_timing(True)
     launches0 = cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss, _, _ = engine.train_step(net, loader.next_batch(), opt, sched)
+        loss, _, _ = one_step(loader.next_batch())
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = cabi.launch_count() - launches0
-    kt = F.timings()
-    kbytes = F.timing_bytes()
-    F.enable_timing(False)
+    # kernels of this library launched inside the timed region: the eager ones (K5) are counted as they launch, the ones inside
+    # the graph were counted once, at capture
+    launches = cabi.launch_count() - launches0 + (graphed.launches_per_replay * args.steps if graphed is not None else 0)
     clk = clocks.stop() if rank == 0 else None
     value = B * world * args.steps / (ms * 1e-3)
     final_loss = float(loss.item())
@@ -236,14 +245,17 @@ def run_ours(args):
     for _ in range(0 if args.no_e2e else 4):
         b = loader.next_batch()
         host.append({k: v.cpu().pin_memory() for k, v in b.items()})
-    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()} if host else {}
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()} if host and graphed is None else {}
     h2d = sum(v.numel() * v.element_size() for v in host[0].values()) if host else 0
 
     def e2e_step(i):
         hb = host[i % len(host)]
-        for k in stage:
-            stage[k].copy_(hb[k], non_blocking=True)
-        l, _, _ = engine.train_step(net, dict(stage), opt, sched)
+        if graphed is not None:
+            l, _, _ = one_step(hb)          # GraphedStep copies the pinned host batch straight into its static device buffers
+        else:
+            for k in stage:
+                stage[k].copy_(hb[k], non_blocking=True)
+            l, _, _ = one_step(dict(stage))
         return float(l.item())          # device -> host read of the step's loss
     ms_e2e, e2e_value = None, None
     if host:
@@ -257,6 +269,26 @@ def run_ours(args):
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+
+    # ---------------- per-kernel in-situ durations: the same K steps, eager, a CUDA-event pair around every C-ABI call ----------
+    # (on the launching stream).  Kept out of the regions `value` / `e2e` are timed over: ~250 bracketed calls per step slow the
+    # host's launch rate (ms_per_step_instrumented says by how much), and events cannot be recorded inside a graph replay.
+    def eager_step(batch):
+        opt.zero_grad(set_to_none=graphed is None)       # a GraphedStep owns the gradient buffers
+        l, _, _ = net(batch)
+        l.backward()
+        opt.step()
+    F.enable_timing(True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eager_step(loader.next_batch())
+    e1.record()
+    barrier()
+    ms_instr = e0.elapsed_time(e1)
+    kt = F.timings()
+    kbytes = F.timing_bytes()
+    F.enable_timing(False)
 
     if rank != 0:
         if world > 1:
@@ -325,7 +357,8 @@ def run_ours(args):
                                   '`--impl reference` runs in full): torch CPU backbone + oracle kornia-0.5.0 head' % spp}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'ms_per_step': ms / args.steps, 'ms_per_step_instrumented': ms_instr / args.steps, 'cuda_graph': graphed is not None,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': workload_config(B, world, args.pool),
             'layout': {'channels_last': bool(args.channels_last), 'cudnn_benchmark': bool(args.cudnn_benchmark), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten',
@@ -362,6 +395,9 @@ def main():
                     help='leave torch.backends.cudnn.benchmark off (default on, as train.py: the shapes of a training run are '
                          'fixed, cuDNN times its convolution algorithms once per shape during the warm-up: 72.2 -> 69.6 ms/step)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true',
+                    help='engine.train_step (DDP at N > 1) instead of the default: forward + backward replayed from one CUDA graph per '
+                         'rank (engine.GraphedStep, train.py --cuda_graph)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer phase (profiling runs)')
     ap.add_argument('--loss-traffic', type=float, default=None, help='dram bytes per launch of the loss kernel from ncu (profiles/)')
     args = ap.parse_args()

@@ -31,8 +31,26 @@ constexpr int kStemRun = 16;        // pixels a thread accumulates in float32 be
 constexpr int kStemRows = 8;        // pooled rows one forward work item walks
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// a kernel launched as a programmatic dependent (host side of the same mechanism)
+template <typename... KArgs, typename... Args>
+inline int launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    return launch_status();
+}
 
-// ---- per-CTA partial sums -> partials[cta][stat][C] (float64), fixed order ------------------------------------------
+// ---- per-CTA partial sums -> partials[stat][C][cta] (float64), fixed order ------------------------------------------
 // every thread holds 8 float64 sums (two statistics x its channel quad); pixel lanes are added in lane order
 __device__ __forceinline__ void stem_cta_partials(const double (&s)[8], double* __restrict__ partials, int Q, int lq, int C) {
     __shared__ double red[8 * kStemThreads];
@@ -44,12 +62,13 @@ __device__ __forceinline__ void stem_cta_partials(const double (&s)[8], double* 
         const int k = o >> lq, qq = o & (Q - 1);
         double sum = 0.0;
         for (int p = 0; p < PL; ++p) sum += red[(k * PL + p) * Q + qq];
-        partials[(static_cast<size_t>(blockIdx.x) * 2 + (k >> 2)) * C + qq * 4 + (k & 3)] = sum;
+        partials[(static_cast<size_t>(k >> 2) * C + qq * 4 + (k & 3)) * gridDim.x + blockIdx.x] = sum;
     }
 }
 
 __global__ void __launch_bounds__(kStemThreads) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ partials,
                                                                 long long n_pix, int Q, int lq) {
+    pdl_launch_dependents();
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
     const long long stride = static_cast<long long>(gridDim.x) * PL;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -72,13 +91,20 @@ __global__ void __launch_bounds__(kStemThreads) bn_stats_kernel(const float* __r
     stem_cta_partials(s, partials, Q, lq, Q * 4);
 }
 
-// one warp per channel: lanes stride over the CTAs' partials, shuffle tree (fixed order => bit reproducible)
+// one warp per channel: lanes stride over the CTAs' partials, shuffle tree (fixed order => bit reproducible).
+// The three kernels of a stage are chained by programmatic dependent launches: a dependent grid is scheduled while its
+// predecessor still runs and blocks in griddepcontrol.wait until that grid has completed and its writes are visible -- the
+// launch latency of the two small follow-up kernels (measured: 17-19 us for a finalize kernel launched the plain way, more
+// than the 16 us statistics pass of a 67 MB tensor) disappears behind the predecessor.
 __device__ __forceinline__ void stem_sum_partials(const double* __restrict__ partials, int G, int C, int c, double& s0, double& s1) {
     const int lane = threadIdx.x & 31;
     s0 = 0.0; s1 = 0.0;
-    for (int g = lane; g < G; g += 32) {
-        s0 += partials[(static_cast<size_t>(g) * 2 + 0) * C + c];
-        s1 += partials[(static_cast<size_t>(g) * 2 + 1) * C + c];
+    const double* p0 = partials + static_cast<size_t>(c) * G;
+    const double* p1 = partials + (static_cast<size_t>(C) + c) * G;
+#pragma unroll 4
+    for (int g = lane; g < G; g += 32) {      // consecutive lanes, consecutive CTAs: 256-byte rows
+        s0 += p0[g];
+        s1 += p1[g];
     }
     s0 = warp_sum(s0);
     s1 = warp_sum(s1);
@@ -89,6 +115,8 @@ __global__ void __launch_bounds__(kStemThreads) bn_finalize_kernel(const double*
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                                                    float momentum, float eps, float* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();   // the statistics grid has completed
     const int c = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5);
     if (c >= C) return;
     double s, ss;
@@ -161,6 +189,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_pool_fwd_kernel(const float
     const int strip = item % strips, n = item / strips;
     const int ox = xb * PL + pl;
     if (ox >= Wo) return;
+    pdl_wait();   // scale / shift come from the finalize kernel this grid was launched behind
     const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
     const float* xn = x + static_cast<size_t>(n) * H * W * C;
     const int oy0 = strip * kStemRows, oy1 = min(oy0 + kStemRows, Ho);
@@ -245,6 +274,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_reduce_kernel(const 
                                                                        const float* __restrict__ gy, const uint8_t* __restrict__ code,
                                                                        double* __restrict__ partials, int N, int H, int W, int Ho,
                                                                        int Wo, int Q, int lq, int xblocks) {
+    pdl_launch_dependents();
     const int C = Q * 4;
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
     const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q), mu = ld4(stats + 2 * C + 4 * q), is = ld4(stats + 3 * C + 4 * q);
@@ -283,6 +313,8 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_bwd_reduce_kernel(const 
 __global__ void __launch_bounds__(kStemThreads) stem_bwd_finalize_kernel(const double* __restrict__ partials, int G, int C, double n,
                                                                          const float* __restrict__ stats, float* __restrict__ coef,
                                                                          float* __restrict__ ggamma, float* __restrict__ gbeta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5);
     if (c >= C) return;
     double s1, s2;
@@ -309,6 +341,7 @@ __global__ void __launch_bounds__(kStemThreads, 3) stem_bwd_apply_kernel(const f
     const int k = item % Ho, n = item / Ho;
     const int m = xb * PL + pl;
     if (m >= Wo) return;
+    pdl_wait();
     const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
     const float4 ca = ld4(coef + 4 * q), cb = ld4(coef + C + 4 * q), cc = ld4(coef + 2 * C + 4 * q);
     StemBlock blk;
@@ -340,6 +373,7 @@ __global__ void __launch_bounds__(kStemThreads) bnact_fwd_kernel(const float* __
                                                                  long long n_pix, int Q, int lq) {
     const int C = Q * 4;
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    pdl_wait();
     const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
     const long long stride = static_cast<long long>(gridDim.x) * PL;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -380,6 +414,7 @@ __global__ void __launch_bounds__(kStemThreads) bnact_bwd_reduce_kernel(const fl
                                                                         const float* __restrict__ stats, const float* __restrict__ gy,
                                                                         float* __restrict__ gr, double* __restrict__ partials,
                                                                         long long n_pix, int Q, int lq) {
+    pdl_launch_dependents();
     const int C = Q * 4;
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
     const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q), mu = ld4(stats + 2 * C + 4 * q), is = ld4(stats + 3 * C + 4 * q);
@@ -425,6 +460,7 @@ __global__ void __launch_bounds__(kStemThreads) bnact_bwd_apply_kernel(const flo
                                                                        float* __restrict__ gx, long long n_pix, int Q, int lq) {
     const int C = Q * 4;
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    pdl_wait();
     const float4 sc = ld4(stats + 4 * q), sh = ld4(stats + C + 4 * q);
     const float4 ca = ld4(coef + 4 * q), cb = ld4(coef + C + 4 * q), cc = ld4(coef + 2 * C + 4 * q);
     const long long stride = static_cast<long long>(gridDim.x) * PL;
@@ -464,7 +500,7 @@ inline int stem_geo(int N, int H, int W, int C, StemGeo& g) {
     if (static_cast<long long>(N) * g.Ho * g.xblocks > 0x7fffffffll) return BH_E_SHAPE;
     return BH_OK;
 }
-inline int stem_reduce_grid() { return kNumSMs * 8; }
+inline int stem_reduce_grid() { return kNumSMs * 4; }   // one wave: every CTA resident when its dependents are scheduled
 inline size_t stem_ws_doubles(int C) { return static_cast<size_t>(stem_reduce_grid()) * 2 * C; }
 
 }  // namespace bh
@@ -498,15 +534,14 @@ extern "C" int bh_stem_fwd(const float* x, const float* gamma, const float* beta
     bn_stats_kernel<<<G, kStemThreads, 0, s>>>(x, partials, n_pix, g.Q, g.lq);
     int st = launch_status();
     if (st != BH_OK) return st;
-    bn_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(n_pix), gamma, beta, running_mean,
-                                                            running_var, momentum, eps, stats);
-    st = launch_status();
+    st = launch_dependent(bn_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, partials, G, C, static_cast<double>(n_pix), gamma,
+                          beta, running_mean, running_var, momentum, eps, stats);
     if (st != BH_OK) return st;
     const int strips = (g.Ho + kStemRows - 1) / kStemRows;
     const long long items = static_cast<long long>(N) * strips * g.xblocks;
-    if (code) stem_pool_fwd_kernel<true><<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, y, code, H, W, g.Ho, g.Wo, g.Q, g.lq, strips, g.xblocks);
-    else stem_pool_fwd_kernel<false><<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, y, nullptr, H, W, g.Ho, g.Wo, g.Q, g.lq, strips, g.xblocks);
-    return launch_status();
+    const dim3 grid(static_cast<unsigned>(items)), block(kStemThreads);
+    if (code) return launch_dependent(stem_pool_fwd_kernel<true>, grid, block, s, x, stats, y, code, H, W, g.Ho, g.Wo, g.Q, g.lq, strips, g.xblocks);
+    return launch_dependent(stem_pool_fwd_kernel<false>, grid, block, s, x, stats, y, code, H, W, g.Ho, g.Wo, g.Q, g.lq, strips, g.xblocks);
 }
 
 extern "C" int bh_stem_bwd(const float* x, const float* stats, const uint8_t* code, const float* gy, float* gx, float* ggamma,
@@ -528,11 +563,11 @@ extern "C" int bh_stem_bwd(const float* x, const float* stats, const uint8_t* co
     stem_bwd_reduce_kernel<<<G, kStemThreads, 0, s>>>(x, stats, gy, code, partials, N, H, W, g.Ho, g.Wo, g.Q, g.lq, g.xblocks);
     int st = launch_status();
     if (st != BH_OK) return st;
-    stem_bwd_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(N) * H * W, stats, coef, ggamma, gbeta);
-    st = launch_status();
+    st = launch_dependent(stem_bwd_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, partials, G, C, static_cast<double>(N) * H * W,
+                          stats, coef, ggamma, gbeta);
     if (st != BH_OK) return st;
-    stem_bwd_apply_kernel<<<static_cast<unsigned>(items), kStemThreads, 0, s>>>(x, stats, coef, gy, code, gx, H, W, g.Ho, g.Wo, g.Q, g.lq, g.xblocks);
-    return launch_status();
+    return launch_dependent(stem_bwd_apply_kernel, dim3(static_cast<unsigned>(items)), dim3(kStemThreads), s, x, stats, coef, gy, code, gx, H, W,
+                            g.Ho, g.Wo, g.Q, g.lq, g.xblocks);
 }
 
 // ---- K7b entry points ---------------------------------------------------------------------------------------------------
@@ -571,14 +606,12 @@ extern "C" int bh_bnact_fwd(const float* x, const float* residual, const float* 
     bn_stats_kernel<<<G, kStemThreads, 0, s>>>(x, partials, n_pix, Q, lq);
     int st = launch_status();
     if (st != BH_OK) return st;
-    bn_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(n_pix), gamma, beta, running_mean,
-                                                            running_var, momentum, eps, stats);
-    st = launch_status();
+    st = launch_dependent(bn_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, partials, G, C, static_cast<double>(n_pix), gamma,
+                          beta, running_mean, running_var, momentum, eps, stats);
     if (st != BH_OK) return st;
-    const int grid = bnact_stream_grid(n_pix, PL, 4);
-    if (residual) bnact_fwd_kernel<true><<<grid, kStemThreads, 0, s>>>(x, residual, stats, y, n_pix, Q, lq);
-    else bnact_fwd_kernel<false><<<grid, kStemThreads, 0, s>>>(x, nullptr, stats, y, n_pix, Q, lq);
-    return launch_status();
+    const dim3 grid(bnact_stream_grid(n_pix, PL, 4)), block(kStemThreads);
+    if (residual) return launch_dependent(bnact_fwd_kernel<true>, grid, block, s, x, residual, stats, y, n_pix, Q, lq);
+    return launch_dependent(bnact_fwd_kernel<false>, grid, block, s, x, residual, stats, y, n_pix, Q, lq);
 }
 
 extern "C" int bh_bnact_bwd(const float* x, const float* y, const float* stats, const float* gy, float* gx, float* gresidual,
@@ -602,11 +635,10 @@ extern "C" int bh_bnact_bwd(const float* x, const float* y, const float* stats, 
     else bnact_bwd_reduce_kernel<false><<<G, kStemThreads, 0, s>>>(x, nullptr, stats, gy, nullptr, partials, n_pix, Q, lq);
     int st = launch_status();
     if (st != BH_OK) return st;
-    stem_bwd_finalize_kernel<<<(C + 7) / 8, kStemThreads, 0, s>>>(partials, G, C, static_cast<double>(n_pix), stats, coef, ggamma, gbeta);
-    st = launch_status();
+    st = launch_dependent(stem_bwd_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, partials, G, C, static_cast<double>(n_pix), stats,
+                          coef, ggamma, gbeta);
     if (st != BH_OK) return st;
-    const int grid = bnact_stream_grid(n_pix, PL, 4);
-    if (gresidual) bnact_bwd_apply_kernel<true><<<grid, kStemThreads, 0, s>>>(x, stats, coef, gresidual, gx, n_pix, Q, lq);
-    else bnact_bwd_apply_kernel<false><<<grid, kStemThreads, 0, s>>>(x, stats, coef, gy, gx, n_pix, Q, lq);
-    return launch_status();
+    const dim3 grid(bnact_stream_grid(n_pix, PL, 4)), block(kStemThreads);
+    if (gresidual) return launch_dependent(bnact_bwd_apply_kernel<true>, grid, block, s, x, stats, coef, gresidual, gx, n_pix, Q, lq);
+    return launch_dependent(bnact_bwd_apply_kernel<false>, grid, block, s, x, stats, coef, gy, gx, n_pix, Q, lq);
 }

@@ -23,8 +23,33 @@ import torch
 from . import cabi
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (the raw query: a tenth of the cost of building a
+    torch.cuda.Stream object, and these wrappers run ~250 times per training step)"""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(device):
+    """context that makes `device` current -- nothing at all when it already is (the usual case: one process per GPU)"""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
 
 
 # In-situ kernel timing for bench.py: when enabled, every C-ABI launch is bracketed by CUDA events recorded on the
@@ -124,7 +149,7 @@ class _Dlt4(torch.autograd.Function):
             corners = corners.contiguous()
         B = delta.shape[0]
         H = torch.empty(B, 3, 3, device=delta.device, dtype=torch.float32)
-        with torch.cuda.device(delta.device), _timed('bh_dlt4_fwd'):
+        with _on(delta.device), _timed('bh_dlt4_fwd'):
             cabi.check(cabi.lib().bh_dlt4_fwd(_ptr(corners), _ptr(delta), _ptr(H), B, float(W), float(Hh), _stream()),
                        'bh_dlt4_fwd')
         ctx.save_for_backward(delta, corners, H)
@@ -139,7 +164,7 @@ class _Dlt4(torch.autograd.Function):
         g_delta = torch.empty_like(delta)
         want_c = corners is not None and ctx.needs_input_grad[1]
         g_corners = torch.empty_like(corners) if want_c else None
-        with torch.cuda.device(delta.device), _timed('bh_dlt4_bwd'):
+        with _on(delta.device), _timed('bh_dlt4_bwd'):
             cabi.check(cabi.lib().bh_dlt4_bwd(_ptr(corners), _ptr(delta), _ptr(H), _ptr(gH), _ptr(g_delta), _ptr(g_corners),
                                               B, ctx.size[0], ctx.size[1], _stream()), 'bh_dlt4_bwd')
         return g_delta, g_corners, None, None
@@ -185,7 +210,7 @@ class _Warp(torch.autograd.Function):
             Hs, Ws = src_hw
         if pool:
             mask = torch.empty((B, out_h // pool, out_w // pool), device=Hc.device, dtype=torch.float32)
-        with torch.cuda.device(Hc.device), _timed('bh_warp_fwd'):
+        with _on(Hc.device), _timed('bh_warp_fwd'):
             cabi.check(lib.bh_warp_fwd(_ptr(src), _ptr(Hc), _ptr(out), _ptr(mask), B, C, Hs, Ws, out_h, out_w,
                                        int(pool or 0), nhwc, _stream()), 'bh_warp_fwd')
         ctx.save_for_backward(src, Hc)
@@ -219,7 +244,7 @@ class _Warp(torch.autograd.Function):
             g_src = torch.zeros_like(src)
         nbytes = lib.bh_warp_bwd_workspace_bytes(B, C, Hs, Ws, Ho, Wo, nhwc)
         ws = torch.empty(max(int(nbytes), 16), device=Hc.device, dtype=torch.uint8)
-        with torch.cuda.device(Hc.device), _timed('bh_warp_bwd'):
+        with _on(Hc.device), _timed('bh_warp_bwd'):
             cabi.check(lib.bh_warp_bwd(_ptr(src if g_out is not None else None), _ptr(Hc), _ptr(g_out), _ptr(g_mask), _ptr(gH),
                                        _ptr(g_src), B, C, Hs, Ws, Ho, Wo, pool, nhwc, _ptr(ws), int(nbytes), _stream()),
                        'bh_warp_bwd')
@@ -292,7 +317,7 @@ class _BihomeLoss(torch.autograd.Function):
         ctx.grads = None
         B, C, h, w = ctx.dims
         g_loss = g_loss.contiguous().float()
-        with torch.cuda.device(g_f1w.device), _timed('bh_bihome_rescale'):
+        with _on(g_f1w.device), _timed('bh_bihome_rescale'):
             cabi.check(cabi.lib().bh_bihome_rescale(_ptr(g_loss), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_m1w),
                                                     _ptr(g_m2w), _ptr(gH12), _ptr(gH21), B, C, h, w, _stream()),
                        'bh_bihome_rescale')
@@ -374,7 +399,7 @@ class _TripletLoss(torch.autograd.Function):
         ctx.grads = None
         B, C, h, w = ctx.dims
         g_loss = g_loss.contiguous().float()
-        with torch.cuda.device(g_f1w.device), _timed('bh_triplet_rescale'):
+        with _on(g_f1w.device), _timed('bh_triplet_rescale'):
             cabi.check(cabi.lib().bh_triplet_rescale(_ptr(g_loss), _ptr(g_f1w), _ptr(g_f2w), _ptr(g_f1), _ptr(g_f2), _ptr(g_a1),
                                                      _ptr(g_b2), _ptr(g_a2), _ptr(g_b1), _ptr(gH12), _ptr(gH21), B, C, h, w, _stream()),
                        'bh_triplet_rescale')
@@ -432,7 +457,7 @@ class _DltN(torch.autograd.Function):
         if four is not None:
             four = four.detach().to(torch.float32).contiguous().view(4, 2)
             delta = torch.empty(B, 4, 2, device=src.device, dtype=torch.float32)
-        with torch.cuda.device(src.device), _timed('bh_dltn_fwd'):
+        with _on(src.device), _timed('bh_dltn_fwd'):
             cabi.check(cabi.lib().bh_dltn_fwd(_ptr(p1), _ptr(p2), _ptr(field), _ptr(choice), _ptr(four), _ptr(Hn), _ptr(delta),
                                               B, N, M, Wf, _stream()), 'bh_dltn_fwd')
         ctx.save_for_backward(p1, p2, field, choice, four)
@@ -500,7 +525,7 @@ def pairgen_apply(images, index, params, patch_size, mean=0.443, std=0.129):
     buf = torch.empty(2 * B, 1, P, P, device=images.device, dtype=torch.float32)
     delta = torch.empty(B, 4, 2, device=images.device, dtype=torch.float32)
     p1, p2 = buf[:B], buf[B:]
-    with torch.cuda.device(images.device), _timed('bh_pairgen_apply'):
+    with _on(images.device), _timed('bh_pairgen_apply'):
         cabi.check(cabi.lib().bh_pairgen_apply(_ptr(images), _ptr(index.contiguous()), _ptr(params.contiguous()), _ptr(p1), _ptr(p2),
                                                _ptr(delta), B, images.shape[0], images.shape[1], images.shape[2], P,
                                                float(mean), float(std), _stream()), 'bh_pairgen_apply')
@@ -516,7 +541,7 @@ def pairgen_image(images, index, params, mean=0.443, std=0.129):
     n, hi, wi, _ = images.shape
     B = index.shape[0]
     out = torch.empty(B, 1, hi, wi, device=images.device, dtype=torch.float32)
-    with torch.cuda.device(images.device), _timed('bh_pairgen_image'):
+    with _on(images.device), _timed('bh_pairgen_image'):
         cabi.check(cabi.lib().bh_pairgen_image(_ptr(images), _ptr(index.contiguous()), _ptr(params.contiguous()), _ptr(out), B, n, hi, wi,
                                                float(mean), float(std), _stream()), 'bh_pairgen_image')
     return out
@@ -529,7 +554,7 @@ def mace(delta_gt, delta_hat):
     _need_cuda_f32('delta_hat', delta_hat)
     a, b = delta_gt.detach().contiguous(), delta_hat.detach().contiguous()
     out = torch.empty(1, device=a.device, dtype=torch.float32)
-    with torch.cuda.device(a.device), _timed('bh_mace'):
+    with _on(a.device), _timed('bh_mace'):
         cabi.check(cabi.lib().bh_mace(_ptr(a), _ptr(b), _ptr(out), a.numel() // 8, _stream()), 'bh_mace')
     return out[0]
 
@@ -545,7 +570,7 @@ def _fh_moments(x):
     lib = cabi.lib()
     grid = lib.bh_fieldhead_grid(0, n)
     parts = torch.empty(grid, C + C * C, device=x.device, dtype=torch.float64)
-    with torch.cuda.device(x.device), _timed('bh_fieldhead_moments'):
+    with _on(x.device), _timed('bh_fieldhead_moments'):
         cabi.check(lib.bh_fieldhead_moments(_ptr(x), _ptr(parts), n, C, _stream()), 'bh_fieldhead_moments')
     s = parts.sum(0)
     return s[:C], s[C:].view(C, C)
@@ -561,7 +586,7 @@ def _fh_fwd(x, W1, b1, W2, b2):
     """x [B,C,H,W] channels-last, folded W1 [hid,C], b1 [hid], W2 [2,hid], b2 [2] -> field [B,2,H,W] (planar)"""
     B, C, H, W = x.shape
     out = torch.empty(B, 2, H, W, device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device), _timed('bh_fieldhead_fwd'):
+    with _on(x.device), _timed('bh_fieldhead_fwd'):
         cabi.check(cabi.lib().bh_fieldhead_fwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(out), B, H * W, C,
                                                W1.shape[0], _fh_tf32(), _stream()), 'bh_fieldhead_fwd')
     return out
@@ -575,7 +600,7 @@ def _fh_bwd(x, W1, b1, W2, g_out):
     grid = lib.bh_fieldhead_grid(1, B * H * W)
     parts = torch.empty(grid, hid * C + 3 * hid + 2, device=x.device, dtype=torch.float32)
     gx = torch.empty_like(x)
-    with torch.cuda.device(x.device), _timed('bh_fieldhead_bwd'):
+    with _on(x.device), _timed('bh_fieldhead_bwd'):
         cabi.check(lib.bh_fieldhead_bwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(g_out), _ptr(gx), _ptr(parts), B, H * W, C,
                                         hid, _fh_tf32(), _stream()), 'bh_fieldhead_bwd')
     s = parts.sum(0)
@@ -586,7 +611,7 @@ def _fh_bwd(x, W1, b1, W2, g_out):
 def _fh_affine(x, a, M, gx):
     """gx += a + M x per pixel, in place"""
     B, C, H, W = x.shape
-    with torch.cuda.device(x.device), _timed('bh_fieldhead_affine'):
+    with _on(x.device), _timed('bh_fieldhead_affine'):
         cabi.check(cabi.lib().bh_fieldhead_affine(_ptr(x), _ptr(a), _ptr(M), _ptr(gx), B * H * W, C, 1, _stream()),
                    'bh_fieldhead_affine')
     return gx
@@ -721,7 +746,7 @@ class _Stem(torch.autograd.Function):
         code = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.uint8) if want_bwd else None
         stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
         ws = _stem_ws(C, x.device)
-        with torch.cuda.device(x.device), _timed('bh_stem_fwd'):
+        with _on(x.device), _timed('bh_stem_fwd'):
             cabi.check(cabi.lib().bh_stem_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(momentum),
                                               float(eps), _ptr(y), _ptr(code), _ptr(stats), _ptr(ws), ws.numel(), N, H, W, C,
                                               _stream()), 'bh_stem_fwd')
@@ -741,7 +766,7 @@ class _Stem(torch.autograd.Function):
         gg = torch.empty(C, device=x.device, dtype=torch.float32) if has_g and ctx.needs_input_grad[1] else None
         gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_b and ctx.needs_input_grad[2] else None
         ws = _stem_ws(C, x.device)
-        with torch.cuda.device(x.device), _timed('bh_stem_bwd'):
+        with _on(x.device), _timed('bh_stem_bwd'):
             cabi.check(cabi.lib().bh_stem_bwd(_ptr(x), _ptr(stats), _ptr(code), _ptr(gy), _ptr(gx), _ptr(gg), _ptr(gb), _ptr(ws),
                                               ws.numel(), N, H, W, C, _stream()), 'bh_stem_bwd')
         return gx, gg, gb, None, None, None, None
@@ -793,7 +818,7 @@ class _BnAct(torch.autograd.Function):
         stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
         ws = _stem_ws(C, x.device)
         # compulsory traffic of the stage: x (+ residual) in, y out
-        with torch.cuda.device(x.device), _timed('bh_bnact_fwd', x.numel() * 4 * (2 if residual is None else 3)):
+        with _on(x.device), _timed('bh_bnact_fwd', x.numel() * 4 * (2 if residual is None else 3)):
             cabi.check(cabi.lib().bh_bnact_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
                                                float(momentum), float(eps), _ptr(y), _ptr(stats), _ptr(ws), ws.numel(), n_pix, C,
                                                _stream()), 'bh_bnact_fwd')
@@ -821,7 +846,7 @@ class _BnAct(torch.autograd.Function):
         gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_b and ctx.needs_input_grad[3] else None
         ws = _stem_ws(C, x.device)
         # compulsory traffic: x, gy (+ y) in, gx (+ gresidual) out
-        with torch.cuda.device(x.device), _timed('bh_bnact_bwd', x.numel() * 4 * (5 if ctx.has_residual else 3)):
+        with _on(x.device), _timed('bh_bnact_bwd', x.numel() * 4 * (5 if ctx.has_residual else 3)):
             cabi.check(cabi.lib().bh_bnact_bwd(_ptr(x), _ptr(y), _ptr(stats), _ptr(gy), _ptr(gx), _ptr(gr), _ptr(gg), _ptr(gb), _ptr(ws),
                                                ws.numel(), N * H * W, C, _stream()), 'bh_bnact_bwd')
         return gx, (gr if ctx.needs_input_grad[1] else None), gg, gb, None, None, None, None

@@ -124,3 +124,55 @@ def test_batchnorm_statistics_stay_rank_local(tmp_path):
             model(x)
         assert torch.allclose(got[rank]['mean'], model.bn.running_mean, atol=1e-6)
         assert torch.allclose(got[rank]['var'], model.bn.running_var, atol=1e-6)
+
+
+def flat_worker(rank, world, port, out):
+    """the data-parallel path of engine.GraphedStep without a DDP wrapper: parameters broadcast once, gradients accumulated
+    into views of one flat buffer, ONE all-reduce (mean) of that buffer -- must equal what DDP computes"""
+    from bihome_b200 import engine
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(rank)                       # different initial weights per rank: sync_module_state must fix that
+    model = TinyBackbone().to(memory_format=torch.channels_last)
+    engine.sync_module_state(model)
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = engine.flatten_gradients(params)
+    assert all(p.grad.stride() == p.stride() and p.grad.shape == p.shape for p in params)
+    p1, p2 = make_batch(4 * world)
+    sl = slice(4 * rank, 4 * rank + 4)
+    results = []
+    for rep in range(2):                          # the second pass checks zero-and-accumulate on the same buffer
+        flat.zero_()
+        oracle_loss(model, p1[sl], p2[sl]).backward()
+        engine.average_gradients(params, flat)
+        results.append([p.grad.clone() for p in params])
+    # coalesced path (gradients that are not views of one buffer)
+    for p in params:
+        p.grad = None
+    oracle_loss(model, p1[sl], p2[sl]).backward()
+    engine.average_gradients(params)
+    if rank == 0:
+        torch.save({'flat': results, 'coalesced': [p.grad.clone() for p in params],
+                    'weights': [p.detach().clone() for p in params]}, out)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_all_reduce_matches_ddp(tmp_path):
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / 'flat.pt')
+    mp.spawn(flat_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)                          # rank 0's weights are the ones every rank ends up with
+    ref = TinyBackbone()
+    for w, p in zip(got['weights'], ref.parameters()):
+        assert torch.equal(w, p.detach())
+    p1, p2 = make_batch(8)
+    oracle_loss(ref, p1, p2).backward()
+    for k, p in enumerate(ref.parameters()):
+        want = p.grad / 2
+        for rep in got['flat']:
+            assert torch.allclose(rep[k], want, rtol=1e-4, atol=1e-6), k
+        assert torch.allclose(got['coalesced'][k], want, rtol=1e-4, atol=1e-6), k

@@ -113,6 +113,9 @@ def train_one_epoch(model, loader, optimizer, gradient_clip, scheduler, loss_fn,
             data['summary_writer_step'] = step
         loss, delta_gt, delta_hat = forward_loss(model, data, loss_fn)
         loss.backward()
+        if cuda_graph and not isinstance(model, torch.nn.parallel.DistributedDataParallel):
+            # --cuda_graph under torchrun: no DDP wrapper (engine.GraphedStep); eager steps exchange their gradients the same way
+            engine.average_gradients([p for p in model.parameters() if p.requires_grad], graphed.flat if graphed is not None else None)
         if gradient_clip > 0:
             torch.nn.utils.clip_grad_norm_(model.parameters(), gradient_clip)
         optimizer.step()
@@ -181,7 +184,7 @@ def do_train(model, train_loader, test_loader, optimizer, gradient_clip, schedul
         t0 = time.perf_counter()
         step = train_one_epoch(model, train_loader, optimizer, gradient_clip, scheduler, loss_fn, epoch, steps_per_epoch,
                                checkpointer, checkpoint_arguments, log_step, writer, self_supervised, log_verbose, max_steps,
-                               cuda_graph=cuda_graph and world == 1)
+                               cuda_graph=cuda_graph)
         torch.cuda.synchronize()
         if rank == 0:
             done = step - epoch * steps_per_epoch
@@ -251,7 +254,10 @@ def main(config_file_path, batch_size=None, max_steps=None, synthetic_pool=256, 
         checkpointer.optimizer = optimizer
 
     net = model
-    if world > 1:
+    if world > 1 and cuda_graph and isinstance(loss_fn, str):
+        # graph replay per rank + one flat all-reduce of the gradients (engine.GraphedStep): no DDP wrapper
+        engine.sync_module_state(model)
+    elif world > 1:
         net = engine.data_parallel(model, local)
         checkpointer.model = net
     self_supervised = 'SELF_SUPERVISED' in config['DATA'] and config['DATA']['SELF_SUPERVISED'] or isinstance(loss_fn, str)
