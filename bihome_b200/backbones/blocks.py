@@ -42,7 +42,17 @@ class _Residual(nn.Module):
         self.lower_is_identity = lower is None
 
     def forward(self, x):
-        skip = x if self.lower_is_identity else self.lower_branch(x)
+        # a skip path that ends in its own BatchNorm (projection / up-sampling blocks): keep its un-normalised tensor and let
+        # the end of the block normalise both branches, add and rectify in one stage (K7c)
+        skip, skip_bn = x, None
+        if not self.lower_is_identity:
+            lower = list(self.lower_branch)
+            if isinstance(lower[-1], nn.BatchNorm2d) and F.bnact2_enabled():
+                for m in lower[:-1]:
+                    skip = m(skip)
+                skip_bn = lower[-1]
+            else:
+                skip = self.lower_branch(x)
         # the memory-bound stages between the convolutions run fused (K7b, csrc/stem.cu) on channels-last CUDA tensors in
         # training: BatchNorm2d -> ReLU inside the branch, BatchNorm2d + skip -> ReLU at its end; anything else (eval mode,
         # NCHW, CPU) takes the modules one by one
@@ -55,10 +65,18 @@ class _Residual(nn.Module):
                     h = F.bn_relu(m, h)
                     i += 2
                     continue
-                if i == n - 1 and F.bnact_supported(m, h, skip):
-                    return F.bn_relu(m, h, residual=skip)
+                if i == n - 1 and skip_bn is not None and h.shape == skip.shape and h.stride() == skip.stride() \
+                        and F.bnact_supported(m, h) and F.bnact_supported(skip_bn, skip):
+                    return F.bn_bn_relu(m, h, skip_bn, skip)
+                if i == n - 1:
+                    if skip_bn is not None:
+                        skip, skip_bn = skip_bn(skip), None
+                    if F.bnact_supported(m, h, skip):
+                        return F.bn_relu(m, h, residual=skip)
             h = m(h)
             i += 1
+        if skip_bn is not None:
+            skip = skip_bn(skip)
         return nn.functional.relu(h + skip)
 
 

@@ -42,6 +42,8 @@ SIGNATURES = {
     'bh_stem_bwd': (_i, [_vp] * 8 + [_sz, _i, _i, _i, _i, _vp]),
     'bh_bnact_fwd': (_i, [_vp] * 6 + [_f, _f] + [_vp] * 3 + [_sz, ctypes.c_longlong, _i, _vp]),
     'bh_bnact_bwd': (_i, [_vp] * 9 + [_sz, ctypes.c_longlong, _i, _vp]),
+    'bh_bnact2_fwd': (_i, [_vp] * 6 + [_f, _f] + [_vp] * 4 + [_f, _f] + [_vp] * 4 + [_sz, ctypes.c_longlong, _i, _vp]),
+    'bh_bnact2_bwd': (_i, [_vp] * 13 + [_sz, ctypes.c_longlong, _i, _vp]),
 }
 
 _lib = None

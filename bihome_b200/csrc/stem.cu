@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_pool_fwd_kernel(const float
                                                                      int W, int Ho, int Wo, int Q, int lq, int strips, int xblocks) {
     const int C = Q * 4;
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
-    int item = blockIdx.x;
+    // items in REVERSE order: the statistics pass swept x front to back, so the tail of the tensor is what the L2 still holds
+    int item = gridDim.x - 1 - blockIdx.x;
     const int xb = item % xblocks;
     item /= xblocks;
     const int strip = item % strips, n = item / strips;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kStemThreads, 3) stem_bwd_apply_kernel(const f
                                                                       int W, int Ho, int Wo, int Q, int lq, int xblocks) {
     const int C = Q * 4;
     const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
-    int item = blockIdx.x;
+    int item = gridDim.x - 1 - blockIdx.x;      // reverse order: the reduce pass left the tail of x / gy in the L2
     const int xb = item % xblocks;
     item /= xblocks;
     const int k = item % Ho, n = item / Ho;
@@ -379,32 +380,35 @@ __global__ void __launch_bounds__(kStemThreads) bnact_fwd_kernel(const float* __
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const float4* r4 = reinterpret_cast<const float4*>(r);
     float4* y4 = reinterpret_cast<float4*>(y);
+    // pixels in REVERSE order (pixel n_pix-1-p): the statistics pass swept x front to back, so the tail of the tensor is
+    // what the L2 still holds when this grid starts
+    const long long last = n_pix - 1;
     long long p = static_cast<long long>(blockIdx.x) * PL + pl;
     for (; p + 3 * stride < n_pix; p += 4 * stride) {
         float4 v[4], w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldg_stream(x4 + (p + u * stride) * Q + q);
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream(x4 + (last - (p + u * stride)) * Q + q);
         if (kRes) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) w[u] = ldg_stream(r4 + (p + u * stride) * Q + q);
+            for (int u = 0; u < 4; ++u) w[u] = ldg_stream(r4 + (last - (p + u * stride)) * Q + q);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float4 o = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z), fmaf(v[u].w, sc.w, sh.w));
             if (kRes) { o.x += w[u].x; o.y += w[u].y; o.z += w[u].z; o.w += w[u].w; }
             o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
-            y4[(p + u * stride) * Q + q] = o;      // the next convolution reads it: leave it in L2
+            y4[(last - (p + u * stride)) * Q + q] = o;      // the next convolution reads it: leave it in L2
         }
     }
     for (; p < n_pix; p += stride) {
-        const float4 v = ldg_stream(x4 + p * Q + q);
+        const float4 v = ldg_stream(x4 + (last - p) * Q + q);
         float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
         if (kRes) {
-            const float4 w = ldg_stream(r4 + p * Q + q);
+            const float4 w = ldg_stream(r4 + (last - p) * Q + q);
             o.x += w.x; o.y += w.y; o.z += w.z; o.w += w.w;
         }
         o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
-        y4[p * Q + q] = o;
+        y4[(last - p) * Q + q] = o;
     }
 }
 
@@ -467,18 +471,127 @@ __global__ void __launch_bounds__(kStemThreads) bnact_bwd_apply_kernel(const flo
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const float4* g4 = reinterpret_cast<const float4*>(g);
     float4* o4 = reinterpret_cast<float4*>(gx);
+    const long long last = n_pix - 1;       // reverse order, as in the forward: the reduce pass left the tail in the L2
     long long p = static_cast<long long>(blockIdx.x) * PL + pl;
     for (; p < n_pix; p += 2 * stride) {
         const bool two = p + stride < n_pix;
-        const float4 x0 = ldg_stream(x4 + p * Q + q), g0 = ldg_stream(g4 + p * Q + q);
+        const long long i0 = (last - p) * Q + q, i1 = (last - p - stride) * Q + q;
+        const float4 x0 = ldg_stream(x4 + i0), g0 = ldg_stream(g4 + i0);
         float4 x1 = x0, g1 = g0;
-        if (two) { x1 = ldg_stream(x4 + (p + stride) * Q + q); g1 = ldg_stream(g4 + (p + stride) * Q + q); }
+        if (two) { x1 = ldg_stream(x4 + i1); g1 = ldg_stream(g4 + i1); }
         const float4 d0 = kRes ? g0 : gate4(g0, x0, sc, sh), d1 = kRes ? g1 : gate4(g1, x1, sc, sh);
-        stg_stream(o4 + p * Q + q, make_float4(fmaf(ca.x, d0.x, fmaf(cb.x, x0.x, cc.x)), fmaf(ca.y, d0.y, fmaf(cb.y, x0.y, cc.y)),
+        stg_stream(o4 + i0, make_float4(fmaf(ca.x, d0.x, fmaf(cb.x, x0.x, cc.x)), fmaf(ca.y, d0.y, fmaf(cb.y, x0.y, cc.y)),
                                                fmaf(ca.z, d0.z, fmaf(cb.z, x0.z, cc.z)), fmaf(ca.w, d0.w, fmaf(cb.w, x0.w, cc.w))));
         if (two)
-            stg_stream(o4 + (p + stride) * Q + q, make_float4(fmaf(ca.x, d1.x, fmaf(cb.x, x1.x, cc.x)), fmaf(ca.y, d1.y, fmaf(cb.y, x1.y, cc.y)),
+            stg_stream(o4 + i1, make_float4(fmaf(ca.x, d1.x, fmaf(cb.x, x1.x, cc.x)), fmaf(ca.y, d1.y, fmaf(cb.y, x1.y, cc.y)),
                                                               fmaf(ca.z, d1.z, fmaf(cb.z, x1.z, cc.z)), fmaf(ca.w, d1.w, fmaf(cb.w, x1.w, cc.w))));
+    }
+}
+
+// ---- K7c: the end of a block whose skip path has its own BatchNorm: y = relu(bn_a(a) + bn_b(b)) ------------------------------
+// (ResNet34ConvBlock with a projection, the up-sampling blocks: src/backbones/utils.py).  Through K7b this is the skip's BatchNorm
+// in cuDNN (which writes r) plus relu(bn(a) + r); here neither r nor its gradient exists: the forward reads a and b and
+// writes y, the backward reads a, b, gy, y twice and writes both input gradients.
+__global__ void __launch_bounds__(kStemThreads) bnact2_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                  const float* __restrict__ stats_a, const float* __restrict__ stats_b,
+                                                                  float* __restrict__ y, long long n_pix, int Q, int lq) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    pdl_wait();
+    const float4 sa = ld4(stats_a + 4 * q), ha = ld4(stats_a + C + 4 * q), sb = ld4(stats_b + 4 * q), hb = ld4(stats_b + C + 4 * q);
+    const float4 sh = make_float4(ha.x + hb.x, ha.y + hb.y, ha.z + hb.z, ha.w + hb.w);
+    const long long stride = static_cast<long long>(gridDim.x) * PL, last = n_pix - 1;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (long long p = static_cast<long long>(blockIdx.x) * PL + pl; p < n_pix; p += 2 * stride) {
+        const bool two = p + stride < n_pix;
+        const long long i0 = (last - p) * Q + q, i1 = (last - p - stride) * Q + q;
+        const float4 u0 = ldg_stream(a4 + i0), v0 = ldg_stream(b4 + i0);
+        float4 u1 = u0, v1 = v0;
+        if (two) { u1 = ldg_stream(a4 + i1); v1 = ldg_stream(b4 + i1); }
+        y4[i0] = make_float4(fmaxf(fmaf(u0.x, sa.x, fmaf(v0.x, sb.x, sh.x)), 0.0f), fmaxf(fmaf(u0.y, sa.y, fmaf(v0.y, sb.y, sh.y)), 0.0f),
+                             fmaxf(fmaf(u0.z, sa.z, fmaf(v0.z, sb.z, sh.z)), 0.0f), fmaxf(fmaf(u0.w, sa.w, fmaf(v0.w, sb.w, sh.w)), 0.0f));
+        if (two)
+            y4[i1] = make_float4(fmaxf(fmaf(u1.x, sa.x, fmaf(v1.x, sb.x, sh.x)), 0.0f), fmaxf(fmaf(u1.y, sa.y, fmaf(v1.y, sb.y, sh.y)), 0.0f),
+                                 fmaxf(fmaf(u1.z, sa.z, fmaf(v1.z, sb.z, sh.z)), 0.0f), fmaxf(fmaf(u1.w, sa.w, fmaf(v1.w, sb.w, sh.w)), 0.0f));
+    }
+}
+
+// both BatchNorms' sums in one pass: partials_a / partials_b [2][C][grid]
+__global__ void __launch_bounds__(kStemThreads, 2) bnact2_bwd_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                            const float* __restrict__ y, const float* __restrict__ stats_a,
+                                                                            const float* __restrict__ stats_b, const float* __restrict__ gy,
+                                                                            double* __restrict__ partials_a, double* __restrict__ partials_b,
+                                                                            long long n_pix, int Q, int lq) {
+    pdl_launch_dependents();
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const float4 ma = ld4(stats_a + 2 * C + 4 * q), ia = ld4(stats_a + 3 * C + 4 * q), mb = ld4(stats_b + 2 * C + 4 * q), ib = ld4(stats_b + 3 * C + 4 * q);
+    const float4 oa = make_float4(-ma.x * ia.x, -ma.y * ia.y, -ma.z * ia.z, -ma.w * ia.w);
+    const float4 ob = make_float4(-mb.x * ib.x, -mb.y * ib.y, -mb.z * ib.z, -mb.w * ib.w);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t[4] = {0, 0, 0, 0};      // s: sum dy, sum dy ahat; t: sum dy bhat (sum dy is shared)
+    long long p = static_cast<long long>(blockIdx.x) * PL + pl;
+    while (p < n_pix) {
+        float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), da = d0, db = d0;
+#pragma unroll 4
+        for (int u = 0; u < kStemRun; ++u) {
+            if (p < n_pix) {
+                const float4 av = ldg_stream(a4 + p * Q + q), bv = ldg_stream(b4 + p * Q + q), yv = ldg_stream(y4 + p * Q + q);
+                float4 d = ldg_stream(g4 + p * Q + q);
+                d.x = yv.x > 0.0f ? d.x : 0.0f; d.y = yv.y > 0.0f ? d.y : 0.0f;
+                d.z = yv.z > 0.0f ? d.z : 0.0f; d.w = yv.w > 0.0f ? d.w : 0.0f;
+                d0.x += d.x; d0.y += d.y; d0.z += d.z; d0.w += d.w;
+                da.x = fmaf(d.x, fmaf(av.x, ia.x, oa.x), da.x); da.y = fmaf(d.y, fmaf(av.y, ia.y, oa.y), da.y);
+                da.z = fmaf(d.z, fmaf(av.z, ia.z, oa.z), da.z); da.w = fmaf(d.w, fmaf(av.w, ia.w, oa.w), da.w);
+                db.x = fmaf(d.x, fmaf(bv.x, ib.x, ob.x), db.x); db.y = fmaf(d.y, fmaf(bv.y, ib.y, ob.y), db.y);
+                db.z = fmaf(d.z, fmaf(bv.z, ib.z, ob.z), db.z); db.w = fmaf(d.w, fmaf(bv.w, ib.w, ob.w), db.w);
+            }
+            p += stride;
+        }
+        s[0] += d0.x; s[1] += d0.y; s[2] += d0.z; s[3] += d0.w;
+        s[4] += da.x; s[5] += da.y; s[6] += da.z; s[7] += da.w;
+        t[0] += db.x; t[1] += db.y; t[2] += db.z; t[3] += db.w;
+    }
+    stem_cta_partials(s, partials_a, Q, lq, C);
+    __syncthreads();       // the shared scratch of stem_cta_partials is reused
+    const double sb2[8] = {s[0], s[1], s[2], s[3], t[0], t[1], t[2], t[3]};
+    stem_cta_partials(sb2, partials_b, Q, lq, C);
+}
+
+// ga = ca0 dy + ca1 a + ca2, gb = cb0 dy + cb1 b + cb2, dy = gy where y > 0
+__global__ void __launch_bounds__(kStemThreads) bnact2_bwd_apply_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                        const float* __restrict__ y, const float* __restrict__ gy,
+                                                                        const float* __restrict__ coef_a, const float* __restrict__ coef_b,
+                                                                        float* __restrict__ ga, float* __restrict__ gb, long long n_pix,
+                                                                        int Q, int lq) {
+    const int C = Q * 4;
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    pdl_wait();
+    const float4 a0 = ld4(coef_a + 4 * q), a1 = ld4(coef_a + C + 4 * q), a2 = ld4(coef_a + 2 * C + 4 * q);
+    const float4 b0 = ld4(coef_b + 4 * q), b1 = ld4(coef_b + C + 4 * q), b2 = ld4(coef_b + 2 * C + 4 * q);
+    const long long stride = static_cast<long long>(gridDim.x) * PL, last = n_pix - 1;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    float4* oa4 = reinterpret_cast<float4*>(ga);
+    float4* ob4 = reinterpret_cast<float4*>(gb);
+    for (long long p = static_cast<long long>(blockIdx.x) * PL + pl; p < n_pix; p += stride) {
+        const long long i = (last - p) * Q + q;
+        const float4 av = ldg_stream(a4 + i), bv = ldg_stream(b4 + i), yv = ldg_stream(y4 + i);
+        float4 d = ldg_stream(g4 + i);
+        d.x = yv.x > 0.0f ? d.x : 0.0f; d.y = yv.y > 0.0f ? d.y : 0.0f;
+        d.z = yv.z > 0.0f ? d.z : 0.0f; d.w = yv.w > 0.0f ? d.w : 0.0f;
+        stg_stream(oa4 + i, make_float4(fmaf(a0.x, d.x, fmaf(a1.x, av.x, a2.x)), fmaf(a0.y, d.y, fmaf(a1.y, av.y, a2.y)),
+                                        fmaf(a0.z, d.z, fmaf(a1.z, av.z, a2.z)), fmaf(a0.w, d.w, fmaf(a1.w, av.w, a2.w))));
+        stg_stream(ob4 + i, make_float4(fmaf(b0.x, d.x, fmaf(b1.x, bv.x, b2.x)), fmaf(b0.y, d.y, fmaf(b1.y, bv.y, b2.y)),
+                                        fmaf(b0.z, d.z, fmaf(b1.z, bv.z, b2.z)), fmaf(b0.w, d.w, fmaf(b1.w, bv.w, b2.w))));
     }
 }
 
@@ -641,4 +754,72 @@ extern "C" int bh_bnact_bwd(const float* x, const float* y, const float* stats, 
     const dim3 grid(bnact_stream_grid(n_pix, PL, 4)), block(kStemThreads);
     if (gresidual) return launch_dependent(bnact_bwd_apply_kernel<true>, grid, block, s, x, stats, coef, gresidual, gx, n_pix, Q, lq);
     return launch_dependent(bnact_bwd_apply_kernel<false>, grid, block, s, x, stats, coef, gy, gx, n_pix, Q, lq);
+}
+
+// ---- K7c entry points: y = relu(bn_a(a) + bn_b(b)) -------------------------------------------------------------------------
+// ws: 2 x bh_stem_workspace_bytes(C) (one region per BatchNorm)
+extern "C" int bh_bnact2_fwd(const float* a, const float* b, const float* gamma_a, const float* beta_a, float* rmean_a, float* rvar_a,
+                             float momentum_a, float eps_a, const float* gamma_b, const float* beta_b, float* rmean_b, float* rvar_b,
+                             float momentum_b, float eps_b, float* y, float* stats_a, float* stats_b, void* ws, size_t ws_bytes,
+                             long long n_pix, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!a || !b || !y || !stats_a || !stats_b || !ws) return BH_E_NULL;
+    int Q, lq, PL;
+    const int rc = bnact_geo(n_pix, C, Q, lq, PL);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(a) || !aligned16(b) || !aligned16(y) || !aligned16(stats_a) || !aligned16(stats_b) || !aligned16(ws)) return BH_E_ALIGN;
+    const size_t region = bh_stem_workspace_bytes(C);
+    if (ws_bytes < 2 * region) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long want = (n_pix + static_cast<long long>(PL) * kStemRun - 1) / (static_cast<long long>(PL) * kStemRun);
+    const int G = static_cast<int>(want < stem_reduce_grid() ? want : stem_reduce_grid());
+    double* pa = static_cast<double*>(ws);
+    double* pb = reinterpret_cast<double*>(static_cast<char*>(ws) + region);
+    bn_stats_kernel<<<G, kStemThreads, 0, s>>>(a, pa, n_pix, Q, lq);
+    int st = launch_status();
+    if (st != BH_OK) return st;
+    st = launch_dependent(bn_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, pa, G, C, static_cast<double>(n_pix), gamma_a, beta_a,
+                          rmean_a, rvar_a, momentum_a, eps_a, stats_a);
+    if (st != BH_OK) return st;
+    bn_stats_kernel<<<G, kStemThreads, 0, s>>>(b, pb, n_pix, Q, lq);
+    st = launch_status();
+    if (st != BH_OK) return st;
+    st = launch_dependent(bn_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, pb, G, C, static_cast<double>(n_pix), gamma_b, beta_b,
+                          rmean_b, rvar_b, momentum_b, eps_b, stats_b);
+    if (st != BH_OK) return st;
+    return launch_dependent(bnact2_fwd_kernel, dim3(bnact_stream_grid(n_pix, PL, 4)), dim3(kStemThreads), s, a, b, stats_a, stats_b, y, n_pix, Q, lq);
+}
+
+extern "C" int bh_bnact2_bwd(const float* a, const float* b, const float* y, const float* stats_a, const float* stats_b, const float* gy,
+                             float* ga, float* gb, float* ggamma_a, float* gbeta_a, float* ggamma_b, float* gbeta_b, void* ws,
+                             size_t ws_bytes, long long n_pix, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!a || !b || !y || !stats_a || !stats_b || !gy || !ga || !gb || !ws) return BH_E_NULL;
+    int Q, lq, PL;
+    const int rc = bnact_geo(n_pix, C, Q, lq, PL);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(a) || !aligned16(b) || !aligned16(y) || !aligned16(gy) || !aligned16(ga) || !aligned16(gb) || !aligned16(stats_a) ||
+        !aligned16(stats_b) || !aligned16(ws))
+        return BH_E_ALIGN;
+    const size_t region = bh_stem_workspace_bytes(C);
+    if (ws_bytes < 2 * region) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long want = (n_pix + static_cast<long long>(PL) * kStemRun - 1) / (static_cast<long long>(PL) * kStemRun);
+    const int cap = kNumSMs * 2;          // the reduce kernel holds two CTAs per SM: one wave
+    const int G = static_cast<int>(want < cap ? want : cap);
+    double* pa = static_cast<double*>(ws);
+    double* pb = reinterpret_cast<double*>(static_cast<char*>(ws) + region);
+    float* ca = reinterpret_cast<float*>(pa + stem_ws_doubles(C));
+    float* cb = reinterpret_cast<float*>(pb + stem_ws_doubles(C));
+    bnact2_bwd_reduce_kernel<<<G, kStemThreads, 0, s>>>(a, b, y, stats_a, stats_b, gy, pa, pb, n_pix, Q, lq);
+    int st = launch_status();
+    if (st != BH_OK) return st;
+    st = launch_dependent(stem_bwd_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, pa, G, C, static_cast<double>(n_pix), stats_a, ca,
+                          ggamma_a, gbeta_a);
+    if (st != BH_OK) return st;
+    st = launch_dependent(stem_bwd_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, pb, G, C, static_cast<double>(n_pix), stats_b, cb,
+                          ggamma_b, gbeta_b);
+    if (st != BH_OK) return st;
+    return launch_dependent(bnact2_bwd_apply_kernel, dim3(bnact_stream_grid(n_pix, PL, 2)), dim3(kStemThreads), s, a, b, y, gy, ca, cb, ga, gb,
+                            n_pix, Q, lq);
 }

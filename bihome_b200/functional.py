@@ -14,6 +14,7 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   field_head(stage, x)                                     K6   Zeng backbone layer8       (src/backbones/Rethinking.py:144-147)
   stem(bn, x)                                              K7   bn1 -> relu -> maxpool     (PerceptualHead.py:56-58, Rethinking.py:31-36)
   bn_relu(bn, x, residual=None)                            K7b  bn -> [+ skip] -> relu     (src/backbones/utils.py, torchvision BasicBlock)
+  bn_bn_relu(bn_a, a, bn_b, b)                             K7c  relu(bn_a(a) + bn_b(b))    (src/backbones/utils.py: blocks with a projection skip)
 """
 import ctypes
 import os
@@ -882,3 +883,58 @@ def bn_relu(bn, x, residual=None):
         residual = residual.contiguous(memory_format=torch.channels_last)
     return _BnAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
                         float(bn.momentum), float(bn.eps))
+
+
+class _BnAct2(torch.autograd.Function):
+    """y = relu(batch_norm_a(a) + batch_norm_b(b)) for channels-last tensors (csrc/stem.cu, K7c)"""
+
+    @staticmethod
+    def forward(ctx, a, b, ga, ba, rma, rva, mom_a, eps_a, gb, bb, rmb, rvb, mom_b, eps_b):
+        N, C, H, W = a.shape
+        n_pix = N * H * W
+        y = torch.empty_like(a)
+        stats = torch.empty((2, 4, C), device=a.device, dtype=torch.float32)
+        ws = torch.empty(2 * int(cabi.lib().bh_stem_workspace_bytes(C)), device=a.device, dtype=torch.uint8)
+        with _on(a.device), _timed('bh_bnact2_fwd', a.numel() * 4 * 3):      # a, b in, y out
+            cabi.check(cabi.lib().bh_bnact2_fwd(_ptr(a), _ptr(b), _ptr(ga), _ptr(ba), _ptr(rma), _ptr(rva), float(mom_a), float(eps_a),
+                                                _ptr(gb), _ptr(bb), _ptr(rmb), _ptr(rvb), float(mom_b), float(eps_b), _ptr(y),
+                                                _ptr(stats[0]), _ptr(stats[1]), _ptr(ws), ws.numel(), n_pix, C, _stream()), 'bh_bnact2_fwd')
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(a, b, y, stats)
+            ctx.affine = (ga is not None, ba is not None, gb is not None, bb is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        a, b, y, stats = ctx.saved_tensors
+        N, C, H, W = a.shape
+        if gy.stride() != a.stride():
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        g_a, g_b = torch.empty_like(a), torch.empty_like(a)
+        need = ctx.needs_input_grad
+        new = lambda have, k: torch.empty(C, device=a.device, dtype=torch.float32) if have and need[k] else None
+        gga, gba, ggb, gbb = new(ctx.affine[0], 2), new(ctx.affine[1], 3), new(ctx.affine[2], 8), new(ctx.affine[3], 9)
+        ws = torch.empty(2 * int(cabi.lib().bh_stem_workspace_bytes(C)), device=a.device, dtype=torch.uint8)
+        with _on(a.device), _timed('bh_bnact2_bwd', a.numel() * 4 * 6):      # a, b, gy, y in, two gradients out
+            cabi.check(cabi.lib().bh_bnact2_bwd(_ptr(a), _ptr(b), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(gy), _ptr(g_a), _ptr(g_b),
+                                                _ptr(gga), _ptr(gba), _ptr(ggb), _ptr(gbb), _ptr(ws), ws.numel(), N * H * W, C, _stream()),
+                       'bh_bnact2_bwd')
+        return (g_a, g_b, gga, gba, None, None, None, None, ggb, gbb, None, None, None, None)
+
+
+def bnact2_enabled():
+    """BH_BNACT2=aten keeps the skip path's BatchNorm on cuDNN (K7b then takes its output as the residual)"""
+    return os.environ.get('BH_BNACT2', 'fused') != 'aten' and os.environ.get('BH_BNACT', 'fused') != 'aten'
+
+
+def bn_bn_relu(bn_a, a, bn_b, b):
+    """``relu(bn_a(a) + bn_b(b))`` in training mode (the end of a residual block whose skip has its own BatchNorm); call only
+    when bnact_supported(bn_a, a) and bnact_supported(bn_b, b) said yes and the two tensors have the same shape and strides"""
+    args = []
+    for bn in (bn_a, bn_b):
+        track = bn.track_running_stats and bn.running_mean is not None
+        if track and bn.num_batches_tracked is not None:
+            with torch.no_grad():
+                bn.num_batches_tracked.add_(1)
+        args += [bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None, float(bn.momentum), float(bn.eps)]
+    return _BnAct2.apply(a, b, *args)

@@ -274,6 +274,23 @@ int bh_bnact_bwd(const float* x, const float* y, const float* stats, const float
                  float* gbeta, void* ws, size_t ws_bytes, long long n_pix, int C, bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7c  y = relu(BatchNorm_a(a) + BatchNorm_b(b)): the end of a residual block whose skip path has its own BatchNorm
+ *
+ * replaces: src/backbones/utils.py  `relu(upper_branch(x) + lower_branch(x))` of ResNet34ConvBlock (projection skip) and the
+ *           up-sampling blocks: two cuDNN BatchNorms, an add and a ReLU forward; threshold_backward + two batch_norm_backward.
+ *
+ * a, b, y, gy, ga, gb: [n_pix, C] rows; stats_a / stats_b [4,C] as in K7.  Neither the skip's normalised tensor nor its
+ * gradient is materialised.  ws: 2 * bh_stem_workspace_bytes(C) bytes.
+ * ------------------------------------------------------------------------------------------- */
+int bh_bnact2_fwd(const float* a, const float* b, const float* gamma_a, const float* beta_a, float* running_mean_a,
+                  float* running_var_a, float momentum_a, float eps_a, const float* gamma_b, const float* beta_b,
+                  float* running_mean_b, float* running_var_b, float momentum_b, float eps_b, float* y, float* stats_a,
+                  float* stats_b, void* ws, size_t ws_bytes, long long n_pix, int C, bh_stream_t stream);
+int bh_bnact2_bwd(const float* a, const float* b, const float* y, const float* stats_a, const float* stats_b, const float* gy,
+                  float* ga, float* gb, float* ggamma_a, float* gbeta_a, float* ggamma_b, float* gbeta_b, void* ws, size_t ws_bytes,
+                  long long n_pix, int C, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MACE: mean over B*4 corners of ||delta_gt - delta_hat||_2  (train.py:401-404, eval.py:133-134)
  * out: 1 float (overwritten).
  * ------------------------------------------------------------------------------------------- */

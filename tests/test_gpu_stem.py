@@ -353,3 +353,50 @@ def test_bn_relu_speed_at_backbone_shapes():
                 (torch.relu(ref(xs) + rs if res else ref(xs)) * g).sum().backward()
             tf, ta = timed(fused), timed(aten)
             print('K7b %s residual=%s: fused %.3f ms, ATen %.3f ms' % (shape, res, tf, ta))
+
+
+# ---- K7c: relu(bn_a(a) + bn_b(b)) ---------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,C,H,W', [(2, 16, 8, 8), (3, 64, 16, 20), (2, 32, 9, 7), (1, 128, 8, 8), (4, 64, 32, 32), (2, 16, 40, 24)])
+def test_bn_bn_relu_matches_the_modules(N, C, H, W):
+    """a on the lattice of the K7b test; b takes seven integer levels and bn_b's weight / bias are chosen so that bn_b(b) is an
+    integer multiple of the level spacing of bn_a(a): every ReLU decision keeps a margin of half a level"""
+    import copy
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    bn_a, _ = _modules(C, seed=C + W)
+    bn_b, _ = _modules(C, seed=C + W + 1, momentum=0.2)
+    a = _lattice_input(N, C, H, W, bn_a, seed=N * 100 + H)
+    n = N * H * W
+    flat = a.double().permute(1, 0, 2, 3).reshape(C, -1)
+    spacing = bn_a.weight.detach().double().abs() * ((flat.max(1).values - flat.min(1).values) / (n - 1)) / torch.sqrt(flat.var(1, unbiased=False) + bn_a.eps)
+    k = torch.randint(-3, 4, (N, C, H, W), generator=torch.Generator().manual_seed(4)).double()
+    b = (0.37 * k + 1.1).float()
+    bflat = b.double().permute(1, 0, 2, 3).reshape(C, -1)
+    sigma_b, mu_b = torch.sqrt(bflat.var(1, unbiased=False) + bn_b.eps), bflat.mean(1)
+    gamma_b = spacing * sigma_b / 0.37                      # bn_b(b) = spacing * k + const
+    beta_b = 2 * spacing + gamma_b * (mu_b - 1.1) / sigma_b   # const = 2 * spacing
+    with torch.no_grad():
+        bn_b.weight.copy_(gamma_b.float())
+        bn_b.bias.copy_(beta_b.float())
+    a = a.to(dev).contiguous(memory_format=torch.channels_last)
+    b = b.to(dev).contiguous(memory_format=torch.channels_last)
+    bn_a, bn_b = bn_a.to(dev).train(), bn_b.to(dev).train()
+    g = torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+    ra, rb = copy.deepcopy(bn_a).double(), copy.deepcopy(bn_b).double()
+    a64, b64 = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    y64 = torch.relu(ra(a64) + rb(b64))
+    (y64 * g.double()).sum().backward()
+    assert F.bnact_supported(bn_a, a) and F.bnact_supported(bn_b, b)
+    xa, xb = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.bn_bn_relu(bn_a, xa, bn_b, xb)
+    (y * g).sum().backward()
+    _close(y.detach(), y64.detach(), TOL, 'output')
+    for mine, ref in ((bn_a, ra), (bn_b, rb)):
+        _close(mine.running_mean, ref.running_mean, TOL, 'running_mean')
+        _close(mine.running_var, ref.running_var, TOL, 'running_var')
+        assert int(mine.num_batches_tracked) == int(ref.num_batches_tracked)
+        _close(mine.weight.grad, ref.weight.grad, 5 * TOL, 'weight gradient')
+        _close(mine.bias.grad, ref.bias.grad, 5 * TOL, 'bias gradient')
+    _close(xa.grad, a64.grad, 5 * TOL, 'gradient of a')
+    _close(xb.grad, b64.grad, 5 * TOL, 'gradient of b')
