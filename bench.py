@@ -324,8 +324,9 @@ def run_ours(args):
         if name in kernels and kernels[name]['avg_ms'] > 0:
             gbs = per_pair * B / (kernels[name]['avg_ms'] * 1e-3) / 1e9
             kernels[name].update({'algorithmic_GBps': gbs, 'frac_of_hbm_peak': gbs / peak})
-    # entry points whose tensors change from call to call (K7b): bytes summed over the timed calls (x [+ residual] in, y out;
-    # x, gy [+ y] in, gx [+ gresidual] out -- the single-pass minimum, although the batch statistics force a second read of x)
+    # entry points whose tensors change from call to call (K7b / K7c): bytes summed over the timed calls -- every input and
+    # output tensor once, plus the second read of what the second pass needs again when that does not fit in the 126 MB L2
+    # (functional._bn_bytes; the batch statistics force two passes)
     for name, total in kbytes.items():
         if name in kernels and name not in ALG and kernels[name]['avg_ms'] > 0:
             gbs = total / (kernels[name]['avg_ms'] * kernels[name]['launches'] * 1e-3) / 1e9

@@ -808,6 +808,17 @@ def stem(bn, x):
 # ------------------------------------------------------------------------------------------------
 # K7b: BatchNorm2d (batch statistics) [+ residual] -> ReLU, the inner stages of the residual blocks
 # ------------------------------------------------------------------------------------------------
+_L2_BYTES = 126e6      # B200: what a second pass can still find on chip
+
+
+def _bn_bytes(x, reread, reads, writes):
+    """algorithmic bytes of a two-pass BatchNorm stage over tensors of x's size (bench.py's per-call accounting): `reads` input
+    tensors and `writes` output tensors once each, plus the `reread` tensors the second pass needs again -- compulsory only
+    when they do not fit in the L2 together (batch statistics need the whole tensor before the first output element)"""
+    t = x.numel() * 4
+    return t * (reads + writes + (reread if reread * t > _L2_BYTES else 0))
+
+
 class _BnAct(torch.autograd.Function):
     """y = relu(batch_norm(x) [+ residual]) for channels-last tensors (csrc/stem.cu, K7b)"""
 
@@ -818,8 +829,7 @@ class _BnAct(torch.autograd.Function):
         y = torch.empty_like(x)
         stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
         ws = _stem_ws(C, x.device)
-        # compulsory traffic of the stage: x (+ residual) in, y out
-        with _on(x.device), _timed('bh_bnact_fwd', x.numel() * 4 * (2 if residual is None else 3)):
+        with _on(x.device), _timed('bh_bnact_fwd', _bn_bytes(x, 1, 1 if residual is None else 2, 1)):
             cabi.check(cabi.lib().bh_bnact_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
                                                float(momentum), float(eps), _ptr(y), _ptr(stats), _ptr(ws), ws.numel(), n_pix, C,
                                                _stream()), 'bh_bnact_fwd')
@@ -846,8 +856,7 @@ class _BnAct(torch.autograd.Function):
         gg = torch.empty(C, device=x.device, dtype=torch.float32) if has_g and ctx.needs_input_grad[2] else None
         gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_b and ctx.needs_input_grad[3] else None
         ws = _stem_ws(C, x.device)
-        # compulsory traffic: x, gy (+ y) in, gx (+ gresidual) out
-        with _on(x.device), _timed('bh_bnact_bwd', x.numel() * 4 * (5 if ctx.has_residual else 3)):
+        with _on(x.device), _timed('bh_bnact_bwd', _bn_bytes(x, 2, 3 if ctx.has_residual else 2, 2 if ctx.has_residual else 1)):
             cabi.check(cabi.lib().bh_bnact_bwd(_ptr(x), _ptr(y), _ptr(stats), _ptr(gy), _ptr(gx), _ptr(gr), _ptr(gg), _ptr(gb), _ptr(ws),
                                                ws.numel(), N * H * W, C, _stream()), 'bh_bnact_bwd')
         return gx, (gr if ctx.needs_input_grad[1] else None), gg, gb, None, None, None, None
@@ -895,7 +904,7 @@ class _BnAct2(torch.autograd.Function):
         y = torch.empty_like(a)
         stats = torch.empty((2, 4, C), device=a.device, dtype=torch.float32)
         ws = torch.empty(2 * int(cabi.lib().bh_stem_workspace_bytes(C)), device=a.device, dtype=torch.uint8)
-        with _on(a.device), _timed('bh_bnact2_fwd', a.numel() * 4 * 3):      # a, b in, y out
+        with _on(a.device), _timed('bh_bnact2_fwd', _bn_bytes(a, 2, 2, 1)):
             cabi.check(cabi.lib().bh_bnact2_fwd(_ptr(a), _ptr(b), _ptr(ga), _ptr(ba), _ptr(rma), _ptr(rva), float(mom_a), float(eps_a),
                                                 _ptr(gb), _ptr(bb), _ptr(rmb), _ptr(rvb), float(mom_b), float(eps_b), _ptr(y),
                                                 _ptr(stats[0]), _ptr(stats[1]), _ptr(ws), ws.numel(), n_pix, C, _stream()), 'bh_bnact2_fwd')
@@ -915,7 +924,7 @@ class _BnAct2(torch.autograd.Function):
         new = lambda have, k: torch.empty(C, device=a.device, dtype=torch.float32) if have and need[k] else None
         gga, gba, ggb, gbb = new(ctx.affine[0], 2), new(ctx.affine[1], 3), new(ctx.affine[2], 8), new(ctx.affine[3], 9)
         ws = torch.empty(2 * int(cabi.lib().bh_stem_workspace_bytes(C)), device=a.device, dtype=torch.uint8)
-        with _on(a.device), _timed('bh_bnact2_bwd', a.numel() * 4 * 6):      # a, b, gy, y in, two gradients out
+        with _on(a.device), _timed('bh_bnact2_bwd', _bn_bytes(a, 4, 4, 2)):
             cabi.check(cabi.lib().bh_bnact2_bwd(_ptr(a), _ptr(b), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(gy), _ptr(g_a), _ptr(g_b),
                                                 _ptr(gga), _ptr(gba), _ptr(ggb), _ptr(gbb), _ptr(ws), ws.numel(), N * H * W, C, _stream()),
                        'bh_bnact2_bwd')
