@@ -301,13 +301,14 @@ def run_ours(args):
     # algorithmic bytes per image pair and launch (SURVEY.md 8d / DESIGN.md section 4); K6 works per pixel of one backbone
     # pass (16 384 pixels per pair): 64 B in, 8 B field, 64 B input gradient
     px = 128 * 128
+    stem_t = B * 64 * 64 * 64 * 4.0
     ALG = {'bh_warp_fwd': 270336, 'bh_warp_bwd': 270408, 'bh_bihome_fwd_bwd': LOSS_BYTES_PER_PAIR,
            'bh_pairgen_apply': 2 * 3 * (128 + 64) ** 2 + 2 * 4 * 128 * 128,
            'bh_fieldhead_moments': 64 * px, 'bh_fieldhead_fwd': 72 * px, 'bh_fieldhead_bwd': 136 * px, 'bh_fieldhead_affine': 192 * px,
-           # K7 per pass over one sample's [64,64,64] stem tensor (1 MiB): forward reads it twice (the batch statistics force the
-           # second pass) and writes the pooled quarter; backward reads it twice, writes its gradient, reads the pooled gradient
-           # and the 1-byte window codes twice
-           'bh_stem_fwd': 2 * 1048576 + 262144, 'bh_stem_bwd': 3 * 1048576 + 2 * (262144 + 65536)}
+           # K7 per pass over the [B,64,64,64] stem tensor (T bytes, pooled quarter T/4, 1-byte codes T/16): every tensor once, plus
+           # the part of the second pass' inputs that cannot have stayed in the 126 MB L2 (the batch statistics force two passes)
+           'bh_stem_fwd': (stem_t + stem_t / 4 + max(0.0, stem_t - 126e6)) / B,
+           'bh_stem_bwd': (2 * stem_t + stem_t / 4 + stem_t / 16 + max(0.0, stem_t + stem_t / 4 + stem_t / 16 - 126e6)) / B}
     NAMES = {'bh_bihome_fwd_bwd': 'bihome_stream_kernel<false,1> + bihome_finish_kernel (bh_bihome_fwd_bwd, channels-last C=64, B<512)',
              'bh_fieldhead_bwd': 'fieldhead_gx_mma_kernel + fieldhead_gw_mma_kernel (bh_fieldhead_bwd: mma.sync TF32 tensor-core kernels, '
                                  'bound by the mma.sync issue rate and the ReLU/projection epilogue, not by HBM)',

@@ -813,10 +813,11 @@ _L2_BYTES = 126e6      # B200: what a second pass can still find on chip
 
 def _bn_bytes(x, reread, reads, writes):
     """algorithmic bytes of a two-pass BatchNorm stage over tensors of x's size (bench.py's per-call accounting): `reads` input
-    tensors and `writes` output tensors once each, plus the `reread` tensors the second pass needs again -- compulsory only
-    when they do not fit in the L2 together (batch statistics need the whole tensor before the first output element)"""
+    tensors and `writes` output tensors once each, plus whatever part of the `reread` tensors the second pass needs again
+    cannot have stayed in the L2 (the batch statistics need the whole tensor before the first output element, so the second
+    pass is compulsory; its traffic is not, up to the L2's capacity)"""
     t = x.numel() * 4
-    return t * (reads + writes + (reread if reread * t > _L2_BYTES else 0))
+    return t * (reads + writes) + max(0.0, reread * t - _L2_BYTES)
 
 
 class _BnAct(torch.autograd.Function):

@@ -32,6 +32,8 @@ if has r; then
 fi
 if has m; then
   timeout 600 python tools/microbench.py > gpurun_out/microbench_$TAG.jsonl 2>&1; echo "microbench rc=$?"; head -14 gpurun_out/microbench_$TAG.jsonl
+  # K7 / K7b per tensor shape of the step, against cuDNN BatchNorm + ATen ReLU / MaxPool
+  timeout 300 python tools/microbench_bn.py > gpurun_out/microbench_bn_$TAG.jsonl 2>&1; echo "microbench_bn rc=$?"; tail -3 gpurun_out/microbench_bn_$TAG.jsonl
 fi
 if has l; then
   # application only: ncu would otherwise follow the field head's self-test into its child process; cudnn.benchmark off: its
@@ -48,5 +50,11 @@ if has n; then
   ncu -i gpurun_out/prof_kernels_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw_$TAG.csv 2> /dev/null
   ls -la gpurun_out/prof_kernels_$TAG.ncu-rep
   if [ $(stat -c %s gpurun_out/prof_kernels_$TAG.ncu-rep) -gt 30000000 ]; then rm -f gpurun_out/prof_kernels_$TAG.ncu-rep; fi
+fi
+if has n; then
+  # the K7 stem kernels (268 MB tensors: ncu's replays are slow, keep the capture short); tools/calls/r04h.sh has the K7b set
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"bn_stats|bn_finalize|stem_" -c 12 -f \
+      -o gpurun_out/prof_stem_$TAG python tools/microbench_bn.py --once --only-stem > gpurun_out/once_stem_$TAG.log 2>&1; echo "ncu stem rc=$?"
+  ncu -i gpurun_out/prof_stem_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_stem_raw_$TAG.csv 2> /dev/null
 fi
 ls -la gpurun_out

@@ -21,6 +21,7 @@ def main():
     ap.add_argument('--once', action='store_true', help='one launch per case (for ncu)')
     ap.add_argument('--warm', action='store_true', help='do not flush the L2 between launches')
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--only-stem', action='store_true', help='skip the K7b shapes (short ncu captures of the K7 kernels)')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -41,7 +42,7 @@ def main():
             ms.append(e0.elapsed_time(e1))
         return sum(ms[-iters:]) / iters
 
-    for shape in SHAPES:
+    for shape in ([] if a.only_stem else SHAPES):
         N, C, H, W = shape
         T = N * C * H * W * 4
         bn = torch.nn.BatchNorm2d(C).to(dev).train()
