@@ -320,7 +320,9 @@ def run_ours(args):
              'bh_bnact_fwd': 'bn_stats_kernel + bn_finalize_kernel + bnact_fwd_kernel (bh_bnact_fwd: BatchNorm [+ residual] -> ReLU of the residual blocks, all shapes of the step)',
              'bh_bnact_bwd': 'bnact_bwd_reduce_kernel + stem_bwd_finalize_kernel + bnact_bwd_apply_kernel (bh_bnact_bwd, all shapes of the step)',
              'bh_bnact2_fwd': '2 x (bn_stats_kernel + bn_finalize_kernel) + bnact2_fwd_kernel (bh_bnact2_fwd: relu(bn(a) + bn(b)), all shapes of the step)',
-             'bh_bnact2_bwd': 'bnact2_bwd_reduce_kernel + 2 x stem_bwd_finalize_kernel + bnact2_bwd_apply_kernel (bh_bnact2_bwd, all shapes of the step)'}
+             'bh_bnact2_bwd': 'bnact2_bwd_reduce_kernel + 2 x stem_bwd_finalize_kernel + bnact2_bwd_apply_kernel (bh_bnact2_bwd, all shapes of the step)',
+             'bh_bias_add': 'bias_add_kernel (bh_bias_add: in-place bias of the transposed convolutions, all shapes of the step)',
+             'bh_bias_grad': 'bn_stats_kernel + bias_grad_finalize_kernel (bh_bias_grad, all shapes of the step)'}
     for name, per_pair in ALG.items():
         if name in kernels and kernels[name]['avg_ms'] > 0:
             gbs = per_pair * B / (kernels[name]['avg_ms'] * 1e-3) / 1e9
@@ -368,7 +370,8 @@ def run_ours(args):
             'layout': {'channels_last': bool(args.channels_last), 'cudnn_benchmark': bool(args.cudnn_benchmark), 'field_head': 'fused (K6)' if F.field_head_enabled(dev) else 'aten',
                        'stem': 'fused (K7)' if 'bh_stem_fwd' in kernels else 'aten',
                        'bn_relu': 'fused (K7b)' if 'bh_bnact_fwd' in kernels else 'aten',
-                       'bn_bn_relu': 'fused (K7c)' if 'bh_bnact2_fwd' in kernels else 'aten'},
+                       'bn_bn_relu': 'fused (K7c)' if 'bh_bnact2_fwd' in kernels else 'aten',
+                       'conv_transpose_bias': 'fused (K8)' if 'bh_bias_add' in kernels else 'aten'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': (ms_e2e / args.steps) if ms_e2e else None},
             'gpu_launches': launches, 'roofline': roofline, 'warp_loss_roofline': warp_loss, 'cpu_baseline': cpu_baseline, 'clocks': clk,

@@ -73,7 +73,10 @@ class _Residual(nn.Module):
                         skip, skip_bn = skip_bn(skip), None
                     if F.bnact_supported(m, h, skip):
                         return F.bn_relu(m, h, residual=skip)
-            h = m(h)
+            if isinstance(m, nn.ConvTranspose2d) and F.convt_bias_supported(m, h):
+                h = F.conv_transpose_bias(m, h)      # K8: cuDNN's transposed convolution + the bias in place
+            else:
+                h = m(h)
             i += 1
         if skip_bn is not None:
             skip = skip_bn(skip)

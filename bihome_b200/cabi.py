@@ -44,6 +44,8 @@ SIGNATURES = {
     'bh_bnact_bwd': (_i, [_vp] * 9 + [_sz, ctypes.c_longlong, _i, _vp]),
     'bh_bnact2_fwd': (_i, [_vp] * 6 + [_f, _f] + [_vp] * 4 + [_f, _f] + [_vp] * 4 + [_sz, ctypes.c_longlong, _i, _vp]),
     'bh_bnact2_bwd': (_i, [_vp] * 13 + [_sz, ctypes.c_longlong, _i, _vp]),
+    'bh_bias_add': (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp]),
+    'bh_bias_grad': (_i, [_vp, _vp, _vp, _sz, ctypes.c_longlong, _i, _vp]),
 }
 
 _lib = None

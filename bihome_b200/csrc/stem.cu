@@ -823,3 +823,82 @@ extern "C" int bh_bnact2_bwd(const float* a, const float* b, const float* y, con
     return launch_dependent(bnact2_bwd_apply_kernel, dim3(bnact_stream_grid(n_pix, PL, 2)), dim3(kStemThreads), s, a, b, y, gy, ca, cb, ga, gb,
                             n_pix, Q, lq);
 }
+
+// =======================================================================================================================
+// K8: the per-channel bias of a transposed convolution, channels-last.  cuDNN's transposed convolution (a data-gradient
+// kernel) has no bias epilogue: ATen adds the bias with a strided broadcast kernel in a pass of its own and reduces its
+// gradient with a generic reduction -- 2.4 ms of the B = 256 training step for the four up-sampling blocks of the Zeng
+// backbone (reference src/backbones/utils.py:65-66, nn.ConvTranspose2d with its default bias=True).
+//   bh_bias_add    y[p, c] += bias[c] in place: one read and one write of the tensor, 16-byte accesses
+//   bh_bias_grad   gbias[c] = sum_p gy[p, c]: the statistics pass of K7 (float32 runs of 16 pixels, float64 above, fixed
+//                  order => bit reproducible) followed by a one-warp-per-channel finish
+// =======================================================================================================================
+namespace bh {
+
+__global__ void __launch_bounds__(kStemThreads) bias_add_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n_pix,
+                                                                int Q, int lq) {
+    const int q = threadIdx.x & (Q - 1), pl = threadIdx.x >> lq, PL = kStemThreads >> lq;
+    const float4 b = ld4(bias + 4 * q);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    float4* y4 = reinterpret_cast<float4*>(y);
+    long long p = static_cast<long long>(blockIdx.x) * PL + pl;
+    // every element is read and written by the same thread; plain (coherent) loads: the tensor is not read-only here
+    for (; p + 3 * stride < n_pix; p += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = y4[(p + u * stride) * Q + q];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u].x += b.x; v[u].y += b.y; v[u].z += b.z; v[u].w += b.w;
+            y4[(p + u * stride) * Q + q] = v[u];      // the next convolution reads it: leave it in L2
+        }
+    }
+    for (; p < n_pix; p += stride) {
+        float4 v = y4[p * Q + q];
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        y4[p * Q + q] = v;
+    }
+}
+
+// one warp per channel over the statistics pass' partials[0][C][G] (the sums; the sums of squares behind them are ignored)
+__global__ void __launch_bounds__(kStemThreads) bias_grad_finalize_kernel(const double* __restrict__ partials, int G, int C,
+                                                                          float* __restrict__ gbias) {
+    pdl_wait();   // the statistics grid has completed
+    const int c = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s, ss;
+    stem_sum_partials(partials, G, C, c, s, ss);
+    if ((threadIdx.x & 31) == 0) gbias[c] = static_cast<float>(s);
+}
+
+}  // namespace bh
+
+extern "C" int bh_bias_add(float* y, const float* bias, long long n_pix, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!y || !bias) return BH_E_NULL;
+    int Q, lq, PL;
+    const int rc = bnact_geo(n_pix, C, Q, lq, PL);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(y) || !aligned16(bias)) return BH_E_ALIGN;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    bias_add_kernel<<<bnact_stream_grid(n_pix, PL, 4), kStemThreads, 0, s>>>(y, bias, n_pix, Q, lq);
+    return launch_status();
+}
+
+extern "C" int bh_bias_grad(const float* gy, float* gbias, void* ws, size_t ws_bytes, long long n_pix, int C, bh_stream_t stream) {
+    using namespace bh;
+    if (!gy || !gbias || !ws) return BH_E_NULL;
+    int Q, lq, PL;
+    const int rc = bnact_geo(n_pix, C, Q, lq, PL);
+    if (rc != BH_OK) return rc;
+    if (!aligned16(gy) || !aligned16(ws)) return BH_E_ALIGN;
+    if (ws_bytes < bh_stem_workspace_bytes(C)) return BH_E_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long want = (n_pix + static_cast<long long>(PL) * kStemRun - 1) / (static_cast<long long>(PL) * kStemRun);
+    const int G = static_cast<int>(want < stem_reduce_grid() ? want : stem_reduce_grid());
+    double* partials = static_cast<double*>(ws);
+    bn_stats_kernel<<<G, kStemThreads, 0, s>>>(gy, partials, n_pix, Q, lq);
+    const int st = launch_status();
+    if (st != BH_OK) return st;
+    return launch_dependent(bias_grad_finalize_kernel, dim3((C + 7) / 8), dim3(kStemThreads), s, partials, G, C, gbias);
+}

@@ -15,6 +15,7 @@ C ABI (include/bihome_b200.h) and returns torch tensors.  Nothing falls back to 
   stem(bn, x)                                              K7   bn1 -> relu -> maxpool     (PerceptualHead.py:56-58, Rethinking.py:31-36)
   bn_relu(bn, x, residual=None)                            K7b  bn -> [+ skip] -> relu     (src/backbones/utils.py, torchvision BasicBlock)
   bn_bn_relu(bn_a, a, bn_b, b)                             K7c  relu(bn_a(a) + bn_b(b))    (src/backbones/utils.py: blocks with a projection skip)
+  conv_transpose_bias(m, x)                                K8   ConvTranspose2d's bias     (src/backbones/utils.py:65-66, up-sampling blocks)
 """
 import ctypes
 import os
@@ -948,3 +949,56 @@ def bn_bn_relu(bn_a, a, bn_b, b):
                 bn.num_batches_tracked.add_(1)
         args += [bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None, float(bn.momentum), float(bn.eps)]
     return _BnAct2.apply(a, b, *args)
+
+
+# ------------------------------------------------------------------------------------------------
+# K8: the bias of a transposed convolution (cuDNN has no bias epilogue for it), channels-last
+# ------------------------------------------------------------------------------------------------
+class _ChannelBias(torch.autograd.Function):
+    """y += bias[c] in place on a channels-last tensor; the bias gradient is the per-channel sum of the upstream gradient,
+    which passes through to y unchanged (csrc/stem.cu, K8)"""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        N, C, H, W = y.shape
+        ctx.mark_dirty(y)
+        with _on(y.device), _timed('bh_bias_add', 2 * y.numel() * 4):
+            cabi.check(cabi.lib().bh_bias_add(_ptr(y), _ptr(bias), N * H * W, C, _stream()), 'bh_bias_add')
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gb = None
+        if ctx.needs_input_grad[1]:
+            N, C, H, W = gy.shape
+            g = gy if _is_nhwc(gy) else gy.contiguous(memory_format=torch.channels_last)
+            gb = torch.empty(C, device=gy.device, dtype=torch.float32)
+            ws = _stem_ws(C, gy.device)
+            with _on(gy.device), _timed('bh_bias_grad', g.numel() * 4):
+                cabi.check(cabi.lib().bh_bias_grad(_ptr(g), _ptr(gb), _ptr(ws), ws.numel(), N * H * W, C, _stream()), 'bh_bias_grad')
+        return gy, gb
+
+
+def convt_bias_supported(m, x):
+    """can K8 add the bias of ``m`` = nn.ConvTranspose2d?  a float32 CUDA input, a float32 bias, zero padding mode, an output
+    channel count the library is compiled for.  BH_CONVT_BIAS=aten keeps the module as it is."""
+    if os.environ.get('BH_CONVT_BIAS', 'fused') == 'aten':
+        return False
+    if not (isinstance(m, torch.nn.ConvTranspose2d) and m.bias is not None and m.bias.dtype == torch.float32
+            and m.padding_mode == 'zeros'):
+        return False
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and m.bias.device == x.device):
+        return False
+    if m.bias.data_ptr() % 16 != 0 or not m.bias.is_contiguous():     # a bias that is a view into a flat parameter buffer
+        return False
+    return bool(cabi.lib().bh_stem_supported(int(m.out_channels)))
+
+
+def conv_transpose_bias(m, x):
+    """``m(x)`` for m = nn.ConvTranspose2d with a bias: the transposed convolution itself stays on cuDNN (without its bias),
+    the bias is added in place by K8 and its gradient reduced by K8.  Same output and gradients as the module; call only
+    when convt_bias_supported() said yes.  An output that cuDNN did not leave channels-last takes ATen's broadcast add."""
+    y = torch.nn.functional.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+    if not _is_nhwc(y):
+        return y + m.bias.view(1, -1, 1, 1)
+    return _ChannelBias.apply(y, m.bias)

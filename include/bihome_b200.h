@@ -291,6 +291,21 @@ int bh_bnact2_bwd(const float* a, const float* b, const float* y, const float* s
                   long long n_pix, int C, bh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K8  per-channel bias of a transposed convolution, channels-last
+ *
+ * replaces: the bias of nn.ConvTranspose2d in the up-sampling blocks (src/backbones/utils.py:65-66, 139-140; default
+ *           bias=True).  cuDNN's transposed convolution has no bias epilogue: ATen adds the bias in a strided broadcast pass
+ *           (`output.add_(reshape_bias(...))`) and reduces `grad_output.sum((0, 2, 3))` with a generic reduction.
+ *
+ * y, gy: [n_pix, C] rows (= channels-last [N,C,H,W]); C as for K7 (bh_stem_supported).
+ *   bh_bias_add    y[p, c] += bias[c], in place.
+ *   bh_bias_grad   gbias[c] (overwritten) = sum over p of gy[p, c], float64 accumulation in a fixed order.
+ * ws: bh_stem_workspace_bytes(C) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int bh_bias_add(float* y, const float* bias, long long n_pix, int C, bh_stream_t stream);
+int bh_bias_grad(const float* gy, float* gbias, void* ws, size_t ws_bytes, long long n_pix, int C, bh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MACE: mean over B*4 corners of ||delta_gt - delta_hat||_2  (train.py:401-404, eval.py:133-134)
  * out: 1 float (overwritten).
  * ------------------------------------------------------------------------------------------- */

@@ -279,7 +279,8 @@ def test_bn_relu_matches_the_modules(N, C, H, W, residual):
 
 @pytest.mark.gpu
 def test_residual_blocks_fused_vs_modules():
-    """the backbone's residual blocks and the extractor's torchvision blocks with K7b on and off (BH_BNACT=aten): same output,
+    """the backbone's residual blocks and the extractor's torchvision blocks with K7b / K8 on and off (BH_BNACT=aten,
+    BH_CONVT_BIAS=aten): same output,
     same parameter gradients, same running statistics -- up to float32 round-off through two convolutions"""
     import copy
     import os
@@ -301,10 +302,11 @@ def test_residual_blocks_fused_vs_modules():
             xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
             ya = run(fused, xa)
             os.environ['BH_BNACT'] = 'aten'
+            os.environ['BH_CONVT_BIAS'] = 'aten'
             try:
                 yb = run(plain, xb)
             finally:
-                del os.environ['BH_BNACT']
+                del os.environ['BH_BNACT'], os.environ['BH_CONVT_BIAS']
             g = torch.randn_like(yb)
             (ya * g).sum().backward()
             (yb * g).sum().backward()
@@ -400,3 +402,78 @@ def test_bn_bn_relu_matches_the_modules(N, C, H, W):
         _close(mine.bias.grad, ref.bias.grad, 5 * TOL, 'bias gradient')
     _close(xa.grad, a64.grad, 5 * TOL, 'gradient of a')
     _close(xb.grad, b64.grad, 5 * TOL, 'gradient of b')
+
+
+# ---- K8: the bias of a transposed convolution ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,C,H,W', [(1, 4, 3, 5), (2, 8, 7, 9), (3, 32, 16, 20), (2, 64, 33, 31), (5, 256, 6, 6), (1, 1024, 4, 3),
+                                     (8, 32, 128, 128), (16, 128, 32, 32)])
+def test_channel_bias_kernels(N, C, H, W):
+    """bh_bias_add / bh_bias_grad through the autograd function: the in-place add is ONE float32 addition per element, so it
+    equals ATen's broadcast add bit for bit; the gradient is a float64 column sum"""
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    g = torch.Generator().manual_seed(N * 1000 + C)
+    y0 = torch.randn(N, C, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(C, generator=g).to(dev).requires_grad_(True)
+    gy = torch.randn(N, C, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    src = y0.clone().requires_grad_(True)
+    y = F._ChannelBias.apply(src * 1.0, bias)            # a non-leaf, like a convolution's output
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y.detach(), y0 + bias.detach().view(1, -1, 1, 1))
+    y.backward(gy)
+    assert torch.equal(src.grad, gy)
+    ref = gy.double().sum((0, 2, 3))
+    _close(bias.grad, ref, 1e-6, 'bias gradient')
+    # an upstream gradient that is not channels-last is laid out first
+    bias.grad = None
+    y = F._ChannelBias.apply(y0.clone(), bias)
+    y.backward(gy.contiguous())
+    _close(bias.grad, ref, 1e-6, 'bias gradient (NCHW upstream gradient)')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,cin,cout,H,W', [(2, 32, 32, 6, 6), (3, 64, 64, 5, 7), (2, 16, 8, 9, 4), (4, 256, 256, 4, 4)])
+def test_conv_transpose_bias_matches_the_module(N, cin, cout, H, W):
+    """F.conv_transpose_bias(m, x) against m(x) evaluated in float64: output, input / weight / bias gradients"""
+    import copy
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    saved = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(cin + H)
+        m = torch.nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2).to(dev).to(memory_format=torch.channels_last)
+        with torch.no_grad():
+            m.bias.normal_()
+        m64 = copy.deepcopy(m).double()
+        x = torch.randn(N, cin, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+        assert F.convt_bias_supported(m, x)
+        xa, xb = x.clone().requires_grad_(True), x.double().requires_grad_(True)
+        ya, yb = F.conv_transpose_bias(m, xa), m64(xb)
+        g = torch.randn_like(ya)
+        (ya * g).sum().backward()
+        (yb * g.double()).sum().backward()
+        _close(ya.detach(), yb.detach(), TOL, 'output')
+        _close(xa.grad, xb.grad, TOL, 'input gradient')
+        _close(m.weight.grad, m64.weight.grad, TOL, 'weight gradient')
+        _close(m.bias.grad, m64.bias.grad, TOL, 'bias gradient')
+        # frozen bias / no_grad: nothing to save, same output
+        with torch.no_grad():
+            _close(F.conv_transpose_bias(m, x), yb.detach(), TOL, 'output under no_grad')
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+
+
+@pytest.mark.gpu
+def test_conv_transpose_bias_refuses_what_it_does_not_cover(monkeypatch):
+    import bihome_b200.functional as F
+    dev = torch.device('cuda', 0)
+    x = torch.randn(2, 8, 4, 4, device=dev).contiguous(memory_format=torch.channels_last)
+    assert F.convt_bias_supported(torch.nn.ConvTranspose2d(8, 8, 2, stride=2).to(dev), x)
+    assert not F.convt_bias_supported(torch.nn.ConvTranspose2d(8, 8, 2, stride=2, bias=False).to(dev), x)
+    assert not F.convt_bias_supported(torch.nn.ConvTranspose2d(8, 6, 2, stride=2).to(dev), x)       # 6 channels: not a power of two
+    assert not F.convt_bias_supported(torch.nn.Conv2d(8, 8, 1).to(dev), x)
+    assert not F.convt_bias_supported(torch.nn.ConvTranspose2d(8, 8, 2, stride=2), x.cpu())
+    monkeypatch.setenv('BH_CONVT_BIAS', 'aten')
+    assert not F.convt_bias_supported(torch.nn.ConvTranspose2d(8, 8, 2, stride=2).to(dev), x)
