@@ -1,8 +1,8 @@
 """Which ATen ops of the training step still move whole tensors around the custom kernels?  (dev tool, not part of the bench)
 
-One eager step of bench.py's workload under torch.profiler with shapes and Python stacks; prints the copy / layout / add /
+One eager step of bench.py's workload under torch.profiler with input shapes; prints the copy / layout / add /
 reduction ops (everything that is neither a convolution nor one of this library's entry points) grouped by input shapes and
-call site, sorted by device time.  usage: python tools/profile_copies.py [B] > gpurun_out/copies.txt"""
+the chain of ops that enclose them (the convolution or autograd node a copy belongs to), sorted by device time.  usage: python tools/profile_copies.py [B] > gpurun_out/copies.txt"""
 import os
 import sys
 
@@ -30,18 +30,29 @@ def main():
     for _ in range(3):
         engine.train_step(model, loader.next_batch(), opt, sched)
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True, with_stack=True) as p:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as p:
         engine.train_step(model, loader.next_batch(), opt, sched)
         torch.cuda.synchronize()
-    rows = []
-    for e in p.key_averages(group_by_input_shape=True, group_by_stack_n=12):
+    # group by (op, input shapes, chain of enclosing ops): the chain names the convolution / autograd node a copy belongs to
+    groups = {}
+    for e in p.events():
+        if e.name not in WATCH:
+            continue
         dev_us = getattr(e, 'self_device_time_total', None)
         if dev_us is None:
             dev_us = getattr(e, 'self_cuda_time_total', 0)
-        if e.key in WATCH and dev_us >= 20:
-            mine = [f for f in e.stack if 'site-packages' not in f and 'profile_copies' not in f][:3]
-            rows.append((dev_us, e.count, e.key, str(e.input_shapes)[:110], ' <- '.join(s.strip()[-90:] for s in mine)))
-    rows.sort(reverse=True)
+        if dev_us <= 0:
+            continue
+        chain, q = [], e.cpu_parent
+        while q is not None and len(chain) < 6:
+            shapes = [s_ for s_ in (q.input_shapes or []) if s_]
+            chain.append(q.name.replace('autograd::engine::evaluate_function: ', 'node ') + (' ' + str(shapes[:3]) if shapes and len(chain) < 5 else ''))
+            q = q.cpu_parent
+        key = (e.name, str(e.input_shapes)[:110], ' <- '.join(chain)[:400])
+        g = groups.setdefault(key, [0.0, 0])
+        g[0] += dev_us
+        g[1] += 1
+    rows = sorted(((us, n) + key for key, (us, n) in groups.items() if us >= 20), reverse=True)
     total = sum(r[0] for r in rows)
     print('# one eager step at B = %d: %d groups of watched ATen ops, %.2f ms of device time' % (B, len(rows), total / 1e3))
     for us, n, key, shapes, site in rows[:60]:
