@@ -122,12 +122,22 @@ class Model(nn.Module):
             bn.running_mean.data.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=m / (1 - m))
         return head(act(bn(y)))
 
+    def _pair(self, a, b):
+        """the two patches stacked along the channels (reference :304,310 `torch.cat`).  When the model is channels-last the
+        [B,2,P,P] tensor is built in that layout right away: handed an NCHW tensor, cuDNN's channels-last convolution
+        re-lays it out in the forward pass and once more for the weight gradient."""
+        w = self.layer1[0].weight
+        if (a.is_cuda and a.dim() == 4 and a.shape[1] == 1 and a.shape == b.shape and a.dtype == b.dtype
+                and w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()):
+            return torch.stack([a[:, 0], b[:, 0]], dim=-1).permute(0, 3, 1, 2)
+        return torch.cat([a, b], dim=1)
+
     def forward(self, data):
         e1, e2 = self.patch_keys
         p1, p2 = data[e1], data[e2]
-        data[self.target_keys[0]] = self._forward(torch.cat([p1, p2], dim=1))
+        data[self.target_keys[0]] = self._forward(self._pair(p1, p2))
         if self.variant == 'doubleline':
-            data[self.target_keys[1]] = self._forward(torch.cat([p2, p1], dim=1))
+            data[self.target_keys[1]] = self._forward(self._pair(p2, p1))
         return data
 
     def predict_homography(self, data):

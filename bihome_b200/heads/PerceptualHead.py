@@ -98,6 +98,12 @@ class AuxiliaryResnet(nn.Module):
                 # explicit channels-last strides make cuDNN pick its NHWC kernels (and bn1/maxpool follow)
                 k_h, k_w = w.shape[-2], w.shape[-1]
                 w = w.as_strided(w.shape, (k_h * k_w, 1, k_w, 1))
+                if x.is_cuda and x.is_contiguous():
+                    # and the same for the one-channel input: ATen's cuDNN backward first lays the upstream gradient out in
+                    # the INPUT's suggested format (NCHW for plain [B,1,H,W] strides) and then back in the weight's
+                    # (channels-last) -- two strided copies of the [B,64,H/2,W/2] gradient per pass, 1.07 ms of the
+                    # B = 256 step (profiles/r05b_copies.txt).  A view, no data moves.
+                    x = x.view(x.shape[0], x.shape[2], x.shape[3], 1).permute(0, 3, 1, 2)
             x = nn.functional.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation)
         else:
             x = r.conv1(x)
