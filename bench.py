@@ -98,8 +98,11 @@ def workload_config(batch, world, pool):
             'l2': 'per-step working set (activations of B=256) >> 126 MB L2: no flush needed'}
 
 
-def cpu_oracle_run(steps, warmup, batch, threads):
-    """the reference's CPU path for the same config: torch backbone on CPU + oracle head (oracle/ref_train.py)"""
+def cpu_oracle_run(steps, warmup, batch, threads, budget_s=None):
+    """the reference's CPU path for the same config: torch backbone on CPU + oracle head (oracle/ref_train.py).
+    Returns (image-pairs/s, seconds per step, image pairs per step).  With a time budget the first (untimed) step is also a
+    probe: when `steps + warmup` steps of `batch` pairs would not fit, the steps become a smaller sample of the same workload
+    (a quarter of the pairs, down to 16) -- the driver runs this arm with the GPU arm's step count."""
     from bihome_b200 import engine
     from bihome_b200.backbones import Rethinking
     from oracle.ref_train import OracleModel
@@ -112,10 +115,13 @@ def cpu_oracle_run(steps, warmup, batch, threads):
     model.backbone.skip_cancelled_bias = False      # the reference's op sequence, literally
     model.train()
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=cfg['SOLVER']['LR'])
-    g = torch.Generator().manual_seed(1)
-    lo = torch.rand(batch, 1, 18, 18, generator=g)
-    p1 = torch.nn.functional.interpolate(lo, size=(128, 128), mode='bicubic', align_corners=True)
-    p2 = torch.roll(p1, shifts=(3, -2), dims=(2, 3)) + 0.05 * torch.randn(batch, 1, 128, 128, generator=g)
+
+    def inputs(n):
+        g = torch.Generator().manual_seed(1)
+        lo = torch.rand(n, 1, 18, 18, generator=g)
+        a = torch.nn.functional.interpolate(lo, size=(128, 128), mode='bicubic', align_corners=True)
+        return a, torch.roll(a, shifts=(3, -2), dims=(2, 3)) + 0.05 * torch.randn(n, 1, 128, 128, generator=g)
+    p1, p2 = inputs(batch)
 
     def step():
         opt.zero_grad()
@@ -123,13 +129,25 @@ def cpu_oracle_run(steps, warmup, batch, threads):
         loss.backward()
         opt.step()
         return float(loss.detach())
-    for _ in range(warmup):
+    done = 0
+    if budget_s is not None:
+        while True:
+            t0 = time.perf_counter()
+            step()
+            probe = time.perf_counter() - t0
+            done = 1
+            if probe * (steps + max(warmup - 1, 0)) <= budget_s or batch <= 16:
+                break
+            batch = max(batch // 4, 16)
+            p1, p2 = inputs(batch)
+            done = 0
+    for _ in range(max(warmup - done, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, batch
 
 
 def run_reference(args):
@@ -138,7 +156,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     # the same B = 256 step as the GPU arm (BatchNorm statistics and the per-step overheads are those of the real workload);
-    # a B = 256 step of the Zeng backbone keeps ~35 GB of activations on the host, so a box with less RAM runs B = 64 steps
+    # a B = 256 step of the Zeng backbone keeps ~35 GB of activations on the host, so a box with less RAM runs B = 64 steps;
+    # a box whose cores would need more than --ref-budget seconds for steps + warmup such steps runs smaller ones
     batch = args.ref_batch
     if batch is None:
         try:
@@ -147,11 +166,12 @@ def run_reference(args):
         except Exception:  # noqa: BLE001
             avail = 0
         batch = args.batch if avail >= 56e9 else 64
-    value, spp = cpu_oracle_run(args.steps, args.warmup, batch, threads)
+    value, spp, used = cpu_oracle_run(args.steps, args.warmup, batch, threads, budget_s=args.ref_budget if args.ref_batch is None else None)
     sample = ('%d steps of B=%d after %d warm-up (%.1f s/step): torch CPU backbone (plain ATen modules, NCHW) + the oracle\'s '
-              'kornia-0.5.0 head and its autograd, Adam, %d host threads' % (args.steps, batch, args.warmup, spp, threads))
-    if batch != args.batch:
-        sample += '; bounded sample: B=%d steps of the B=%d workload (host RAM)' % (batch, args.batch)
+              'kornia-0.5.0 head and its autograd, Adam, %d host threads' % (args.steps, used, args.warmup, spp, threads))
+    if used != args.batch:
+        sample += '; bounded sample: B=%d steps of the B=%d workload (%s)' % (used, args.batch, 'host RAM' if used == batch else
+                                                                              'time budget of %d s for the run' % args.ref_budget)
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': spp * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
@@ -357,7 +377,7 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, spp = cpu_oracle_run(steps=2, warmup=1, batch=64, threads=threads)
+        v, spp, _ = cpu_oracle_run(steps=2, warmup=1, batch=64, threads=threads)
         cpu_baseline = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                         'sample': '2 steps of B=64 after 1 warm-up (%.1f s/step; bounded sample of the B=256 workload, which '
                                   '`--impl reference` runs in full): torch CPU backbone + oracle kornia-0.5.0 head' % spp}
@@ -398,6 +418,8 @@ def main():
     ap.add_argument('--field-head', default=None, choices=['aten', 'fused'],
                     help="Zeng backbone's last stage: 'aten' = the four torch modules (default), 'fused' = K6 (csrc/fieldhead.cu); "
                          "unset = BH_FIELD_HEAD, else the device's self-test decides (bihome_b200/autotune.py)")
+    ap.add_argument('--ref-budget', type=int, default=600, help='--impl reference: seconds the whole run (steps + warmup) may take before the steps '
+                    'become smaller samples of the workload')
     ap.add_argument('--ref-batch', type=int, default=None, help='--impl reference: image pairs per CPU step (default: --batch, 64 on a box with < 56 GB of free RAM)')
     ap.add_argument('--no-cudnn-benchmark', dest='cudnn_benchmark', action='store_false', default=True,
                     help='leave torch.backends.cudnn.benchmark off (default on, as train.py: the shapes of a training run are '

@@ -308,3 +308,24 @@ def test_bench_reference_arm_line_follows_the_contract():
     r = subprocess.run([sys.executable, bench, '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'], capture_output=True,
                        text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_layout_helpers_keep_the_cpu_path_and_the_values():
+    """the channels-last shortcuts of the GPU step (K8's bias split, the backbone's input pair, the extractor's one-channel
+    input view) are off for CPU tensors, and the input pair holds the values of the reference's torch.cat either way"""
+    import bihome_b200.functional as F
+    from bihome_b200 import engine
+    m = torch.nn.ConvTranspose2d(8, 8, 2, stride=2)
+    assert not F.convt_bias_supported(m, torch.zeros(1, 8, 4, 4))                   # CPU tensor: the module runs as it is
+    assert not F.convt_bias_supported(torch.nn.Conv2d(8, 8, 1), torch.zeros(1, 8, 4, 4))
+    backbone = engine.build_model(cfg('pds-coco/zeng-bihome-lr-1e-3.yaml'), pretrained=False)[0]
+    a, b = torch.rand(3, 1, 16, 16), torch.rand(3, 1, 16, 16)
+    for mod in (backbone, backbone.to(memory_format=torch.channels_last)):
+        x = mod._pair(a, b)
+        assert torch.equal(x, torch.cat([a, b], dim=1)) and x.is_contiguous()      # CPU: the reference's NCHW cat
+    # the construction the CUDA branch uses: the same values, channels-last strides, one kernel
+    y = torch.stack([a[:, 0], b[:, 0]], dim=-1).permute(0, 3, 1, 2)
+    assert torch.equal(y, torch.cat([a, b], dim=1)) and y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()
+    # and the one-channel view of AuxiliaryResnet.forward: same values, strides that read as channels-last
+    v = a.view(3, 16, 16, 1).permute(0, 3, 1, 2)
+    assert torch.equal(v, a) and v.stride() == (256, 1, 16, 1)
