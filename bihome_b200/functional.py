@@ -999,6 +999,6 @@ def conv_transpose_bias(m, x):
     the bias is added in place by K8 and its gradient reduced by K8.  Same output and gradients as the module; call only
     when convt_bias_supported() said yes.  An output that cuDNN did not leave channels-last takes ATen's broadcast add."""
     y = torch.nn.functional.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
-    if not _is_nhwc(y):
-        return y + m.bias.view(1, -1, 1, 1)
+    if not _is_nhwc(y) or y.dtype != torch.float32:          # NCHW output, or a reduced-precision one under autocast
+        return y + m.bias.view(1, -1, 1, 1).to(y.dtype)
     return _ChannelBias.apply(y, m.bias)
